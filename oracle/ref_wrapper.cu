@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// Builds the reference's own CPU IVF-Flat path, UNMODIFIED, from the sources
+// where they lie under $(REF)/engine (ivf_flat_index.cpp + kernels.cu are
+// #included below; nothing is copied into this repository) and exposes it
+// through a small extern "C" surface so tests/ and bench.py's cpu_baseline /
+// --impl reference legs can drive it with ctypes.  Output goes to oracle/_ref/.
+//
+// With Config::use_gpu=false the reference executes no CUDA call
+// (ivf_flat_index.cpp:111-115,153-157,236-249), so this runs without a GPU.
+// The TransferManager of the reference does not compile (duplicate member
+// definitions, transfer_manager.cpp:186-200 vs 515-630); the seven methods the
+// index object references are stubbed here and are never reached on the CPU
+// path.
+#include <cfloat>
+#include <cstdint>
+#include <algorithm>
+#include <functional>
+#include <thread>
+#include <string>
+#include <mutex>
+#include <vector>
+#include <chrono>
+#include <iostream>
+#include <sstream>
+
+#define private public
+#include "ivf_flat_index.h"
+#undef private
+#include "ivf_flat_index.cpp"
+#include "kernels.cu"
+
+namespace vdb {
+void* TransferManager::allocate_device(size_t) { return nullptr; }
+void TransferManager::free_device(void*) {}
+cudaStream_t TransferManager::get_stream() { return nullptr; }
+void TransferManager::return_stream(cudaStream_t) {}
+void TransferManager::enqueue_transfer(const Transfer&) {}
+void TransferManager::synchronize() {}
+void TransferManager::synchronize_stream(cudaStream_t) {}
+}  // namespace vdb
+
+namespace {
+struct Quiet {  // the reference prints progress to std::cout; keep test logs clean
+    std::streambuf* old;
+    std::ostringstream sink;
+    Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    ~Quiet() { std::cout.rdbuf(old); }
+};
+vdb::kernels::Metric to_metric(int m) {
+    return m == 0 ? vdb::kernels::Metric::L2
+         : m == 1 ? vdb::kernels::Metric::InnerProduct
+                  : vdb::kernels::Metric::Cosine;
+}
+}  // namespace
+
+extern "C" {
+
+void* ref_create(uint32_t dim, uint32_t nlist, int metric) {
+    Quiet q;
+    vdb::IVFFlatIndex::Config cfg{};
+    cfg.dimension = dim;
+    cfg.nlist = nlist;
+    cfg.metric = to_metric(metric);
+    cfg.use_gpu = false;
+    try {
+        return new vdb::IVFFlatIndex(cfg, nullptr);
+    } catch (...) {
+        return nullptr;
+    }
+}
+
+void ref_destroy(void* h) { delete static_cast<vdb::IVFFlatIndex*>(h); }
+
+void ref_train(void* h, const float* x, uint64_t n) {
+    Quiet q;
+    static_cast<vdb::IVFFlatIndex*>(h)->train(x, n);
+}
+
+void ref_add(void* h, const float* x, const uint64_t* ids, uint64_t n) {
+    Quiet q;
+    static_cast<vdb::IVFFlatIndex*>(h)->add(x, ids, n);
+}
+
+// One query per search() call: the reference keeps its per-probe buffers
+// outside the query loop and does not clear them when a probed list is empty
+// (ivf_flat_index.cpp:210-211,225), so a batched call can leak query q-1's
+// candidates into query q.  Per-query calls are bit-identical wherever that
+// bug does not fire.  nprobe is clamped to nlist because
+// the reference indexes past probe_lists otherwise (:221-222 vs :331).
+void ref_search(void* h, const float* q, uint32_t nq, uint32_t nprobe, uint32_t k,
+                float* D, uint64_t* I, int nthreads) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    const uint32_t dim = idx->config_.dimension;
+    vdb::IVFFlatIndex::SearchParams p;
+    p.nprobe = std::min(nprobe, idx->config_.nlist);
+    p.k = k;
+    if (nthreads <= 1) {
+        for (uint32_t i = 0; i < nq; ++i)
+            idx->search(q + (size_t)i * dim, 1, p, D + (size_t)i * k, I + (size_t)i * k);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=] {
+            for (uint32_t i = t; i < nq; i += nthreads)
+                idx->search(q + (size_t)i * dim, 1, p, D + (size_t)i * k, I + (size_t)i * k);
+        });
+    for (auto& t : th) t.join();
+}
+
+// The reference's batched call exactly as a caller would issue it (stale
+// buffers included); used to document the quirk, not for parity.
+void ref_search_batched(void* h, const float* q, uint32_t nq, uint32_t nprobe, uint32_t k,
+                        float* D, uint64_t* I) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    vdb::IVFFlatIndex::SearchParams p;
+    p.nprobe = std::min(nprobe, idx->config_.nlist);
+    p.k = k;
+    idx->search(q, nq, p, D, I);
+}
+
+void ref_assign(void* h, const float* x, uint64_t n, uint32_t* out) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    std::vector<uint32_t> a;
+    idx->assign_to_lists(x, n, a);
+    std::copy(a.begin(), a.end(), out);
+}
+
+void ref_select_nprobe(void* h, const float* q, uint32_t nprobe, uint32_t* out) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    auto v = idx->select_nprobe_lists(q, nprobe);
+    std::copy(v.begin(), v.end(), out);
+}
+
+void ref_get_centroids(void* h, float* out) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    std::copy(idx->centroids_.begin(), idx->centroids_.end(), out);
+}
+
+void ref_set_centroids(void* h, const float* in) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    std::copy(in, in + idx->centroids_.size(), idx->centroids_.begin());
+}
+
+void ref_list_sizes(void* h, uint64_t* out) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    for (size_t i = 0; i < idx->lists_.size(); ++i) out[i] = idx->lists_[i]->count;
+}
+
+void ref_list_ids(void* h, uint32_t list, uint64_t* out) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    auto& l = idx->lists_[list];
+    std::copy(l->ids.begin(), l->ids.end(), out);
+}
+
+uint64_t ref_total_vectors(void* h) {
+    return static_cast<vdb::IVFFlatIndex*>(h)->get_total_vectors();
+}
+
+}  // extern "C"
