@@ -1,0 +1,854 @@
+// vdb_index: the device-resident IVF-Flat index behind the C ABI.
+//
+// Host orchestration of IVFFlatIndex::{train, add, search}
+// (ivf_flat_index.cpp:49-256) with every arithmetic step on the GPU.
+// HBM layout: centroids [nlist][ld] fp32; every inverted list is a chain of
+// fixed-size pages ([page_rows][ld] fp32 rows + [page_rows] u64 ids) carved
+// from geometrically growing slabs (64 MiB .. 2 GiB), so add() appends without ever moving resident rows and a
+// page is the unit of scan work.  There is no host copy of the vectors and no
+// CPU fallback.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "kmeans.cuh"
+#include "scan.cuh"
+
+namespace vdb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+constexpr uint64_t SLAB_BYTES = 64ull << 20;
+constexpr uint32_t CENTROID_PAGE_ROWS = 64;
+constexpr uint64_t ADD_CHUNK_BYTES = 1ull << 30;
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int32_t reserve(size_t n) {
+        if (n <= cap) return VDB_OK;
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 16;
+        VDB_CUDA_TRY(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return VDB_OK;
+    }
+    void release() {
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+}  // namespace
+}  // namespace vdb
+
+using namespace vdb;
+
+struct vdb_index {
+    vdb_config cfg{};
+    uint32_t dim = 0, ld = 0, nlist = 0, page_rows = 0;
+    uint64_t page_bytes = 0, ids_off = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool trained = false;
+    std::mutex mu;
+
+    DevBuf<float> centroids;  // [nlist][ld]
+    // flat paged view of the centroid table (the coarse step scans it like a list)
+    DevBuf<uint32_t> c_rows, c_page_off;
+    DevBuf<uint64_t> c_page_vec, c_page_ids;
+    uint32_t c_npages = 0;
+
+    // inverted lists: host mirror of the page chains + device tables
+    std::vector<uint32_t> h_rows;
+    std::vector<std::vector<uint32_t>> h_pages;
+    std::vector<void*> slabs;
+    std::vector<uint64_t> page_addr;
+    uint32_t pages_per_slab = 0, pages_used = 0;
+    DevBuf<uint32_t> d_rows, d_page_off;
+    DevBuf<uint64_t> d_page_vec, d_page_ids;
+    std::vector<uint32_t> npages_desc;  // page counts, descending (search slot bound)
+
+    uint64_t total_vectors = 0, local_vectors = 0, slab_bytes_total = 0;
+
+    ScanWorkspace ws_coarse, ws_scan;
+    DevBuf<float> q_buf, coarse_d, out_d;
+    DevBuf<uint64_t> coarse_i, out_i;
+    DevBuf<uint32_t> probes, zero_probes, assign_buf, hist_buf, fill_buf;
+    DevBuf<float> stage_buf;
+    DevBuf<uint64_t> ids_stage;
+    ScanLaunchInfo last_scan_info{};
+    bool have_search = false;
+    // profiling: event quintuples (coarse start, then the four scan_search marks) per search
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    uint32_t prof_used = 0;
+
+    uint64_t hbm_bytes() const {
+        return slab_bytes_total + centroids.bytes() + c_rows.bytes() + c_page_off.bytes() + c_page_vec.bytes() +
+               c_page_ids.bytes() + d_rows.bytes() + d_page_off.bytes() + d_page_vec.bytes() + d_page_ids.bytes() +
+               ws_coarse.bytes + ws_scan.bytes + q_buf.bytes() + coarse_d.bytes() + out_d.bytes() +
+               coarse_i.bytes() + out_i.bytes() + probes.bytes() + zero_probes.bytes() + assign_buf.bytes() +
+               hist_buf.bytes() + fill_buf.bytes() + stage_buf.bytes() + ids_stage.bytes();
+    }
+};
+
+namespace {
+
+ListTable centroid_table(vdb_index* ix) {
+    ListTable lt;
+    lt.rows = ix->c_rows.p;
+    lt.page_off = ix->c_page_off.p;
+    lt.page_vec = ix->c_page_vec.p;
+    lt.page_ids = ix->c_page_ids.p;
+    lt.ids_flat = nullptr;
+    lt.nlist = 1;
+    lt.page_rows = CENTROID_PAGE_ROWS;
+    lt.ld = ix->ld;
+    return lt;
+}
+
+ListTable list_table(vdb_index* ix) {
+    ListTable lt;
+    lt.rows = ix->d_rows.p;
+    lt.page_off = ix->d_page_off.p;
+    lt.page_vec = ix->d_page_vec.p;
+    lt.page_ids = ix->d_page_ids.p;
+    lt.ids_flat = nullptr;
+    lt.nlist = ix->nlist;
+    lt.page_rows = ix->page_rows;
+    lt.ld = ix->ld;
+    return lt;
+}
+
+// Describe a flat [n][ld] device array as a one-list paged view.
+int32_t build_flat_view(const float* base, uint64_t n, uint32_t ld, uint32_t page_rows, DevBuf<uint32_t>& rows,
+                        DevBuf<uint32_t>& page_off, DevBuf<uint64_t>& page_vec, DevBuf<uint64_t>& page_ids,
+                        uint32_t* npages_out, cudaStream_t stream) {
+    const uint32_t npages = (uint32_t)((n + page_rows - 1) / page_rows);
+    std::vector<uint64_t> pv(std::max(npages, 1u)), pi(std::max(npages, 1u), 0);
+    for (uint32_t i = 0; i < npages; ++i) pv[i] = (uint64_t)(uintptr_t)(base + (size_t)i * page_rows * ld);
+    uint32_t hrows = (uint32_t)n, hoff[2] = {0, npages};
+    VDB_TRY(rows.reserve(1));
+    VDB_TRY(page_off.reserve(2));
+    VDB_TRY(page_vec.reserve(pv.size()));
+    VDB_TRY(page_ids.reserve(pi.size()));
+    VDB_CUDA_TRY(cudaMemcpyAsync(rows.p, &hrows, 4, cudaMemcpyHostToDevice, stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(page_off.p, hoff, 8, cudaMemcpyHostToDevice, stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(page_vec.p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice, stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(page_ids.p, pi.data(), pi.size() * 8, cudaMemcpyHostToDevice, stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors die here
+    *npages_out = npages;
+    return VDB_OK;
+}
+
+int32_t refresh_centroid_view(vdb_index* ix) {
+    return build_flat_view(ix->centroids.p, ix->nlist, ix->ld, CENTROID_PAGE_ROWS, ix->c_rows, ix->c_page_off,
+                           ix->c_page_vec, ix->c_page_ids, &ix->c_npages, ix->stream);
+}
+
+int32_t alloc_page(vdb_index* ix, uint32_t* page) {
+    if (ix->pages_used == ix->page_addr.size()) {
+        // slabs grow geometrically: 64 MiB first, doubling the resident total, capped at 2 GiB
+        const uint64_t want = std::min<uint64_t>(2ull << 30, std::max<uint64_t>(SLAB_BYTES, ix->slab_bytes_total));
+        const uint32_t slab_pages = (uint32_t)std::max<uint64_t>(1, want / ix->page_bytes);
+        const uint64_t slab = (uint64_t)slab_pages * ix->page_bytes;
+        if (ix->cfg.max_gpu_memory && ix->hbm_bytes() + slab > ix->cfg.max_gpu_memory) {
+            set_last_error("max_gpu_memory exceeded while growing the inverted lists");
+            return VDB_OUT_OF_MEMORY;
+        }
+        void* p = nullptr;
+        VDB_CUDA_TRY(cudaMalloc(&p, slab));
+        ix->slabs.push_back(p);
+        ix->slab_bytes_total += slab;
+        for (uint32_t i = 0; i < slab_pages; ++i)
+            ix->page_addr.push_back((uint64_t)(uintptr_t)p + (uint64_t)i * ix->page_bytes);
+    }
+    *page = ix->pages_used++;
+    return VDB_OK;
+}
+
+int32_t upload_list_tables(vdb_index* ix) {
+    const uint32_t nlist = ix->nlist;
+    std::vector<uint32_t> off(nlist + 1, 0);
+    for (uint32_t l = 0; l < nlist; ++l) off[l + 1] = off[l] + (uint32_t)ix->h_pages[l].size();
+    const uint32_t npages = off[nlist];
+    std::vector<uint64_t> pv(std::max(npages, 1u), 0), pi(std::max(npages, 1u), 0);
+    for (uint32_t l = 0; l < nlist; ++l)
+        for (size_t j = 0; j < ix->h_pages[l].size(); ++j) {
+            const uint64_t a = ix->page_addr[ix->h_pages[l][j]];
+            pv[off[l] + j] = a;
+            pi[off[l] + j] = a + ix->ids_off;
+        }
+    VDB_TRY(ix->d_rows.reserve(nlist));
+    VDB_TRY(ix->d_page_off.reserve(nlist + 1));
+    VDB_TRY(ix->d_page_vec.reserve(pv.size()));
+    VDB_TRY(ix->d_page_ids.reserve(pi.size()));
+    VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), nlist * 4, cudaMemcpyHostToDevice, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_page_off.p, off.data(), (nlist + 1) * 4, cudaMemcpyHostToDevice, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_page_vec.p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_page_ids.p, pi.data(), pi.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->npages_desc.resize(nlist);
+    for (uint32_t l = 0; l < nlist; ++l) ix->npages_desc[l] = (uint32_t)ix->h_pages[l].size();
+    std::sort(ix->npages_desc.begin(), ix->npages_desc.end(), std::greater<uint32_t>());
+    return VDB_OK;
+}
+
+// rows [n][dim] at `src` (host or device) -> device [n][ld], zero padded; returns the device pointer
+// (src itself when it already is a device array with dim == ld)
+int32_t stage_rows(vdb_index* ix, const float* src, uint64_t n, DevBuf<float>& buf, const float** out,
+                   cudaStream_t stream) {
+    const bool dev = is_device_ptr(src);
+    if (dev && ix->dim == ix->ld && !((uintptr_t)src & 15)) {
+        *out = src;
+        return VDB_OK;
+    }
+    VDB_TRY(buf.reserve((size_t)n * ix->ld));
+    if (dev) {
+        VDB_TRY(launch_pad_rows(src, ix->dim, ix->dim, buf.p, ix->ld, n, stream));
+    } else if (ix->dim == ix->ld) {
+        VDB_CUDA_TRY(cudaMemcpyAsync(buf.p, src, (size_t)n * ix->ld * 4, cudaMemcpyHostToDevice, stream));
+    } else {
+        VDB_CUDA_TRY(cudaMemsetAsync(buf.p, 0, (size_t)n * ix->ld * 4, stream));
+        VDB_CUDA_TRY(cudaMemcpy2DAsync(buf.p, (size_t)ix->ld * 4, src, (size_t)ix->dim * 4, (size_t)ix->dim * 4, n,
+                                       cudaMemcpyHostToDevice, stream));
+    }
+    *out = buf.p;
+    return VDB_OK;
+}
+
+uint64_t slot_bound(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t ppi) {
+    uint64_t s = 0;
+    for (uint32_t i = 0; i < np && i < ix->npages_desc.size(); ++i) s += (ix->npages_desc[i] + ppi - 1) / ppi;
+    return s * nq;
+}
+
+// coarse: top-np centroids of every query = select_nprobe_lists (ivf_flat_index.cpp:298-336)
+int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t np, cudaStream_t stream) {
+    VDB_TRY(ix->zero_probes.reserve(nq));
+    VDB_CUDA_TRY(cudaMemsetAsync(ix->zero_probes.p, 0, (size_t)nq * 4, stream));
+    VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
+    VDB_TRY(ix->coarse_i.reserve((size_t)nq * np));
+    VDB_TRY(ix->probes.reserve((size_t)nq * np));
+    // keep the partial-result buffer below ~64 MiB by widening the page range per item
+    uint32_t ppi = 1;
+    while ((uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi) * np * 12 > (64ull << 20)) ppi *= 2;
+    const uint64_t slots = (uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi);
+    return scan_search(centroid_table(ix), q_dev, nq, ix->zero_probes.p, 1, np, ix->cfg.metric, ppi, slots,
+                       ix->ws_coarse, ix->coarse_d.p, ix->coarse_i.p, ix->probes.p, stream);
+}
+
+int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t nq, uint32_t nprobe, uint32_t k,
+                      float* out_d, uint64_t* out_i, cudaStream_t stream) {
+    const uint32_t np = std::min(nprobe, ix->nlist);  // the reference reads past probe_lists instead (:221-222)
+    cudaEvent_t* ev = nullptr;
+    if (ix->profiling && (ix->prof_used + 1) * 5 <= ix->prof_events.size()) {
+        ev = ix->prof_events.data() + (size_t)ix->prof_used * 5;
+        ++ix->prof_used;
+        cudaEventRecord(ev[0], stream);
+        ++ev;
+    }
+    VDB_TRY(coarse_select(ix, q_dev, nq, np, stream));
+    uint32_t ppi = 1;
+    while (slot_bound(ix, nq, np, ppi) * k * 12 > (1ull << 30)) ppi *= 2;
+    const uint64_t slots = slot_bound(ix, nq, np, ppi);
+    VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,
+                        out_d, out_i, nullptr, stream, &ix->last_scan_info, ev));
+    ix->have_search = true;
+    return VDB_OK;
+}
+
+int32_t check_index(vdb_index* ix) {
+    if (!ix) {
+        set_last_error("null index handle");
+        return VDB_INVALID_ARGUMENT;
+    }
+    return VDB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vdb_last_error_string(void) { return g_last_error.c_str(); }
+
+const char* vdb_status_string(int32_t s) {
+    switch (s) {
+        case VDB_OK: return "OK";
+        case VDB_INVALID_ARGUMENT: return "INVALID_ARGUMENT";
+        case VDB_OUT_OF_MEMORY: return "OUT_OF_MEMORY";
+        case VDB_CUDA_ERROR: return "CUDA_ERROR";
+        case VDB_NCCL_ERROR: return "NCCL_ERROR";
+        case VDB_NOT_TRAINED: return "NOT_TRAINED";
+        default: return "INTERNAL";
+    }
+}
+
+int32_t vdb_version(void) { return 100; }
+
+void vdb_config_default(vdb_config* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->metric = VDB_METRIC_L2;
+    cfg->max_gpu_memory = 0;
+    cfg->train_mode = VDB_TRAIN_AUTO;
+    cfg->coarse_mode = VDB_COARSE_AUTO;
+    cfg->shard_count = 1;
+}
+
+int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
+    VDB_REQUIRE(cfg && out, "null config or output handle");
+    // ctor contract: dimension and nlist must be > 0 (ivf_flat_index.cpp:17-19)
+    VDB_REQUIRE(cfg->dimension > 0 && cfg->nlist > 0, "Invalid configuration: dimension and nlist must be > 0");
+    VDB_REQUIRE(cfg->dimension <= 2048, "dimension must be <= 2048 (kernels.cuh MAX_DIM)");
+    VDB_REQUIRE(cfg->metric == VDB_METRIC_L2 || cfg->metric == VDB_METRIC_IP,
+                "metric must be L2 or InnerProduct (the reference CPU path computes 0 for Cosine)");
+    VDB_REQUIRE(cfg->shard_count >= 1 && cfg->shard_rank < cfg->shard_count, "bad shard rank/count");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device: this library has no CPU path");
+        return VDB_CUDA_ERROR;
+    }
+    VDB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device ordinal out of range");
+    std::unique_ptr<vdb_index> ix(new vdb_index());
+    ix->cfg = *cfg;
+    ix->dim = cfg->dimension;
+    ix->ld = round_up(cfg->dimension, 4);
+    ix->nlist = cfg->nlist;
+    ix->device = cfg->device;
+    uint32_t pr = cfg->page_rows;
+    if (pr == 0) {
+        const uint64_t target = ix->ld >= 256 ? (768ull << 10) : (256ull << 10);
+        pr = (uint32_t)std::max<uint64_t>(16, target / (ix->ld * 4ull) / 16 * 16);
+    }
+    VDB_REQUIRE(pr % 16 == 0 && pr <= 65536, "page_rows must be a multiple of 16, <= 65536");
+    ix->page_rows = pr;
+    ix->ids_off = (uint64_t)pr * ix->ld * 4;
+    ix->page_bytes = (ix->ids_off + (uint64_t)pr * 8 + 255) / 256 * 256;
+    ix->pages_per_slab = (uint32_t)std::max<uint64_t>(1, SLAB_BYTES / ix->page_bytes);
+    ix->h_rows.assign(ix->nlist, 0);
+    ix->h_pages.resize(ix->nlist);
+    DeviceGuard g(ix->device);
+    VDB_CUDA_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    VDB_TRY(ix->centroids.reserve((size_t)ix->nlist * ix->ld));
+    VDB_CUDA_TRY(cudaMemsetAsync(ix->centroids.p, 0, ix->centroids.bytes(), ix->stream));  // centroids_ value-init (:22)
+    VDB_TRY(refresh_centroid_view(ix.get()));
+    VDB_TRY(upload_list_tables(ix.get()));
+    *out = ix.release();
+    return VDB_OK;
+}
+
+int32_t vdb_index_destroy(vdb_index* ix) {
+    if (!ix) return VDB_OK;
+    {
+        DeviceGuard g(ix->device);
+        cudaDeviceSynchronize();
+        for (void* s : ix->slabs) cudaFree(s);
+        ix->centroids.release(); ix->c_rows.release(); ix->c_page_off.release(); ix->c_page_vec.release();
+        ix->c_page_ids.release(); ix->d_rows.release(); ix->d_page_off.release(); ix->d_page_vec.release();
+        ix->d_page_ids.release(); ix->q_buf.release(); ix->coarse_d.release(); ix->out_d.release();
+        ix->coarse_i.release(); ix->out_i.release(); ix->probes.release(); ix->zero_probes.release();
+        ix->assign_buf.release(); ix->hist_buf.release(); ix->fill_buf.release(); ix->stage_buf.release();
+        ix->ids_stage.release();
+        ix->ws_coarse.release();
+        ix->ws_scan.release();
+        for (auto e : ix->prof_events) cudaEventDestroy(e);
+        if (ix->stream) cudaStreamDestroy(ix->stream);
+    }
+    delete ix;
+    return VDB_OK;
+}
+
+int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(vectors && n >= 1, "train: no vectors");
+    VDB_REQUIRE(n < 0xffffffffull, "train: at most 2^32-2 training vectors");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    const float* x = nullptr;
+    DevBuf<float> train_buf;
+    int32_t st = stage_rows(ix, vectors, n, train_buf, &x, ix->stream);
+    KMeansScratch sc;
+    if (st == VDB_OK) st = sc.reserve((uint32_t)n, ix->nlist, ix->ld);
+    const uint32_t ldx = ix->ld;
+    // k-means++ seeding, always L2 (ivf_flat_index.cpp:63-104)
+    if (st == VDB_OK)
+        st = kmeanspp_seed_exact(x, (uint32_t)n, ldx, ix->dim, ix->ld, ix->nlist, ix->centroids.p, sc, ix->stream);
+    // exactly 10 Lloyd iterations; assignment honours the index metric (:109-142, :275-285)
+    for (int iter = 0; iter < 10 && st == VDB_OK; ++iter) {
+        st = kmeans_assign_exact(x, n, ldx, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric, sc.assign,
+                                 nullptr, ix->stream);
+        if (st == VDB_OK)
+            st = kmeans_update_exact(x, (uint32_t)n, ldx, sc.assign, ix->nlist, ix->ld, ix->centroids.p, sc,
+                                     ix->stream);
+    }
+    if (st == VDB_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) {
+        set_last_error(std::string("train: ") + cudaGetErrorString(cudaGetLastError()));
+        st = VDB_CUDA_ERROR;
+    }
+    sc.release();
+    train_buf.release();
+    if (st == VDB_OK) ix->trained = true;
+    return st;
+}
+
+int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
+    VDB_TRY(check_index(ix));
+    if (n == 0) return VDB_OK;
+    VDB_REQUIRE(vectors, "add: null vectors");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    const uint64_t chunk_rows = std::max<uint64_t>(1024, ADD_CHUNK_BYTES / (ix->ld * 4ull));
+    const bool ids_dev = is_device_ptr(ids);
+    for (uint64_t lo = 0; lo < n; lo += chunk_rows) {
+        const uint64_t m = std::min(chunk_rows, n - lo);
+        const float* x = nullptr;
+        VDB_TRY(stage_rows(ix, vectors + lo * ix->dim, m, ix->stage_buf, &x, ix->stream));
+        const uint64_t* dids = nullptr;
+        if (ids) {
+            if (ids_dev) {
+                dids = ids + lo;
+            } else {
+                VDB_TRY(ix->ids_stage.reserve(m));
+                VDB_CUDA_TRY(cudaMemcpyAsync(ix->ids_stage.p, ids + lo, m * 8, cudaMemcpyHostToDevice, ix->stream));
+                dids = ix->ids_stage.p;
+            }
+        }
+        // assign (ivf_flat_index.cpp:151-157)
+        VDB_TRY(ix->assign_buf.reserve(m));
+        VDB_TRY(kmeans_assign_exact(x, m, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric,
+                                    ix->assign_buf.p, nullptr, ix->stream));
+        // per-list counts -> grow the page chains
+        VDB_TRY(ix->hist_buf.reserve(ix->nlist));
+        VDB_TRY(ix->fill_buf.reserve(ix->nlist));
+        VDB_CUDA_TRY(cudaMemsetAsync(ix->hist_buf.p, 0, ix->nlist * 4, ix->stream));
+        VDB_CUDA_TRY(cudaMemsetAsync(ix->fill_buf.p, 0, ix->nlist * 4, ix->stream));
+        VDB_TRY(launch_hist(ix->assign_buf.p, m, ix->nlist, ix->cfg.shard_rank, ix->cfg.shard_count, ix->hist_buf.p,
+                            ix->stream));
+        std::vector<uint32_t> hist(ix->nlist);
+        VDB_CUDA_TRY(cudaMemcpyAsync(hist.data(), ix->hist_buf.p, ix->nlist * 4, cudaMemcpyDeviceToHost, ix->stream));
+        VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        std::vector<uint32_t> new_rows = ix->h_rows;
+        uint64_t added = 0;
+        for (uint32_t l = 0; l < ix->nlist; ++l) {
+            if (!hist[l]) continue;
+            VDB_REQUIRE((uint64_t)new_rows[l] + hist[l] < 0xffffffffull, "add: a list would exceed 2^32 rows");
+            new_rows[l] += hist[l];
+            added += hist[l];
+            const uint32_t need = (new_rows[l] + ix->page_rows - 1) / ix->page_rows;
+            while (ix->h_pages[l].size() < need) {
+                uint32_t pg;
+                VDB_TRY(alloc_page(ix, &pg));
+                ix->h_pages[l].push_back(pg);
+            }
+        }
+        // device tables: page chains now, old row counts as the append base
+        VDB_TRY(upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
+        VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, ix->assign_buf.p, ix->d_rows.p,
+                                    ix->fill_buf.p, ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p,
+                                    ix->page_rows, ix->ld, ix->cfg.shard_rank, ix->cfg.shard_count, ix->stream));
+        ix->h_rows = new_rows;
+        VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), ix->nlist * 4, cudaMemcpyHostToDevice,
+                                     ix->stream));
+        VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        ix->local_vectors += added;
+    }
+    ix->total_vectors += n;  // total_vectors_ += n_vectors (:200)
+    return VDB_OK;
+}
+
+int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe, uint32_t k,
+                               float* distances_dev, uint64_t* indices_dev, void* stream) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(queries_dev && distances_dev && indices_dev, "search: null buffer");
+    VDB_REQUIRE(nq >= 1 && k >= 1 && nprobe >= 1, "search: nq, k and nprobe must be >= 1");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* q = queries_dev;
+    if (ix->dim != ix->ld || ((uintptr_t)queries_dev & 15)) {
+        VDB_TRY(ix->q_buf.reserve((size_t)nq * ix->ld));
+        VDB_TRY(launch_pad_rows(queries_dev, ix->dim, ix->dim, ix->q_buf.p, ix->ld, nq, s));
+        q = ix->q_buf.p;
+    }
+    return search_device(ix, q, nq, nprobe, k, distances_dev, indices_dev, s);
+}
+
+int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
+                         float* distances, uint64_t* indices) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(queries && distances && indices, "search: null buffer");
+    VDB_REQUIRE(nq >= 1 && k >= 1 && nprobe >= 1, "search: nq, k and nprobe must be >= 1");
+    VDB_REQUIRE(k <= (uint32_t)scan_max_k(), "search: k must be <= 2048");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    const float* q = nullptr;
+    VDB_TRY(stage_rows(ix, queries, nq, ix->q_buf, &q, ix->stream));
+    const bool out_dev = is_device_ptr(distances);
+    VDB_REQUIRE(out_dev == is_device_ptr(indices), "search: distances and indices must live on the same side");
+    float* od = distances;
+    uint64_t* oi = indices;
+    if (!out_dev) {
+        VDB_TRY(ix->out_d.reserve((size_t)nq * k));
+        VDB_TRY(ix->out_i.reserve((size_t)nq * k));
+        od = ix->out_d.p;
+        oi = ix->out_i.p;
+    }
+    VDB_TRY(search_device(ix, q, nq, nprobe, k, od, oi, ix->stream));
+    if (!out_dev) {
+        VDB_CUDA_TRY(cudaMemcpyAsync(distances, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+        VDB_CUDA_TRY(cudaMemcpyAsync(indices, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
+    }
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t* lists) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(queries && lists && nq >= 1 && nprobe >= 1, "select_nprobe: bad arguments");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    const uint32_t np = std::min(nprobe, ix->nlist);
+    const float* q = nullptr;
+    VDB_TRY(stage_rows(ix, queries, nq, ix->q_buf, &q, ix->stream));
+    VDB_TRY(coarse_select(ix, q, nq, np, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(lists, ix->probes.p, (size_t)nq * np * 4,
+                                 is_device_ptr(lists) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                 ix->stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+int32_t vdb_index_assign(vdb_index* ix, const float* vectors, uint64_t n, uint32_t* lists) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(vectors && lists, "assign: null buffer");
+    if (n == 0) return VDB_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    const float* x = nullptr;
+    VDB_TRY(stage_rows(ix, vectors, n, ix->stage_buf, &x, ix->stream));
+    VDB_TRY(ix->assign_buf.reserve(n));
+    VDB_TRY(kmeans_assign_exact(x, n, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric,
+                                ix->assign_buf.p, nullptr, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(lists, ix->assign_buf.p, n * 4,
+                                 is_device_ptr(lists) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                 ix->stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+int32_t vdb_index_get_centroids(vdb_index* ix, float* out) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out, "get_centroids: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    VDB_CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)ix->dim * 4, ix->centroids.p, (size_t)ix->ld * 4, (size_t)ix->dim * 4,
+                                   ix->nlist, cudaMemcpyDefault, ix->stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+int32_t vdb_index_set_centroids(vdb_index* ix, const float* in) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(in, "set_centroids: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    VDB_CUDA_TRY(cudaMemsetAsync(ix->centroids.p, 0, (size_t)ix->nlist * ix->ld * 4, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpy2DAsync(ix->centroids.p, (size_t)ix->ld * 4, in, (size_t)ix->dim * 4, (size_t)ix->dim * 4,
+                                   ix->nlist, cudaMemcpyDefault, ix->stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->trained = true;
+    return VDB_OK;
+}
+
+int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out, "list_sizes: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    for (uint32_t l = 0; l < ix->nlist; ++l) out[l] = ix->h_rows[l];
+    return VDB_OK;
+}
+
+int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out && list < ix->nlist, "list_ids: bad arguments");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    uint32_t left = ix->h_rows[list];
+    for (size_t j = 0; j < ix->h_pages[list].size() && left; ++j) {
+        const uint32_t take = std::min(left, ix->page_rows);
+        const void* src = (const void*)(uintptr_t)(ix->page_addr[ix->h_pages[list][j]] + ix->ids_off);
+        VDB_CUDA_TRY(cudaMemcpyAsync(out + (size_t)j * ix->page_rows, src, (size_t)take * 8, cudaMemcpyDefault,
+                                     ix->stream));
+        left -= take;
+    }
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out, "stats: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    std::memset(out, 0, sizeof(*out));
+    out->total_vectors = ix->total_vectors;
+    out->local_vectors = ix->local_vectors;
+    out->gpu_memory_bytes = ix->hbm_bytes();
+    out->pages = ix->pages_used;
+    out->dimension = ix->dim;
+    out->nlist = ix->nlist;
+    out->row_stride = ix->ld;
+    out->page_rows = ix->page_rows;
+    out->trained = ix->trained ? 1 : 0;
+    return VDB_OK;
+}
+
+int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out, "search stats: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    std::memset(out, 0, sizeof(*out));
+    out->bytes_per_row = 4ull * ix->dim + 8;
+    if (!ix->have_search) return VDB_OK;
+    unsigned long long st[2] = {0, 0};
+    uint32_t tot[2] = {0, 0};
+    VDB_CUDA_TRY(cudaDeviceSynchronize());
+    VDB_CUDA_TRY(cudaMemcpy(st, ix->ws_scan.stats, 16, cudaMemcpyDeviceToHost));
+    VDB_CUDA_TRY(cudaMemcpy(tot, ix->ws_scan.totals, 8, cudaMemcpyDeviceToHost));
+    out->algorithmic_rows = st[0];
+    out->unique_rows = st[1];
+    out->scan_items = tot[0];
+    return VDB_OK;
+}
+
+int32_t vdb_index_set_profiling(vdb_index* ix, int32_t enable) {
+    VDB_TRY(check_index(ix));
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    ix->profiling = enable != 0;
+    ix->prof_used = 0;
+    if (ix->profiling && ix->prof_events.empty()) {
+        ix->prof_events.resize(5 * 4096);
+        for (auto& e : ix->prof_events) VDB_CUDA_TRY(cudaEventCreate(&e));
+    }
+    return VDB_OK;
+}
+
+int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms, uint32_t* searches) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out_ms && searches, "read_profile: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    VDB_CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < 4; ++i) out_ms[i] = 0.f;
+    for (uint32_t sidx = 0; sidx < ix->prof_used; ++sidx) {
+        cudaEvent_t* e = ix->prof_events.data() + (size_t)sidx * 5;
+        for (int i = 0; i < 4; ++i) {
+            float ms = 0.f;
+            VDB_CUDA_TRY(cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+            out_ms[i] += ms;
+        }
+    }
+    *searches = ix->prof_used;
+    ix->prof_used = 0;
+    return VDB_OK;
+}
+
+int32_t vdb_index_warmup(vdb_index* ix, const uint32_t* lists, uint32_t n) {
+    VDB_TRY(check_index(ix));
+    for (uint32_t i = 0; i < n; ++i) VDB_REQUIRE(lists && lists[i] < ix->nlist, "warmup: list id out of range");
+    return VDB_OK;  // every list is HBM-resident from add() on; nothing to load (ivf_flat_index.cpp:387-444)
+}
+
+int32_t vdb_bruteforce_search(const float* database, const float* queries, const uint64_t* ids, uint64_t n,
+                              uint32_t nq, uint32_t dim, uint32_t k, float* distances, uint64_t* indices,
+                              int32_t metric, void* stream) {
+    VDB_REQUIRE(database && queries && distances && indices, "bruteforce: null buffer");
+    VDB_REQUIRE(n >= 1 && n < 0xffffffffull && nq >= 1 && dim >= 1 && dim <= 2048 && k >= 1,
+                "bruteforce: bad shape");
+    VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "bruteforce: metric must be L2 or InnerProduct");
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t ld = round_up(dim, 4);
+    const bool db_dev = is_device_ptr(database), q_dev = is_device_ptr(queries), o_dev = is_device_ptr(distances);
+    VDB_REQUIRE(o_dev == is_device_ptr(indices), "bruteforce: distances and indices must live on the same side");
+    DevBuf<float> dbb, qb, od;
+    DevBuf<uint64_t> oi, idb, pv, pi;
+    DevBuf<uint32_t> rows, poff, zero;
+    ScanWorkspace ws;
+    auto cleanup = [&] {
+        dbb.release(); qb.release(); od.release(); oi.release(); idb.release(); pv.release(); pi.release();
+        rows.release(); poff.release(); zero.release(); ws.release();
+    };
+    auto run = [&]() -> int32_t {
+        const float* db = database;
+        if (!db_dev || dim != ld || ((uintptr_t)database & 15)) {  // bulk TMA needs 16-byte aligned rows
+            VDB_TRY(dbb.reserve((size_t)n * ld));
+            if (db_dev) {
+                VDB_TRY(launch_pad_rows(database, dim, dim, dbb.p, ld, n, s));
+            } else {
+                VDB_CUDA_TRY(cudaMemsetAsync(dbb.p, 0, (size_t)n * ld * 4, s));
+                VDB_CUDA_TRY(cudaMemcpy2DAsync(dbb.p, (size_t)ld * 4, database, (size_t)dim * 4, (size_t)dim * 4, n,
+                                               cudaMemcpyHostToDevice, s));
+            }
+            db = dbb.p;
+        }
+        const float* q = queries;
+        if (!q_dev || dim != ld || ((uintptr_t)queries & 15)) {
+            VDB_TRY(qb.reserve((size_t)nq * ld));
+            if (q_dev) {
+                VDB_TRY(launch_pad_rows(queries, dim, dim, qb.p, ld, nq, s));
+            } else {
+                VDB_CUDA_TRY(cudaMemsetAsync(qb.p, 0, (size_t)nq * ld * 4, s));
+                VDB_CUDA_TRY(cudaMemcpy2DAsync(qb.p, (size_t)ld * 4, queries, (size_t)dim * 4, (size_t)dim * 4, nq,
+                                               cudaMemcpyHostToDevice, s));
+            }
+            q = qb.p;
+        }
+        const uint64_t* dids = ids;
+        if (ids && !is_device_ptr(ids)) {
+            VDB_TRY(idb.reserve(n));
+            VDB_CUDA_TRY(cudaMemcpyAsync(idb.p, ids, n * 8, cudaMemcpyHostToDevice, s));
+            dids = idb.p;
+        }
+        const uint32_t page_rows = 256;
+        uint32_t npages = 0;
+        VDB_TRY(build_flat_view(db, n, ld, page_rows, rows, poff, pv, pi, &npages, s));
+        ListTable lt;
+        lt.rows = rows.p; lt.page_off = poff.p; lt.page_vec = pv.p; lt.page_ids = pi.p;
+        lt.ids_flat = dids; lt.nlist = 1; lt.page_rows = page_rows; lt.ld = ld;
+        VDB_TRY(zero.reserve(nq));
+        VDB_CUDA_TRY(cudaMemsetAsync(zero.p, 0, (size_t)nq * 4, s));
+        // items ~ tiles x ranges: aim at a few per SM, and keep the partial buffer modest
+        const uint64_t tiles = (nq + 15) / 16;
+        uint32_t ppi = (uint32_t)std::max<uint64_t>(1, (uint64_t)npages * tiles / (NUM_SMS_B200 * 6));
+        while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (1ull << 30)) ppi *= 2;
+        const uint64_t slots = (uint64_t)nq * ((npages + ppi - 1) / ppi);
+        float* dd = distances;
+        uint64_t* di = indices;
+        if (!o_dev) {
+            VDB_TRY(od.reserve((size_t)nq * k));
+            VDB_TRY(oi.reserve((size_t)nq * k));
+            dd = od.p;
+            di = oi.p;
+        }
+        VDB_TRY(scan_search(lt, q, nq, zero.p, 1, k, metric, ppi, slots, ws, dd, di, nullptr, s));
+        if (!o_dev) {
+            VDB_CUDA_TRY(cudaMemcpyAsync(distances, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+            VDB_CUDA_TRY(cudaMemcpyAsync(indices, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+        }
+        VDB_CUDA_TRY(cudaStreamSynchronize(s));  // temporaries are freed on return
+        return VDB_OK;
+    };
+    const int32_t st = run();
+    cleanup();
+    return st;
+}
+
+int32_t vdb_kmeans_assign(const float* vectors, const float* centroids, uint32_t* assignments, float* distances,
+                          uint64_t n, uint32_t n_centroids, uint32_t dim, int32_t metric, void* stream) {
+    VDB_REQUIRE(vectors && centroids && assignments, "kmeans_assign: null buffer");
+    VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "kmeans_assign: metric must be L2 or InnerProduct");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vdev = is_device_ptr(vectors), cdev = is_device_ptr(centroids), adev = is_device_ptr(assignments);
+    DevBuf<float> vb, cb, db;
+    DevBuf<uint32_t> ab;
+    auto run = [&]() -> int32_t {
+        const float* v = vectors;
+        const float* c = centroids;
+        if (!vdev) {
+            VDB_TRY(vb.reserve((size_t)n * dim));
+            VDB_CUDA_TRY(cudaMemcpyAsync(vb.p, vectors, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s));
+            v = vb.p;
+        }
+        if (!cdev) {
+            VDB_TRY(cb.reserve((size_t)n_centroids * dim));
+            VDB_CUDA_TRY(cudaMemcpyAsync(cb.p, centroids, (size_t)n_centroids * dim * 4, cudaMemcpyHostToDevice, s));
+            c = cb.p;
+        }
+        uint32_t* a = assignments;
+        float* d = distances;
+        if (!adev) {
+            VDB_TRY(ab.reserve(n));
+            a = ab.p;
+            if (distances) {
+                VDB_TRY(db.reserve(n));
+                d = db.p;
+            }
+        }
+        VDB_TRY(kmeans_assign_exact(v, n, dim, c, n_centroids, dim, dim, metric, a, d, s));
+        if (!adev) {
+            VDB_CUDA_TRY(cudaMemcpyAsync(assignments, a, n * 4, cudaMemcpyDeviceToHost, s));
+            if (distances) VDB_CUDA_TRY(cudaMemcpyAsync(distances, d, n * 4, cudaMemcpyDeviceToHost, s));
+        }
+        if (!vdev || !cdev || !adev) VDB_CUDA_TRY(cudaStreamSynchronize(s));
+        return VDB_OK;
+    };
+    const int32_t st = run();
+    vb.release(); cb.release(); db.release(); ab.release();
+    return st;
+}
+
+int32_t vdb_kmeans_accumulate(const float* vectors_dev, const uint32_t* assignments_dev, uint64_t n,
+                              uint32_t n_centroids, uint32_t dim, float* sums_dev, uint32_t* counts_dev,
+                              void* stream) {
+    VDB_REQUIRE(vectors_dev && assignments_dev && sums_dev && counts_dev, "kmeans_accumulate: null buffer");
+    VDB_REQUIRE(dim % 4 == 0, "kmeans_accumulate: dim must be a multiple of 4 (pad the rows)");
+    VDB_REQUIRE(n < 0xffffffffull, "kmeans_accumulate: too many rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    KMeansScratch sc;
+    int32_t st = sc.reserve((uint32_t)n, n_centroids, dim);
+    if (st == VDB_OK)
+        st = kmeans_cluster_sums(vectors_dev, (uint32_t)n, dim, assignments_dev, n_centroids, dim, sums_dev,
+                                 counts_dev, sc, s);
+    if (st == VDB_OK && cudaStreamSynchronize(s) != cudaSuccess) st = VDB_CUDA_ERROR;
+    sc.release();
+    return st;
+}
+
+int32_t vdb_kmeans_finalize(const float* sums_dev, const uint32_t* counts_dev, float* centroids_dev,
+                            uint32_t n_centroids, uint32_t dim, void* stream) {
+    VDB_REQUIRE(sums_dev && counts_dev && centroids_dev, "kmeans_finalize: null buffer");
+    return kmeans_divide(sums_dev, counts_dev, n_centroids, dim, centroids_dev, (cudaStream_t)stream);
+}
+
+int32_t vdb_merge_topk(const float* dist_parts_dev, const uint64_t* id_parts_dev, uint32_t parts, uint32_t nq,
+                       uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream) {
+    VDB_REQUIRE(dist_parts_dev && id_parts_dev && distances_dev && indices_dev, "merge_topk: null buffer");
+    return merge_parts(dist_parts_dev, id_parts_dev, parts, nq, k, distances_dev, indices_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

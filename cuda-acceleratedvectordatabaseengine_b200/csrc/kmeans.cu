@@ -1,0 +1,595 @@
+// k-means training and assignment kernels for sm_100a.
+//
+// Replaces IVFFlatIndex::train / assign_to_lists (ivf_flat_index.cpp:49-145,
+// 259-295) and kmeans_assign_kernel (kernels.cuh:315-354).
+//
+// The kernels in this file are the ORDER-EXACT family: every fp32 sum is
+// accumulated in the reference's order (ascending dimension for distances,
+// ascending input row for centroid sums) with separate round-to-nearest
+// multiply and add (__fmul_rn/__fadd_rn are never contracted into FMA), so
+// centroids, assignments and list membership are bit-identical to the
+// reference's CPU path, including its seeded k-means++ (std::mt19937(42) and
+// libstdc++'s uniform distributions are restated on the device).
+#include "kmeans.cuh"
+
+namespace vdb {
+namespace {
+
+// ---------------------------------------------------------------- assignment
+
+constexpr int TV = 64, TC = 64, DK = 32;
+
+// 64 vectors x 64 centroids per block step, 4x4 pairs per thread; the d loop
+// runs in ascending order so each pair's sum is the reference's sequential sum.
+__global__ void __launch_bounds__(256) assign_exact_kernel(const float* __restrict__ x, uint64_t n, uint32_t ldx,
+                                                           const float* __restrict__ c, uint32_t nc, uint32_t ldc,
+                                                           uint32_t dim, int metric, uint32_t* __restrict__ assign,
+                                                           float* __restrict__ dist_out) {
+    __shared__ float sv[TV][DK + 1];
+    __shared__ float sc[TC][DK + 1];
+    __shared__ float sbd[TV][17];
+    __shared__ uint32_t sbi[TV][17];
+    const uint32_t tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint64_t v0 = (uint64_t)blockIdx.x * TV;
+
+    float bd[4];
+    uint32_t bi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bd[i] = FLT_MAX;  // min_dist = numeric_limits<float>::max(), best_list = 0 (:266-267)
+        bi[i] = 0;
+    }
+    for (uint32_t c0 = 0; c0 < nc; c0 += TC) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (uint32_t d0 = 0; d0 < dim; d0 += DK) {
+            for (uint32_t e = tid; e < TV * DK; e += 256) {
+                const uint32_t r = e / DK, dd = e % DK;
+                const uint64_t v = v0 + r;
+                sv[r][dd] = (v < n && d0 + dd < dim) ? x[v * ldx + d0 + dd] : 0.f;
+                const uint32_t cc = c0 + r;
+                sc[r][dd] = (cc < nc && d0 + dd < dim) ? c[(size_t)cc * ldc + d0 + dd] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int dd = 0; dd < DK; ++dd) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = sv[ty + 16 * i][dd];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = sc[tx + 16 * j][dd];
+                if (metric == VDB_METRIC_L2) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float diff = __fsub_rn(a[i], b[j]);
+                            acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(diff, diff));
+                        }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(a[i], b[j]));
+                }
+            }
+            __syncthreads();
+        }
+        // strict '<' in ascending centroid order: the lowest index wins ties (:287)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t cc = c0 + tx + 16 * j;
+            if (cc < nc) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float d = (metric == VDB_METRIC_L2) ? acc[i][j] : -acc[i][j];
+                    if (d < bd[i]) {
+                        bd[i] = d;
+                        bi[i] = cc;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sbd[ty + 16 * i][tx] = bd[i];
+        sbi[ty + 16 * i][tx] = bi[i];
+    }
+    __syncthreads();
+    if (tid < TV) {
+        float d = sbd[tid][0];
+        uint32_t b = sbi[tid][0];
+        for (int t = 1; t < 16; ++t) {
+            const float dt = sbd[tid][t];
+            const uint32_t bt = sbi[tid][t];
+            if (dt < d || (dt == d && bt < b)) {
+                d = dt;
+                b = bt;
+            }
+        }
+        const uint64_t v = v0 + tid;
+        if (v < n) {
+            assign[v] = b;
+            if (dist_out) dist_out[v] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ seeding
+
+// std::mt19937 state kept in device memory
+struct DevRng {
+    uint32_t mt[624];
+    uint32_t idx;
+};
+
+__device__ void rng_seed(DevRng* g, uint32_t seed) {
+    g->mt[0] = seed;
+    for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t)i;
+    g->idx = 624;
+}
+
+__device__ uint32_t rng_next(DevRng* g) {
+    if (g->idx >= 624) {
+        for (int i = 0; i < 624; ++i) {
+            uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7fffffffu);
+            g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->idx = 0;
+    }
+    uint32_t y = g->mt[g->idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// libstdc++ uniform_int_distribution<uint64_t>(0, n-1) on a 32-bit engine (Lemire)
+__device__ uint64_t rng_below(DevRng* g, uint32_t range) {
+    uint64_t product = (uint64_t)rng_next(g) * (uint64_t)range;
+    uint32_t low = (uint32_t)product;
+    if (low < range) {
+        const uint32_t threshold = (0u - range) % range;
+        while (low < threshold) {
+            product = (uint64_t)rng_next(g) * (uint64_t)range;
+            low = (uint32_t)product;
+        }
+    }
+    return product >> 32;
+}
+
+// libstdc++ uniform_real_distribution<float>(0, b): generate_canonical<float,24>
+__device__ float rng_real_0_b(DevRng* g, float b) {
+    float ret = __fdiv_rn(__uint2float_rn(rng_next(g)), 4294967296.0f);
+    if (ret >= 1.0f) ret = __uint_as_float(0x3f7fffffu);  // nextafter(1, 0)
+    return __fadd_rn(__fmul_rn(ret, __fsub_rn(b, 0.0f)), 0.0f);
+}
+
+// first centroid = row uniform_int(0, n-1) (ivf_flat_index.cpp:53-60); min-distances start at FLT_MAX
+__global__ void seed_init_kernel(DevRng* g, const float* __restrict__ x, uint32_t n, uint32_t ldx, uint32_t ld,
+                                 float* __restrict__ centroids, uint32_t* picked) {
+    __shared__ uint32_t s_first;
+    if (threadIdx.x == 0) {
+        rng_seed(g, 42);
+        s_first = (uint32_t)rng_below(g, n);
+        picked[0] = s_first;
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < ld; d += blockDim.x) centroids[d] = x[(size_t)s_first * ldx + d];
+}
+
+__global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// squared L2 distance of every training row to the newest centroid, summed in
+// ascending d (one thread per row, tiles transposed through shared memory so
+// the HBM reads stay coalesced), folded into the running minimum (:68-88).
+__global__ void __launch_bounds__(128) seed_dist_kernel(const float* __restrict__ x, uint32_t n, uint32_t ldx,
+                                                        uint32_t dim, const float* __restrict__ cnew,
+                                                        float* __restrict__ mind) {
+    __shared__ float tile[128][33];
+    __shared__ float sc[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint64_t v0 = (uint64_t)blockIdx.x * 128;
+    float acc = 0.f;
+    for (uint32_t d0 = 0; d0 < dim; d0 += 32) {
+        const bool dok = d0 + lane < dim;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const uint64_t v = v0 + w * 32 + i;
+            tile[w * 32 + i][lane] = (v < n && dok) ? x[v * ldx + d0 + lane] : 0.f;
+        }
+        if (tid < 32) sc[tid] = dok ? cnew[d0 + tid] : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int dd = 0; dd < 32; ++dd) {
+            const float diff = __fsub_rn(tile[tid][dd], sc[dd]);
+            acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+        }
+        __syncthreads();
+    }
+    const uint64_t v = v0 + tid;
+    if (v < n) {
+        const float m = mind[v];
+        mind[v] = acc < m ? acc : m;  // std::min(min_dist, dist)
+    }
+}
+
+constexpr uint32_t SEQ_CHUNK = 1024;
+
+// One warp: total = sequential fp32 sum of mind[] (ivf_flat_index.cpp:87),
+// target = uniform_real(0,total) (:91-92), first row whose sequential running
+// sum reaches the target becomes centroid `cidx` (:95-103).  Lane 0 carries the
+// dependent add chain; the warp stages the data through shared memory.
+__global__ void __launch_bounds__(32) seed_sample_kernel(DevRng* g, const float* __restrict__ x, uint32_t n,
+                                                         uint32_t ldx, uint32_t ld, const float* __restrict__ mind,
+                                                         float* __restrict__ ckpt, float* __restrict__ centroids,
+                                                         uint32_t cidx, uint32_t* picked) {
+    __shared__ float buf[SEQ_CHUNK];
+    __shared__ uint32_t s_pick;
+    __shared__ float s_start;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t nchunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    float run = 0.f;
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+        const uint32_t base = ch * SEQ_CHUNK;
+        for (uint32_t i = lane; i < SEQ_CHUNK; i += 32) buf[i] = (base + i < n) ? mind[base + i] : 0.f;
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t m = min(SEQ_CHUNK, n - base);
+#pragma unroll 8
+            for (uint32_t i = 0; i < m; ++i) run = __fadd_rn(run, buf[i]);
+            ckpt[ch] = run;  // running sum after this chunk
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const float total = run;
+        const float target = rng_real_0_b(g, total);
+        // running sums are non-decreasing (the terms are >= 0), so the first chunk whose
+        // end-of-chunk sum reaches the target holds the first row that does
+        uint32_t ch = 0;
+        while (ch < nchunks && !(ckpt[ch] >= target)) ++ch;
+        s_pick = 0xffffffffu;
+        s_start = 0.f;
+        if (ch < nchunks) {
+            s_pick = ch;
+            s_start = ch ? ckpt[ch - 1] : 0.f;
+        }
+        ckpt[nchunks] = target;
+    }
+    __syncwarp();
+    const uint32_t ch = s_pick;
+    if (ch == 0xffffffffu) {  // no row reaches the target: the reference leaves the slot as it was
+        if (lane == 0) picked[cidx] = 0xffffffffu;
+        return;
+    }
+    const uint32_t base = ch * SEQ_CHUNK;
+    for (uint32_t i = lane; i < SEQ_CHUNK; i += 32) buf[i] = (base + i < n) ? mind[base + i] : 0.f;
+    __syncwarp();
+    if (lane == 0) {
+        const float target = ckpt[nchunks];
+        float cum = s_start;
+        const uint32_t m = min(SEQ_CHUNK, n - base);
+        uint32_t v = 0xffffffffu;
+        for (uint32_t i = 0; i < m; ++i) {
+            cum = __fadd_rn(cum, buf[i]);
+            if (cum >= target) {
+                v = base + i;
+                break;
+            }
+        }
+        s_pick = v;
+        picked[cidx] = v;
+    }
+    __syncwarp();
+    const uint32_t v = s_pick;
+    if (v == 0xffffffffu) return;
+    for (uint32_t d = lane; d < ld; d += 32) centroids[(size_t)cidx * ld + d] = x[(size_t)v * ldx + d];
+}
+
+// ------------------------------------------------------------- Lloyd update
+
+// Stable bucketing of row numbers by cluster (members of a cluster in input
+// order) = a counting sort whose chunks are walked by one warp each.
+__global__ void __launch_bounds__(32) member_hist_kernel(const uint32_t* __restrict__ assign, uint32_t n,
+                                                         uint32_t chunk, uint32_t nc, uint32_t* __restrict__ M) {
+    const uint32_t ch = blockIdx.x, lane = threadIdx.x;
+    const uint64_t lo = (uint64_t)ch * chunk, hi = min((uint64_t)n, lo + chunk);
+    uint32_t* row = M + (size_t)ch * nc;
+    for (uint64_t v = lo + lane; v < hi; v += 32) atomicAdd(&row[assign[v]], 1u);
+}
+
+// per cluster: exclusive prefix of the chunk counts down the column, cluster total
+__global__ void member_colscan_kernel(uint32_t* __restrict__ M, uint32_t nchunks, uint32_t nc,
+                                      uint32_t* __restrict__ counts) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nc) return;
+    uint32_t run = 0;
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+        const uint32_t t = M[(size_t)ch * nc + key];
+        M[(size_t)ch * nc + key] = run;
+        run += t;
+    }
+    counts[key] = run;
+}
+
+// exclusive scan of counts -> coff[nc+1] (single block)
+__global__ void __launch_bounds__(1024) member_keyscan_kernel(const uint32_t* __restrict__ counts, uint32_t nc,
+                                                              uint32_t* __restrict__ coff) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = (nc + 1023) / 1024;
+    const uint32_t lo = min(tid * chunk, nc), hi = min(lo + chunk, nc);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += counts[i];
+    s_part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const uint32_t t = s_part[i];
+            s_part[i] = run;
+            run += t;
+        }
+        coff[nc] = run;
+    }
+    __syncthreads();
+    uint32_t run = s_part[tid];
+    for (uint32_t i = lo; i < hi; ++i) {
+        coff[i] = run;
+        run += counts[i];
+    }
+}
+
+__global__ void __launch_bounds__(32) member_rank_kernel(const uint32_t* __restrict__ assign, uint32_t n,
+                                                         uint32_t chunk, uint32_t nc, uint32_t* __restrict__ M,
+                                                         const uint32_t* __restrict__ coff,
+                                                         uint32_t* __restrict__ members) {
+    const uint32_t ch = blockIdx.x, lane = threadIdx.x;
+    const uint64_t lo = (uint64_t)ch * chunk, hi = min((uint64_t)n, lo + chunk);
+    uint32_t* row = M + (size_t)ch * nc;
+    for (uint64_t v0 = lo; v0 < hi; v0 += 32) {
+        const uint64_t v = v0 + lane;
+        const bool ok = v < hi;
+        const unsigned active = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const uint32_t key = assign[v];
+            const unsigned same = __match_any_sync(active, key);
+            const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+            const uint32_t before = row[key];
+            members[coff[key] + before + rank] = (uint32_t)v;
+            __syncwarp(active);
+            if (rank == 0) row[key] = before + __popc(same);
+        }
+        __syncwarp();
+    }
+}
+
+// sums of each cluster's rows, added in ascending input row (ivf_flat_index.cpp:123-131)
+__global__ void __launch_bounds__(128) cluster_sum_kernel(const float* __restrict__ x, uint32_t ldx,
+                                                          const uint32_t* __restrict__ members,
+                                                          const uint32_t* __restrict__ coff, uint32_t ld,
+                                                          float* __restrict__ sums) {
+    const uint32_t c = blockIdx.x;
+    const uint32_t d4 = blockIdx.y * blockDim.x + threadIdx.x;
+    if (d4 >= (ld >> 2)) return;
+    const uint32_t lo = coff[c], hi = coff[c + 1];
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const uint32_t ldx4 = ldx >> 2;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t m = lo;
+    for (; m + 4 <= hi; m += 4) {
+        const float4 a = x4[(size_t)members[m] * ldx4 + d4];
+        const float4 b = x4[(size_t)members[m + 1] * ldx4 + d4];
+        const float4 cc = x4[(size_t)members[m + 2] * ldx4 + d4];
+        const float4 d = x4[(size_t)members[m + 3] * ldx4 + d4];
+        s.x = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.x, a.x), b.x), cc.x), d.x);
+        s.y = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.y, a.y), b.y), cc.y), d.y);
+        s.z = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.z, a.z), b.z), cc.z), d.z);
+        s.w = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.w, a.w), b.w), cc.w), d.w);
+    }
+    for (; m < hi; ++m) {
+        const float4 a = x4[(size_t)members[m] * ldx4 + d4];
+        s.x = __fadd_rn(s.x, a.x);
+        s.y = __fadd_rn(s.y, a.y);
+        s.z = __fadd_rn(s.z, a.z);
+        s.w = __fadd_rn(s.w, a.w);
+    }
+    reinterpret_cast<float4*>(sums)[(size_t)c * (ld >> 2) + d4] = s;
+}
+
+// centroid = sum / count where count > 0; an empty cluster keeps its centroid (:134-141)
+__global__ void centroid_divide_kernel(const float* __restrict__ sums, const uint32_t* __restrict__ counts,
+                                       uint32_t nc, uint32_t ld, float* __restrict__ centroids) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)nc * ld) return;
+    const uint32_t c = (uint32_t)(i / ld);
+    const uint32_t cnt = counts[c];
+    if (cnt > 0) centroids[i] = __fdiv_rn(sums[i], __uint2float_rn(cnt));
+}
+
+// ----------------------------------------------------------------------- add
+
+__global__ void hist_kernel(const uint32_t* __restrict__ assign, uint64_t n, uint32_t nlist, uint32_t shard_rank,
+                            uint32_t shard_count, uint32_t* __restrict__ hist) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t l = assign[v];
+    if (l < nlist && (l % shard_count) == shard_rank) atomicAdd(&hist[l], 1u);
+}
+
+// one warp per new row: claim the next slot of its list, copy row + id into the page
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ x, uint32_t ldx,
+                                                           const uint64_t* __restrict__ ids, uint64_t id_base,
+                                                           uint64_t n, const uint32_t* __restrict__ assign,
+                                                           const uint32_t* __restrict__ old_rows,
+                                                           uint32_t* __restrict__ fill,
+                                                           const uint32_t* __restrict__ page_off,
+                                                           const uint64_t* __restrict__ page_vec,
+                                                           const uint64_t* __restrict__ page_ids, uint32_t page_rows,
+                                                           uint32_t ld, uint32_t shard_rank, uint32_t shard_count) {
+    const uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (v >= n) return;
+    const uint32_t l = assign[v];
+    if ((l % shard_count) != shard_rank) return;
+    uint32_t pos = 0;
+    if (lane == 0) pos = old_rows[l] + atomicAdd(&fill[l], 1u);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    const uint32_t pg = page_off[l] + pos / page_rows, r = pos % page_rows;
+    float4* dst = reinterpret_cast<float4*>(page_vec[pg]) + (size_t)r * (ld >> 2);
+    const float4* src = reinterpret_cast<const float4*>(x + v * ldx);
+    for (uint32_t c = lane; c < (ld >> 2); c += 32) dst[c] = src[c];
+    if (lane == 0) reinterpret_cast<uint64_t*>(page_ids[pg])[r] = ids ? ids[v] : id_base + v;
+}
+
+// [n][dim] (any stride) -> [n][ld] zero-padded
+__global__ void pad_rows_kernel(const float* __restrict__ src, uint32_t lds, uint32_t dim, float* __restrict__ dst,
+                                uint32_t ld, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ld) return;
+    const uint64_t r = i / ld;
+    const uint32_t d = (uint32_t)(i - r * ld);
+    dst[i] = d < dim ? src[r * lds + d] : 0.f;
+}
+
+__global__ void gather_ids_kernel(const uint64_t* __restrict__ page_ids_base, uint32_t rows, uint64_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) out[i] = page_ids_base[i];
+}
+
+}  // namespace
+
+size_t rng_state_bytes() { return sizeof(DevRng); }
+
+int32_t kmeans_assign_exact(const float* x, uint64_t n, uint32_t ldx, const float* c, uint32_t nc, uint32_t ldc,
+                            uint32_t dim, int metric, uint32_t* assign, float* dist_out, cudaStream_t stream) {
+    if (n == 0) return VDB_OK;
+    VDB_REQUIRE(nc >= 1 && dim >= 1, "assign: empty centroid table");
+    const uint64_t blocks = (n + TV - 1) / TV;
+    VDB_REQUIRE(blocks < (1ull << 31), "assign: too many rows for one call");
+    assign_exact_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, n, ldx, c, nc, ldc, dim, metric, assign, dist_out);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeanspp_seed_exact(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
+                            float* centroids, KMeansScratch& sc, cudaStream_t stream) {
+    seed_init_kernel<<<1, 256, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, centroids, sc.picked);
+    fill_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(sc.mind, n, FLT_MAX);
+    for (uint32_t c = 1; c < nlist; ++c) {
+        seed_dist_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, ldx, dim, centroids + (size_t)(c - 1) * ld,
+                                                               sc.mind);
+        seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, sc.ckpt, centroids, c,
+                                                 sc.picked);
+    }
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeans_members(const uint32_t* assign, uint32_t n, uint32_t nc, KMeansScratch& sc, cudaStream_t stream) {
+    const uint32_t nchunks = sc.nchunks, chunk = sc.chunk;
+    VDB_CUDA_TRY(cudaMemsetAsync(sc.M, 0, (size_t)nchunks * nc * 4, stream));
+    member_hist_kernel<<<nchunks, 32, 0, stream>>>(assign, n, chunk, nc, sc.M);
+    member_colscan_kernel<<<(nc + 255) / 256, 256, 0, stream>>>(sc.M, nchunks, nc, sc.counts);
+    member_keyscan_kernel<<<1, 1024, 0, stream>>>(sc.counts, nc, sc.coff);
+    member_rank_kernel<<<nchunks, 32, 0, stream>>>(assign, n, chunk, nc, sc.M, sc.coff, sc.members);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeans_update_exact(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
+                            uint32_t ld, float* centroids, KMeansScratch& sc, cudaStream_t stream) {
+    VDB_TRY(kmeans_members(assign, n, nc, sc, stream));
+    dim3 grid(nc, ((ld >> 2) + 127) / 128);
+    cluster_sum_kernel<<<grid, 128, 0, stream>>>(x, ldx, sc.members, sc.coff, ld, sc.sums);
+    const uint64_t tot = (uint64_t)nc * ld;
+    centroid_divide_kernel<<<(uint32_t)((tot + 255) / 256), 256, 0, stream>>>(sc.sums, sc.counts, nc, ld, centroids);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeans_cluster_sums(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
+                            uint32_t ld, float* sums, uint32_t* counts, KMeansScratch& sc, cudaStream_t stream) {
+    VDB_TRY(kmeans_members(assign, n, nc, sc, stream));
+    dim3 grid(nc, ((ld >> 2) + 127) / 128);
+    cluster_sum_kernel<<<grid, 128, 0, stream>>>(x, ldx, sc.members, sc.coff, ld, sums);
+    VDB_CUDA_TRY(cudaMemcpyAsync(counts, sc.counts, (size_t)nc * 4, cudaMemcpyDeviceToDevice, stream));
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeans_divide(const float* sums, const uint32_t* counts, uint32_t nc, uint32_t ld, float* centroids,
+                      cudaStream_t stream) {
+    const uint64_t tot = (uint64_t)nc * ld;
+    centroid_divide_kernel<<<(uint32_t)((tot + 255) / 256), 256, 0, stream>>>(sums, counts, nc, ld, centroids);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t KMeansScratch::reserve(uint32_t n, uint32_t nc, uint32_t ld) {
+    release();
+    nchunks = std::min<uint32_t>(1024, (n + 1023) / 1024);
+    if (nchunks == 0) nchunks = 1;
+    chunk = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
+    if (chunk == 0) chunk = 32;
+    VDB_CUDA_TRY(cudaMalloc(&rng, rng_state_bytes()));
+    VDB_CUDA_TRY(cudaMalloc(&mind, (size_t)std::max(n, 1u) * 4));
+    VDB_CUDA_TRY(cudaMalloc(&ckpt, ((size_t)(n + SEQ_CHUNK - 1) / SEQ_CHUNK + 2) * 4));
+    VDB_CUDA_TRY(cudaMalloc(&picked, (size_t)nc * 4));
+    VDB_CUDA_TRY(cudaMalloc(&M, (size_t)nchunks * nc * 4));
+    VDB_CUDA_TRY(cudaMalloc(&counts, (size_t)nc * 4));
+    VDB_CUDA_TRY(cudaMalloc(&coff, (size_t)(nc + 1) * 4));
+    VDB_CUDA_TRY(cudaMalloc(&members, (size_t)std::max(n, 1u) * 4));
+    VDB_CUDA_TRY(cudaMalloc(&sums, (size_t)nc * ld * 4));
+    VDB_CUDA_TRY(cudaMalloc(&assign, (size_t)std::max(n, 1u) * 4));
+    return VDB_OK;
+}
+
+void KMeansScratch::release() {
+    cudaFree(rng); cudaFree(mind); cudaFree(ckpt); cudaFree(picked); cudaFree(M);
+    cudaFree(counts); cudaFree(coff); cudaFree(members); cudaFree(sums); cudaFree(assign);
+    rng = nullptr; mind = nullptr; ckpt = nullptr; picked = nullptr; M = nullptr; counts = nullptr;
+    coff = nullptr; members = nullptr; sums = nullptr; assign = nullptr;
+}
+
+int32_t launch_hist(const uint32_t* assign, uint64_t n, uint32_t nlist, uint32_t shard_rank, uint32_t shard_count,
+                    uint32_t* hist, cudaStream_t stream) {
+    if (n == 0) return VDB_OK;
+    hist_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, stream>>>(assign, n, nlist, shard_rank, shard_count, hist);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, uint64_t id_base, uint64_t n,
+                            const uint32_t* assign, const uint32_t* old_rows, uint32_t* fill,
+                            const uint32_t* page_off, const uint64_t* page_vec, const uint64_t* page_ids,
+                            uint32_t page_rows, uint32_t ld, uint32_t shard_rank, uint32_t shard_count,
+                            cudaStream_t stream) {
+    if (n == 0) return VDB_OK;
+    const uint64_t blocks = (n * 32 + 255) / 256;
+    scatter_rows_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, ldx, ids, id_base, n, assign, old_rows, fill,
+                                                              page_off, page_vec, page_ids, page_rows, ld,
+                                                              shard_rank, shard_count);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t launch_pad_rows(const float* src, uint32_t lds, uint32_t dim, float* dst, uint32_t ld, uint64_t n,
+                        cudaStream_t stream) {
+    if (n == 0) return VDB_OK;
+    const uint64_t tot = n * ld;
+    pad_rows_kernel<<<(uint32_t)((tot + 255) / 256), 256, 0, stream>>>(src, lds, dim, dst, ld, n);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+}  // namespace vdb

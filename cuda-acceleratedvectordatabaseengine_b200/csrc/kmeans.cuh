@@ -1,0 +1,44 @@
+// Host-visible interface of the training / assignment kernels (kmeans.cu).
+#pragma once
+#include <algorithm>
+#include "common.cuh"
+
+namespace vdb {
+
+struct KMeansScratch {
+    void* rng = nullptr;        // device std::mt19937 state
+    float* mind = nullptr;      // [n] running min squared distance to the chosen seeds
+    float* ckpt = nullptr;      // sequential-sum checkpoints
+    uint32_t* picked = nullptr; // [nlist] training row chosen for each seed
+    uint32_t* M = nullptr;      // [nchunks][nlist] counting-sort matrix
+    uint32_t* counts = nullptr; // [nlist]
+    uint32_t* coff = nullptr;   // [nlist+1]
+    uint32_t* members = nullptr;// [n] rows bucketed by cluster, input order inside a cluster
+    float* sums = nullptr;      // [nlist][ld]
+    uint32_t* assign = nullptr; // [n]
+    uint32_t nchunks = 0, chunk = 0;
+    int32_t reserve(uint32_t n, uint32_t nc, uint32_t ld);
+    void release();
+};
+
+int32_t kmeans_assign_exact(const float* x, uint64_t n, uint32_t ldx, const float* c, uint32_t nc, uint32_t ldc,
+                            uint32_t dim, int metric, uint32_t* assign, float* dist_out, cudaStream_t stream);
+int32_t kmeanspp_seed_exact(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
+                            float* centroids, KMeansScratch& sc, cudaStream_t stream);
+int32_t kmeans_update_exact(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
+                            uint32_t ld, float* centroids, KMeansScratch& sc, cudaStream_t stream);
+int32_t kmeans_cluster_sums(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
+                            uint32_t ld, float* sums, uint32_t* counts, KMeansScratch& sc, cudaStream_t stream);
+int32_t kmeans_divide(const float* sums, const uint32_t* counts, uint32_t nc, uint32_t ld, float* centroids,
+                      cudaStream_t stream);
+int32_t launch_hist(const uint32_t* assign, uint64_t n, uint32_t nlist, uint32_t shard_rank, uint32_t shard_count,
+                    uint32_t* hist, cudaStream_t stream);
+int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, uint64_t id_base, uint64_t n,
+                            const uint32_t* assign, const uint32_t* old_rows, uint32_t* fill,
+                            const uint32_t* page_off, const uint64_t* page_vec, const uint64_t* page_ids,
+                            uint32_t page_rows, uint32_t ld, uint32_t shard_rank, uint32_t shard_count,
+                            cudaStream_t stream);
+int32_t launch_pad_rows(const float* src, uint32_t lds, uint32_t dim, float* dst, uint32_t ld, uint64_t n,
+                        cudaStream_t stream);
+
+}  // namespace vdb

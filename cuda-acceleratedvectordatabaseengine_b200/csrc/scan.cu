@@ -1,0 +1,844 @@
+// The inverted-list scan engine for sm_100a.
+//
+// Replaces, for the whole query batch at once, what the reference does one
+// (query, list) pair at a time:
+//   select_nprobe_lists  ivf_flat_index.cpp:298-336   (run as a scan over the centroid table)
+//   search_list_cpu/gpu  ivf_flat_index.cpp:339-384, 521-617 + bruteforce_search_kernel kernels.cuh:84-185
+//   merge_results        ivf_flat_index.cpp:474-518
+//
+// Three kernels, no host synchronisation in between:
+//   1. build_groups_kernel  groups the (query, probe) pairs by list, so that a
+//      list probed by several queries of the batch is streamed from HBM once,
+//      and cuts the work into items (list page range x tile of <= QT queries).
+//   2. scan_kernel          persistent, one CTA per SM.  A producer warp
+//      streams the item's rows HBM -> shared memory with 1-D bulk TMA copies
+//      (cp.async.bulk + mbarrier complete_tx) through an S-stage ring; eight
+//      consumer warps hold one row slice per lane in registers (128-bit,
+//      conflict-free shared loads), stream the tile's queries from shared
+//      memory, accumulate exact fp32 (q-v)^2 or q.v, and push candidates that
+//      beat the running k-th distance into a per-query shared pool that is
+//      bitonic-compacted to the best k (the fused top-k).
+//   3. merge_kernel         per query: page partials -> per-list top-k
+//      (multiset, as search_list_cpu returns it) -> sort by (dist,id), drop
+//      duplicate ids, pad: merge_results.
+#include "scan.cuh"
+#include "topk.cuh"
+
+namespace vdb {
+
+namespace {
+
+constexpr int STAGE_ROWS = 16;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int SCAN_THREADS = CONSUMER_THREADS + 32;
+constexpr int MAX_QT = 16;
+constexpr uint32_t MAX_K = 2048;
+constexpr uint32_t SMEM_BUDGET = 227 * 1024;
+
+struct WorkList {
+    uint32_t *gcount, *gfill, *goff, *ioff, *gpairs, *pair_slot;
+    ScanItem* items;
+    uint32_t* totals;
+    unsigned long long* stats;
+};
+
+// ---------------------------------------------------------------- utilities
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    // 1024 threads; returns the exclusive prefix of v over the block
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();  // protect s_warp reuse
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = s_warp[lane];
+        uint32_t u = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, u, o);
+            if (lane >= o) u += y;
+        }
+        s_warp[lane] = u - t;  // exclusive prefix of the warp sums
+        if (lane == 31) s_warp[32] = u;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[w] + x - v;
+}
+
+__device__ __forceinline__ uint32_t n_ranges(const ListTable& lt, uint32_t l, uint32_t ppi) {
+    uint32_t npages = lt.page_off[l + 1] - lt.page_off[l];
+    return (npages + ppi - 1) / ppi;
+}
+
+// ------------------------------------------------------- 1. probe grouping
+
+__global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const uint32_t* __restrict__ probes,
+                                                            uint32_t npairs, uint32_t QT, uint32_t ppi,
+                                                            WorkList wl) {
+    __shared__ uint32_t s_warp[33];
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t nlist = lt.nlist;
+
+    for (uint32_t l = tid; l < nlist; l += NT) {
+        wl.gcount[l] = 0;
+        wl.gfill[l] = 0;
+    }
+    if (tid == 0) {
+        wl.stats[0] = 0;
+        wl.stats[1] = 0;
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < npairs; p += NT) {
+        uint32_t l = probes[p];
+        if (l < nlist && lt.rows[l] > 0) atomicAdd(&wl.gcount[l], 1u);
+    }
+    __syncthreads();
+
+    // exclusive scans over lists: grouped-pair offsets and item offsets
+    {
+        const uint32_t chunk = (nlist + NT - 1) / NT;
+        const uint32_t lo = min(tid * chunk, nlist), hi = min(lo + chunk, nlist);
+        uint32_t g = 0, it = 0;
+        unsigned long long alg = 0, uniq = 0;
+        for (uint32_t l = lo; l < hi; ++l) {
+            uint32_t c = wl.gcount[l];
+            if (c) {
+                g += c;
+                it += ((c + QT - 1) / QT) * n_ranges(lt, l, ppi);
+                alg += (unsigned long long)lt.rows[l] * c;
+                uniq += lt.rows[l];
+            }
+        }
+        uint32_t tot_g, tot_it;
+        uint32_t base_g = block_exclusive_scan(g, s_warp, &tot_g);
+        uint32_t base_it = block_exclusive_scan(it, s_warp, &tot_it);
+        for (uint32_t l = lo; l < hi; ++l) {
+            wl.goff[l] = base_g;
+            wl.ioff[l] = base_it;
+            uint32_t c = wl.gcount[l];
+            if (c) {
+                base_g += c;
+                base_it += ((c + QT - 1) / QT) * n_ranges(lt, l, ppi);
+            }
+        }
+        if (tid == 0) {
+            wl.goff[nlist] = tot_g;
+            wl.ioff[nlist] = tot_it;
+            wl.totals[0] = tot_it;
+        }
+        if (alg) atomicAdd(&wl.stats[0], alg);
+        if (uniq) atomicAdd(&wl.stats[1], uniq);
+    }
+    // exclusive scan over pairs: first partial-result slot of each pair
+    {
+        const uint32_t chunk = (npairs + NT - 1) / NT;
+        const uint32_t lo = min(tid * chunk, npairs), hi = min(lo + chunk, npairs);
+        uint32_t s = 0;
+        for (uint32_t p = lo; p < hi; ++p) {
+            uint32_t l = probes[p];
+            if (l < nlist && lt.rows[l] > 0) s += n_ranges(lt, l, ppi);
+        }
+        uint32_t tot;
+        uint32_t base = block_exclusive_scan(s, s_warp, &tot);
+        for (uint32_t p = lo; p < hi; ++p) {
+            wl.pair_slot[p] = base;
+            uint32_t l = probes[p];
+            if (l < nlist && lt.rows[l] > 0) base += n_ranges(lt, l, ppi);
+        }
+        if (tid == 0) {
+            wl.pair_slot[npairs] = tot;
+            wl.totals[1] = tot;
+        }
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < npairs; p += NT) {
+        uint32_t l = probes[p];
+        if (l < nlist && lt.rows[l] > 0) {
+            uint32_t pos = wl.goff[l] + atomicAdd(&wl.gfill[l], 1u);
+            wl.gpairs[pos] = p;
+        }
+    }
+    for (uint32_t l = tid; l < nlist; l += NT) {
+        uint32_t c = wl.gcount[l];
+        if (!c) continue;
+        uint32_t nr = n_ranges(lt, l, ppi), nt = (c + QT - 1) / QT;
+        uint32_t o = wl.ioff[l], g0 = wl.goff[l];
+        for (uint32_t t = 0; t < nt; ++t)
+            for (uint32_t r = 0; r < nr; ++r) {
+                ScanItem it;
+                it.list = l;
+                it.gbase = g0 + t * QT;
+                it.qcount = min(QT, c - t * QT);
+                it.range = r;
+                wl.items[o + t * nr + r] = it;
+            }
+    }
+}
+
+// ------------------------------------------------------------ 2. list scan
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk TMA copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
+// consumer barrier that also ORs a per-thread flag across the 256 consumer threads
+__device__ __forceinline__ bool consumer_bar_or(bool flag) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "bar.red.or.pred q, 1, %2, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((uint32_t)flag), "n"(CONSUMER_THREADS)
+        : "memory");
+    return r != 0;
+}
+
+struct ScanParams {
+    ListTable lt;
+    const float* queries;  // [nq][ld]
+    const ScanItem* items;
+    const uint32_t* totals;
+    const uint32_t* gpairs;
+    const uint32_t* pair_slot;
+    float* part_d;
+    uint64_t* part_i;
+    uint32_t k, P, QT, ppi, S, np, check_interval;
+    int metric;
+};
+
+struct ScanSmem {
+    float* stages;
+    float* sq;
+    uint64_t* pool_i;
+    float* pool_d;
+    uint32_t* cnt;
+    float* thr;
+    uint32_t* spair;
+    uint64_t* full;
+    uint64_t* empty;
+};
+
+__device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
+    ScanSmem s;
+    const uint32_t stage_bytes = STAGE_ROWS * p.lt.ld * 4;
+    uint8_t* q = base;
+    s.stages = (float*)q;
+    q += (size_t)p.S * stage_bytes;
+    s.sq = (float*)q;
+    q += (size_t)p.QT * p.lt.ld * 4;
+    s.pool_i = (uint64_t*)q;
+    q += (size_t)p.QT * p.P * 8;
+    s.pool_d = (float*)q;
+    q += (size_t)p.QT * p.P * 4;
+    s.cnt = (uint32_t*)q;
+    q += MAX_QT * 4;
+    s.thr = (float*)q;
+    q += MAX_QT * 4;
+    s.spair = (uint32_t*)q;
+    q += MAX_QT * 4;
+    q = (uint8_t*)(((uintptr_t)q + 7) & ~(uintptr_t)7);
+    s.full = (uint64_t*)q;
+    q += 8 * 8;
+    s.empty = (uint64_t*)q;
+    return s;
+}
+
+static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P) {
+    return S * STAGE_ROWS * ld * 4 + QT * ld * 4 + QT * P * 12 + 3 * MAX_QT * 4 + 8 + 16 * 8;
+}
+
+// One warp sorts query j's pool and keeps the best k (multiset: duplicates of
+// an id inside one list survive, exactly like search_list_cpu's partial_sort).
+__device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams& p, uint32_t j, uint32_t lane) {
+    float* d = s.pool_d + (size_t)j * p.P;
+    uint64_t* id = s.pool_i + (size_t)j * p.P;
+    const uint32_t c = min(s.cnt[j], p.P);
+    const uint32_t n2 = dev_next_pow2(max(c, 1u));
+    for (uint32_t i = c + lane; i < n2; i += 32) {
+        d[i] = FLT_MAX;
+        id[i] = ID_PAD;
+    }
+    __syncwarp();
+    bitonic_sort_pairs(d, id, n2, lane, 32, [] { __syncwarp(); });
+    const uint32_t nc = min(c, p.k);
+    if (lane == 0) {
+        s.cnt[j] = nc;
+        s.thr[j] = (nc >= p.k) ? d[p.k - 1] : INFINITY;
+    }
+    __syncwarp();
+}
+
+template <int NJ>
+__device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSmem& s) {
+    const uint32_t ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
+    const uint32_t ld = p.lt.ld, ld4 = ld >> 2;
+    const uint32_t total = *p.totals;
+    const uint32_t limit = p.P - p.check_interval * STAGE_ROWS;
+    constexpr int R = STAGE_ROWS / CONSUMER_WARPS;  // rows of a stage per warp
+    uint32_t stage = 0, phase = 0;
+
+    for (uint32_t ii = blockIdx.x; ii < total; ii += gridDim.x) {
+        const ScanItem it = p.items[ii];
+        const uint32_t qcount = it.qcount;
+        // the tile's queries -> shared memory
+        for (uint32_t idx = ctid; idx < qcount * ld4; idx += CONSUMER_THREADS) {
+            uint32_t j = idx / ld4, c = idx - j * ld4;
+            uint32_t q = p.gpairs[it.gbase + j] / p.np;
+            reinterpret_cast<float4*>(s.sq)[j * ld4 + c] =
+                __ldg(reinterpret_cast<const float4*>(p.queries) + (size_t)q * ld4 + c);
+        }
+        if (ctid < qcount) {
+            s.cnt[ctid] = 0;
+            s.thr[ctid] = INFINITY;
+            s.spair[ctid] = p.gpairs[it.gbase + ctid];
+        }
+        consumer_bar();
+
+        const uint32_t l = it.list;
+        const uint32_t rows = p.lt.rows[l];
+        const uint32_t pg_first = p.lt.page_off[l];
+        const uint32_t pg0 = pg_first + it.range * p.ppi;
+        const uint32_t pgN = min(pg0 + p.ppi, p.lt.page_off[l + 1]);
+        uint32_t since_check = 0;
+        bool over = false;  // this thread pushed a candidate at or beyond the compaction mark
+
+        for (uint32_t pg = pg0; pg < pgN; ++pg) {
+            const uint32_t row_base = (pg - pg_first) * p.lt.page_rows;  // list-relative row of the page start
+            const uint32_t rows_in_page = min(p.lt.page_rows, rows - row_base);
+            const uint64_t* page_ids = reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]);
+            for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
+                const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
+                mbar_wait(&s.full[stage], phase);
+                // this warp's rows of the stage -> registers (lane owns float4 columns lane, lane+32, ...)
+                const float4* st4 = reinterpret_cast<const float4*>(s.stages + (size_t)stage * STAGE_ROWS * ld);
+                float4 v[R][NJ];
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const uint32_t r = warp + CONSUMER_WARPS * i;
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj) {
+                        const uint32_t c4 = lane + 32 * jj;
+                        v[i][jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.empty[stage]);  // slot free: the rows now live in registers
+                if (++stage == p.S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+
+                for (uint32_t j = 0; j < qcount; ++j) {
+                    const float4* q4 = reinterpret_cast<const float4*>(s.sq) + j * ld4;
+                    float4 qv[NJ];
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj) {
+                        const uint32_t c4 = lane + 32 * jj;
+                        qv[jj] = (c4 < ld4) ? q4[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float thr = s.thr[j];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const uint32_t r = warp + CONSUMER_WARPS * i;
+                        if (r >= nr) continue;  // warp-uniform
+                        float a0 = 0.f, a1 = 0.f;
+                        if (p.metric == VDB_METRIC_L2) {
+#pragma unroll
+                            for (int jj = 0; jj < NJ; ++jj) {
+                                float dx = qv[jj].x - v[i][jj].x, dy = qv[jj].y - v[i][jj].y;
+                                float dz = qv[jj].z - v[i][jj].z, dw = qv[jj].w - v[i][jj].w;
+                                a0 = fmaf(dx, dx, a0);
+                                a1 = fmaf(dy, dy, a1);
+                                a0 = fmaf(dz, dz, a0);
+                                a1 = fmaf(dw, dw, a1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < NJ; ++jj) {
+                                a0 = fmaf(qv[jj].x, v[i][jj].x, a0);
+                                a1 = fmaf(qv[jj].y, v[i][jj].y, a1);
+                                a0 = fmaf(qv[jj].z, v[i][jj].z, a0);
+                                a1 = fmaf(qv[jj].w, v[i][jj].w, a1);
+                            }
+                        }
+                        float tot = a0 + a1;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                        if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
+                        if (tot <= thr && lane == 0) {
+                            const uint32_t lr = row_base + r0 + r;  // list-relative row
+                            uint64_t id = page_ids ? page_ids[r0 + r] : (p.lt.ids_flat ? p.lt.ids_flat[lr] : lr);
+                            uint32_t pos = atomicAdd(&s.cnt[j], 1u);
+                            over |= (pos >= limit);
+                            if (pos < p.P) {
+                                s.pool_d[(size_t)j * p.P + pos] = tot;
+                                s.pool_i[(size_t)j * p.P + pos] = id;
+                            }
+                        }
+                    }
+                }
+
+                if (++since_check == p.check_interval) {
+                    since_check = 0;
+                    // counts only grow between checks, so some pool passed the mark iff some thread saw it
+                    const bool need = consumer_bar_or(over);
+                    over = false;
+                    if (need) {
+                        for (uint32_t j = warp; j < qcount; j += CONSUMER_WARPS)
+                            if (s.cnt[j] > limit) compact_pool(s, p, j, lane);
+                        consumer_bar();
+                    }
+                }
+            }
+        }
+
+        // item done: best k of every query of the tile -> its partial-result slot
+        consumer_bar();
+        for (uint32_t j = warp; j < qcount; j += CONSUMER_WARPS) {
+            compact_pool(s, p, j, lane);
+            const uint32_t nc = s.cnt[j];
+            const size_t slot = (size_t)p.pair_slot[s.spair[j]] + it.range;
+            for (uint32_t i = lane; i < p.k; i += 32) {
+                p.part_d[slot * p.k + i] = i < nc ? s.pool_d[(size_t)j * p.P + i] : FLT_MAX;
+                p.part_i[slot * p.k + i] = i < nc ? s.pool_i[(size_t)j * p.P + i] : ID_PAD;
+            }
+        }
+        consumer_bar();
+    }
+}
+
+__device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSmem& s) {
+    const uint32_t total = *p.totals;
+    const uint32_t ld = p.lt.ld;
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t ii = blockIdx.x; ii < total; ii += gridDim.x) {
+        const ScanItem it = p.items[ii];
+        const uint32_t l = it.list;
+        const uint32_t rows = p.lt.rows[l];
+        const uint32_t pg_first = p.lt.page_off[l];
+        const uint32_t pg0 = pg_first + it.range * p.ppi;
+        const uint32_t pgN = min(pg0 + p.ppi, p.lt.page_off[l + 1]);
+        for (uint32_t pg = pg0; pg < pgN; ++pg) {
+            const uint32_t row_base = (pg - pg_first) * p.lt.page_rows;
+            const uint32_t rows_in_page = min(p.lt.page_rows, rows - row_base);
+            const float* src = reinterpret_cast<const float*>(p.lt.page_vec[pg]);
+            for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
+                const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
+                const uint32_t bytes = nr * ld * 4;
+                mbar_wait(&s.empty[stage], phase ^ 1);
+                mbar_expect_tx(&s.full[stage], bytes);
+                tma_bulk_g2s(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
+                             &s.full[stage]);
+                if (++stage == p.S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const ScanSmem s = carve(smem_raw, p);
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < p.S; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < CONSUMER_THREADS) {
+        consumer_loop<NJ>(p, s);
+    } else if (threadIdx.x == CONSUMER_THREADS) {
+        producer_loop(p, s);
+    }
+}
+
+// ------------------------------------------------------------------ 3. merge
+
+struct MergeParams {
+    const float* part_d;
+    const uint64_t* part_i;
+    const uint32_t* pair_slot;  // null: `parts` mode, slot(q, p) = p * nq + q, one slot per pair
+    uint32_t nq, np, k, P;
+    float* out_d;
+    uint64_t* out_i;
+    uint32_t* out_u32;
+};
+
+constexpr int MERGE_THREADS = 256;
+
+struct MergePool {
+    float* d;
+    uint64_t* id;
+    uint32_t* cnt;
+    float* thr;
+};
+
+__device__ __forceinline__ void pool_push_block(const MergePool& pl, uint32_t P, const float* src_d,
+                                                const uint64_t* src_i, uint32_t n) {
+    // all threads; caller guarantees cnt + n <= P
+    const float thr = *pl.thr;
+    for (uint32_t i = threadIdx.x; i < n; i += MERGE_THREADS) {
+        float d = src_d[i];
+        uint64_t id = src_i[i];
+        if (id == ID_PAD && d == FLT_MAX) continue;  // padding of a short partial
+        if (d <= thr) {
+            uint32_t pos = atomicAdd(pl.cnt, 1u);
+            if (pos < P) {
+                pl.d[pos] = d;
+                pl.id[pos] = id;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// sort the pool; optionally drop later occurrences of an id (merge_results
+// keeps the first = best); keep k; refresh the admission threshold.
+__device__ __forceinline__ void pool_compact_block(const MergePool& pl, uint32_t P, uint32_t k, bool dedup,
+                                                   float* tmp_d, uint64_t* tmp_i, uint32_t* s_scan) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t c = min(*pl.cnt, P);
+    const uint32_t n2 = dev_next_pow2(max(c, 1u));
+    for (uint32_t i = c + tid; i < n2; i += MERGE_THREADS) {
+        pl.d[i] = FLT_MAX;
+        pl.id[i] = ID_PAD;
+    }
+    __syncthreads();
+    bitonic_sort_pairs(pl.d, pl.id, n2, tid, MERGE_THREADS, [] { __syncthreads(); });
+    if (dedup && c > 1) {
+        // keep[i] = no earlier entry carries the same id; stable compaction through tmp
+        const uint32_t per = (c + MERGE_THREADS - 1) / MERGE_THREADS;
+        const uint32_t lo = min(tid * per, c), hi = min(lo + per, c);
+        uint32_t kept = 0;
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint64_t id = pl.id[i];
+            bool dup = false;
+            for (uint32_t j = 0; j < i; ++j)
+                if (pl.id[j] == id) {
+                    dup = true;
+                    break;
+                }
+            if (!dup) ++kept;
+        }
+        // block exclusive scan of kept (MERGE_THREADS = 256 threads)
+        const uint32_t lane = tid & 31, w = tid >> 5;
+        uint32_t x = kept;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_scan[w] = x;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int i = 0; i < MERGE_THREADS / 32; ++i) {
+                uint32_t t = s_scan[i];
+                s_scan[i] = run;
+                run += t;
+            }
+            s_scan[MERGE_THREADS / 32] = run;
+        }
+        __syncthreads();
+        uint32_t pos = s_scan[w] + x - kept;
+        const uint32_t total = s_scan[MERGE_THREADS / 32];
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint64_t id = pl.id[i];
+            bool dup = false;
+            for (uint32_t j = 0; j < i; ++j)
+                if (pl.id[j] == id) {
+                    dup = true;
+                    break;
+                }
+            if (!dup) {
+                tmp_d[pos] = pl.d[i];
+                tmp_i[pos] = id;
+                ++pos;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < total; i += MERGE_THREADS) {
+            pl.d[i] = tmp_d[i];
+            pl.id[i] = tmp_i[i];
+        }
+        c = total;
+        __syncthreads();
+    }
+    const uint32_t nc = min(c, k);
+    if (tid == 0) {
+        *pl.cnt = nc;
+        *pl.thr = (nc >= k) ? pl.d[k - 1] : INFINITY;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) uint8_t msmem[];
+    const uint32_t P = p.P, k = p.k;
+    uint64_t* i1 = (uint64_t*)msmem;
+    uint64_t* i2 = i1 + P;
+    uint64_t* i3 = i2 + P;  // scratch of the de-duplicating compaction
+    float* d1 = (float*)(i3 + P);
+    float* d2 = d1 + P;
+    float* d3 = d2 + P;
+    __shared__ uint32_t cnt1, cnt2;
+    __shared__ float thr1, thr2;
+    __shared__ uint32_t s_scan[MERGE_THREADS / 32 + 1];
+    const MergePool L1{d1, i1, &cnt1, &thr1};  // per-list multiset top-k
+    const MergePool L2{d2, i2, &cnt2, &thr2};  // across lists, de-duplicated
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        cnt2 = 0;
+        thr2 = INFINITY;
+    }
+    __syncthreads();
+
+    for (uint32_t pr = 0; pr < p.np; ++pr) {
+        uint32_t slot0, ns;
+        if (p.pair_slot) {
+            const uint32_t pair = q * p.np + pr;
+            slot0 = p.pair_slot[pair];
+            ns = p.pair_slot[pair + 1] - slot0;
+        } else {
+            slot0 = pr * p.nq + q;
+            ns = 1;
+        }
+        if (ns == 0) continue;
+        const float* src_d = p.part_d + (size_t)slot0 * k;
+        const uint64_t* src_i = p.part_i + (size_t)slot0 * k;
+        if (ns > 1) {
+            // level 1: the list's page partials -> its top-k, duplicates kept
+            if (tid == 0) {
+                cnt1 = 0;
+                thr1 = INFINITY;
+            }
+            __syncthreads();
+            for (uint32_t sidx = 0; sidx < ns; ++sidx) {
+                if (cnt1 + k > P) pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+                pool_push_block(L1, P, src_d + (size_t)sidx * k, src_i + (size_t)sidx * k, k);
+            }
+            pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+            src_d = d1;
+            src_i = i1;
+        }
+        // level 2
+        const uint32_t n = (ns > 1) ? cnt1 : k;
+        if (cnt2 + n > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+        pool_push_block(L2, P, src_d, src_i, n);
+    }
+    pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+    const uint32_t nc = cnt2;
+    for (uint32_t i = tid; i < k; i += MERGE_THREADS) {
+        const float d = i < nc ? d2[i] : FLT_MAX;
+        const uint64_t id = i < nc ? i2[i] : ID_PAD;
+        p.out_d[(size_t)q * k + i] = d;
+        p.out_i[(size_t)q * k + i] = id;
+        if (p.out_u32) p.out_u32[(size_t)q * k + i] = (id == ID_PAD) ? 0xffffffffu : (uint32_t)id;
+    }
+}
+
+uint32_t merge_pool_size(uint32_t k) { return next_pow2(k * 2 < 64 ? 64 : k * 2); }
+
+template <int NJ>
+int32_t launch_scan(const ScanParams& sp, uint32_t grid, uint32_t smem, cudaStream_t stream) {
+    static bool configured[8] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && !configured[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(scan_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)SMEM_BUDGET));
+        configured[dev] = true;
+    }
+    scan_kernel<NJ><<<grid, SCAN_THREADS, smem, stream>>>(sp);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+}  // namespace
+
+int32_t scan_max_k() { return (int32_t)MAX_K; }
+
+int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k) {
+    cudaGetDevice(&device);
+    if (nlists + 1 > cap_lists) {
+        cudaFree(gcount); cudaFree(gfill); cudaFree(goff); cudaFree(ioff);
+        cap_lists = nlists + 1;
+        VDB_CUDA_TRY(cudaMalloc(&gcount, cap_lists * 4));
+        VDB_CUDA_TRY(cudaMalloc(&gfill, cap_lists * 4));
+        VDB_CUDA_TRY(cudaMalloc(&goff, cap_lists * 4));
+        VDB_CUDA_TRY(cudaMalloc(&ioff, cap_lists * 4));
+    }
+    if (npairs + 1 > cap_pairs) {
+        cudaFree(gpairs); cudaFree(pair_slot);
+        cap_pairs = npairs + 1;
+        VDB_CUDA_TRY(cudaMalloc(&gpairs, (size_t)cap_pairs * 4));
+        VDB_CUDA_TRY(cudaMalloc(&pair_slot, (size_t)cap_pairs * 4));
+    }
+    if (nslots > cap_slots) {
+        cudaFree(items);
+        cap_slots = nslots + nslots / 4 + 64;
+        VDB_CUDA_TRY(cudaMalloc(&items, cap_slots * sizeof(ScanItem)));
+    }
+    if (cap_slots * k > cap_part) {
+        cudaFree(part_d); cudaFree(part_i);
+        cap_part = cap_slots * k;
+        VDB_CUDA_TRY(cudaMalloc(&part_d, cap_part * 4));
+        VDB_CUDA_TRY(cudaMalloc(&part_i, cap_part * 8));
+    }
+    if (!totals) {
+        VDB_CUDA_TRY(cudaMalloc(&totals, 4 * 4));
+        VDB_CUDA_TRY(cudaMalloc(&stats, 4 * 8));
+        VDB_CUDA_TRY(cudaMemset(stats, 0, 4 * 8));
+    }
+    bytes = (uint64_t)cap_lists * 16 + (uint64_t)cap_pairs * 8 + cap_slots * sizeof(ScanItem) + cap_part * 12 + 48;
+    return VDB_OK;
+}
+
+void ScanWorkspace::release() {
+    cudaFree(gcount); cudaFree(gfill); cudaFree(goff); cudaFree(ioff);
+    cudaFree(gpairs); cudaFree(pair_slot); cudaFree(items);
+    cudaFree(part_d); cudaFree(part_i); cudaFree(totals); cudaFree(stats);
+    *this = ScanWorkspace();
+}
+
+int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
+                    uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
+                    float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
+                    ScanLaunchInfo* info, cudaEvent_t* ev) {
+    VDB_REQUIRE(k >= 1 && k <= MAX_K, "k must be in [1, 2048]");
+    VDB_REQUIRE(lt.ld % 4 == 0 && lt.ld >= 4 && lt.ld <= 2048, "row stride must be a multiple of 4 floats, <= 2048");
+    VDB_REQUIRE(lt.page_rows % STAGE_ROWS == 0, "page_rows must be a multiple of 16");
+    VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "metric must be L2 or InnerProduct");
+    VDB_REQUIRE(nq >= 1 && np >= 1 && ppi >= 1, "empty search");
+    const uint64_t npairs64 = (uint64_t)nq * np;
+    VDB_REQUIRE(npairs64 < (1ull << 31) && max_slots < (1ull << 31), "search too large for one call");
+    const uint32_t npairs = (uint32_t)npairs64;
+
+    // shared-memory plan: pool size P, query tile QT, ring depth S
+    uint32_t P = next_pow2(std::max(k + 64, 2 * k));
+    uint32_t S = 4, QT = MAX_QT;
+    auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P) <= SMEM_BUDGET; };
+    while (QT > 1 && !fits(2, QT)) QT >>= 1;
+    VDB_REQUIRE(fits(2, QT), "dimension * k too large for the scan kernel's shared memory");
+    while (S > 2 && !fits(S, QT)) --S;
+    // prefer a deeper ring over a wider tile when the tile is large anyway
+    while (S < 3 && QT > 4 && fits(S + 1, QT / 2)) { QT >>= 1; ++S; }
+    const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
+    const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P);
+
+    VDB_TRY(ws.reserve(lt.nlist, npairs, std::max<uint64_t>(max_slots, 1), k));
+
+    WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats};
+    if (ev) cudaEventRecord(ev[0], stream);
+    build_groups_kernel<<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, QT, ppi, wl);
+    VDB_CUDA_TRY(cudaGetLastError());
+
+    ScanParams sp;
+    sp.lt = lt;
+    sp.queries = queries_dev;
+    sp.items = ws.items;
+    sp.totals = ws.totals;
+    sp.gpairs = ws.gpairs;
+    sp.pair_slot = ws.pair_slot;
+    sp.part_d = ws.part_d;
+    sp.part_i = ws.part_i;
+    sp.k = k; sp.P = P; sp.QT = QT; sp.ppi = ppi; sp.S = S; sp.np = np;
+    sp.check_interval = check_interval;
+    sp.metric = metric;
+
+    int dev = 0, sms = NUM_SMS_B200;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, std::max<uint64_t>(max_slots, 1));
+    const uint32_t nj_need = (lt.ld / 4 + 31) / 32;
+    uint32_t NJ;
+    if (ev) cudaEventRecord(ev[1], stream);
+    if (nj_need <= 1) { NJ = 1; VDB_TRY(launch_scan<1>(sp, grid, smem, stream)); }
+    else if (nj_need <= 2) { NJ = 2; VDB_TRY(launch_scan<2>(sp, grid, smem, stream)); }
+    else if (nj_need <= 4) { NJ = 4; VDB_TRY(launch_scan<4>(sp, grid, smem, stream)); }
+    else if (nj_need <= 6) { NJ = 6; VDB_TRY(launch_scan<6>(sp, grid, smem, stream)); }
+    else if (nj_need <= 8) { NJ = 8; VDB_TRY(launch_scan<8>(sp, grid, smem, stream)); }
+    else if (nj_need <= 12) { NJ = 12; VDB_TRY(launch_scan<12>(sp, grid, smem, stream)); }
+    else { NJ = 16; VDB_TRY(launch_scan<16>(sp, grid, smem, stream)); }
+
+    if (ev) cudaEventRecord(ev[2], stream);
+    MergeParams mp;
+    mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot;
+    mp.nq = nq; mp.np = np; mp.k = k; mp.P = merge_pool_size(k);
+    mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = out_u32;
+    const uint32_t msmem = mp.P * 36;
+    static bool mconf[8] = {false};
+    if (dev < 8 && !mconf[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36));
+        mconf[dev] = true;
+    }
+    merge_kernel<<<nq, MERGE_THREADS, msmem, stream>>>(mp);
+    VDB_CUDA_TRY(cudaGetLastError());
+    if (ev) cudaEventRecord(ev[3], stream);
+    if (info) *info = ScanLaunchInfo{QT, P, S, NJ, grid, smem, check_interval};
+    return VDB_OK;
+}
+
+int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts, uint32_t nq, uint32_t k,
+                    float* out_d, uint64_t* out_i, cudaStream_t stream) {
+    VDB_REQUIRE(k >= 1 && k <= MAX_K && parts >= 1 && nq >= 1, "merge: bad shape");
+    MergeParams mp;
+    mp.part_d = dparts; mp.part_i = iparts; mp.pair_slot = nullptr;
+    mp.nq = nq; mp.np = parts; mp.k = k; mp.P = merge_pool_size(k);
+    mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36));
+    merge_kernel<<<nq, MERGE_THREADS, mp.P * 36, stream>>>(mp);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+}  // namespace vdb

@@ -1,0 +1,55 @@
+// Host-visible interface of the scan engine (scan.cu): probe grouping, the
+// persistent list-scan kernel with fused top-k, and the (dist,id) merge.
+#pragma once
+#include "common.cuh"
+
+namespace vdb {
+
+// One unit of scan work: `qcount` queries (pairs gpairs[gbase..gbase+qcount))
+// against page range `range` of list `list`.
+struct ScanItem {
+    uint32_t list, gbase, qcount, range;
+};
+
+// Device scratch of one search call.  Grown on demand, reused across calls.
+struct ScanWorkspace {
+    int device = 0;
+    // per-list arrays (sized nlist+1)
+    uint32_t *gcount = nullptr, *gfill = nullptr, *goff = nullptr, *ioff = nullptr;
+    uint32_t cap_lists = 0;
+    // per-pair arrays
+    uint32_t *gpairs = nullptr, *pair_slot = nullptr;
+    uint32_t cap_pairs = 0;
+    // items / partial results
+    ScanItem* items = nullptr;
+    float* part_d = nullptr;
+    uint64_t* part_i = nullptr;
+    uint64_t cap_slots = 0, cap_part = 0;
+    uint32_t* totals = nullptr;             // [0] items, [1] slots
+    unsigned long long* stats = nullptr;    // [0] algorithmic rows, [1] unique rows
+    uint64_t bytes = 0;
+
+    int32_t reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k);
+    void release();
+};
+
+struct ScanLaunchInfo {
+    uint32_t QT, P, S, NJ, grid, smem_bytes, check_interval;
+};
+
+// probes_dev: [nq][np] list ids (entries >= nlist or naming empty lists are
+// skipped).  max_slots: caller's upper bound on sum over pairs of page ranges.
+// ppi: pages per scan item.  Results (device): out_d/out_i [nq][k]; optional
+// out_u32 receives the ids narrowed to 32 bits (probe lists).
+int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
+                    uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
+                    float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
+                    ScanLaunchInfo* info = nullptr, cudaEvent_t* ev = nullptr);  // ev[0..3]: start, scan start, scan end, merge end
+
+// merge_results across `parts` blocks of [nq][k]
+int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts, uint32_t nq, uint32_t k,
+                    float* out_d, uint64_t* out_i, cudaStream_t stream);
+
+int32_t scan_max_k();
+
+}  // namespace vdb

@@ -1,0 +1,190 @@
+/*
+ * vdb_b200.h -- C ABI of the B200-native IVF-Flat hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, POD arguments, an
+ * int32 status return, no exceptions and no torch / C++ types in any
+ * signature.  Each entry point names the reference interface it replaces
+ * (wedevxer/CUDA-AcceleratedVectorDatabaseEngine, file:line).  The reference's
+ * host object links against exactly two kernel launchers and seven
+ * TransferManager methods; the C++ mirror of vdb::IVFFlatIndex
+ * in cuda-acceleratedvectordatabaseengine_b200/host/ and the ctypes binding in
+ * cuda-acceleratedvectordatabaseengine_b200/__init__.py sit on top of this
+ * header and nothing else.
+ *
+ * Pointer rules: every `const float*` / `const uint64_t*` input and every
+ * output array may be HOST or DEVICE memory unless the name says `_dev`
+ * (cudaPointerGetAttributes decides); inputs are borrowed for the duration of
+ * the call, outputs are caller-allocated, the library owns all HBM it
+ * allocates.  There is no CPU fallback anywhere: a missing device or a failed
+ * launch is reported as a status code.
+ */
+#ifndef VDB_B200_H
+#define VDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VDB_OK = 0,
+    VDB_INVALID_ARGUMENT = 1, /* ctor's std::invalid_argument, ivf_flat_index.cpp:17-19 */
+    VDB_OUT_OF_MEMORY = 2,    /* pool alloc returning nullptr, transfer_manager.cpp:125 */
+    VDB_CUDA_ERROR = 3,       /* cudaGetLastError polling, ivf_flat_index.cpp:575 */
+    VDB_NCCL_ERROR = 4,
+    VDB_NOT_TRAINED = 5,
+    VDB_INTERNAL = 6
+} vdb_status;
+
+/* kernels.cuh:24-28.  L2 is the SQUARED distance, InnerProduct is -dot. */
+typedef enum { VDB_METRIC_L2 = 0, VDB_METRIC_IP = 1, VDB_METRIC_COSINE = 2 } vdb_metric;
+
+/* EXACT reproduces the reference's fp32 summation order in k-means++ seeding,
+ * assignment and centroid update bit for bit; FAST uses parallel reductions
+ * (and, where enabled, the tensor-core assignment) and agrees statistically.
+ * AUTO = EXACT while n * nlist * dim is small. */
+typedef enum { VDB_TRAIN_AUTO = 0, VDB_TRAIN_EXACT = 1, VDB_TRAIN_FAST = 2 } vdb_train_mode;
+
+/* How the query x centroid coarse distances are produced:
+ * SIMT   exact fp32 scan kernel (same kernel as the list scan);
+ * TENSOR tcgen05 TF32 contraction + exact fp32 re-check of every candidate
+ *        within the rounding-error bound of the nprobe-th distance. */
+typedef enum { VDB_COARSE_AUTO = 0, VDB_COARSE_SIMT = 1, VDB_COARSE_TENSOR = 2 } vdb_coarse_mode;
+
+/* IVFFlatIndex::Config, ivf_flat_index.h:16-22 (dimension, nlist, metric,
+ * max_gpu_memory keep their meaning; use_gpu has no counterpart: there is no
+ * CPU path).  Zero-initialise and call vdb_config_default() first. */
+typedef struct {
+    uint32_t dimension;
+    uint32_t nlist;
+    int32_t metric;          /* vdb_metric */
+    int32_t device;          /* CUDA device ordinal */
+    uint64_t max_gpu_memory; /* cap on HBM owned by this index, 0 = no cap (ivf_flat_index.h:21) */
+    int32_t train_mode;      /* vdb_train_mode */
+    int32_t coarse_mode;     /* vdb_coarse_mode */
+    uint32_t page_rows;      /* rows per inverted-list page, 0 = auto */
+    uint32_t shard_rank;     /* this process owns lists l with l % shard_count == shard_rank */
+    uint32_t shard_count;    /* 1 = unsharded */
+    uint32_t reserved[5];
+} vdb_config;
+
+typedef struct {
+    uint64_t total_vectors;      /* get_total_vectors(), ivf_flat_index.h:64 (all shards' adds seen by this rank) */
+    uint64_t local_vectors;      /* rows resident on this device */
+    uint64_t gpu_memory_bytes;   /* get_gpu_memory_usage(), ivf_flat_index.cpp:707-709 */
+    uint64_t pages;              /* inverted-list pages in use */
+    uint32_t dimension, nlist, row_stride, page_rows;
+    int32_t trained;
+    int32_t reserved;
+} vdb_stats;
+
+/* Byte accounting of the most recent search: probed rows summed
+ * per query (algorithmic) and over distinct probed lists (unique). */
+typedef struct {
+    uint64_t algorithmic_rows;
+    uint64_t unique_rows;
+    uint64_t scan_items;
+    uint64_t bytes_per_row; /* 4*dim + 8 */
+} vdb_search_stats;
+
+typedef struct vdb_index vdb_index;
+typedef struct vdb_arena vdb_arena;
+
+const char* vdb_last_error_string(void);
+const char* vdb_status_string(int32_t status);
+int32_t vdb_version(void);
+
+void vdb_config_default(vdb_config* cfg);
+
+/* IVFFlatIndex::IVFFlatIndex(const Config&, TransferManager*), ivf_flat_index.cpp:13-33 */
+int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out);
+/* IVFFlatIndex::~IVFFlatIndex, ivf_flat_index.cpp:36-46 */
+int32_t vdb_index_destroy(vdb_index* ix);
+
+/* IVFFlatIndex::train, ivf_flat_index.cpp:49-145: k-means++ (mt19937(42)) +
+ * 10 Lloyd iterations, all on the device. */
+int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n);
+/* IVFFlatIndex::add, ivf_flat_index.cpp:148-202: assign + append. */
+int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n);
+/* IVFFlatIndex::search, ivf_flat_index.cpp:205-256.  distances/indices are
+ * [nq][k]; missing results are padded FLT_MAX / UINT64_MAX (:380-383,:514-517).
+ * nprobe is clamped to nlist.  Thread-safe against concurrent searches. */
+int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
+                         float* distances, uint64_t* indices);
+/* Same, device pointers only, enqueued on `stream` (a cudaStream_t) without a
+ * host synchronisation: the form the sharded path and the benchmark use. */
+int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe,
+                               uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
+/* select_nprobe_lists, ivf_flat_index.cpp:298-336: [nq][min(nprobe,nlist)] list ids. */
+int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe,
+                                uint32_t* lists);
+/* assign_to_lists, ivf_flat_index.cpp:259-295. */
+int32_t vdb_index_assign(vdb_index* ix, const float* vectors, uint64_t n, uint32_t* lists);
+
+/* Test hooks / persistence seam: centroids_ is [nlist][dimension] fp32 row-major. */
+int32_t vdb_index_get_centroids(vdb_index* ix, float* out);
+int32_t vdb_index_set_centroids(vdb_index* ix, const float* in);
+int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out /* [nlist] */);
+int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out /* [list size] */);
+int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out);
+int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out);
+/* Profiling for the roofline report: when enabled, CUDA events on the launching
+ * stream bracket, for every search, [0] the coarse step, [1] probe grouping,
+ * [2] the list-scan kernel, [3] the merge.  read_profile synchronises, returns
+ * the summed milliseconds since the last call and the number of searches. */
+int32_t vdb_index_set_profiling(vdb_index* ix, int32_t enable);
+int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms /* [4] */, uint32_t* searches);
+/* warmup_lists()/warmup_all() of the server contract (query_service.cpp:191,195):
+ * lists are always HBM-resident here, so this only validates ids. */
+int32_t vdb_index_warmup(vdb_index* ix, const uint32_t* lists, uint32_t n);
+
+/* kernels::launch_bruteforce_search<float>, kernels.cu:13-43 / kernels.cuh:391-396:
+ * exact top-k of nq queries against a flat [n][dim] row-major database.
+ * ids may be NULL (row number is the id).  k is not capped at 32. */
+int32_t vdb_bruteforce_search(const float* database, const float* queries, const uint64_t* ids, uint64_t n,
+                              uint32_t nq, uint32_t dim, uint32_t k, float* distances, uint64_t* indices,
+                              int32_t metric, void* stream);
+/* kernels::launch_kmeans_assign<float>, kernels.cu:80-92 / kernels.cuh:410-414.
+ * The reference kernel is L2-only; `metric` follows the CPU path instead
+ * (ivf_flat_index.cpp:275-285).  distances may be NULL. */
+int32_t vdb_kmeans_assign(const float* vectors, const float* centroids, uint32_t* assignments, float* distances,
+                          uint64_t n, uint32_t n_centroids, uint32_t dim, int32_t metric, void* stream);
+/* Data-parallel k-means building blocks (device pointers): per-cluster fp32
+ * sums / counts of this rank's rows, and the division step after the caller
+ * has all-reduced them (ivf_flat_index.cpp:123-141). */
+int32_t vdb_kmeans_accumulate(const float* vectors_dev, const uint32_t* assignments_dev, uint64_t n,
+                              uint32_t n_centroids, uint32_t dim, float* sums_dev, uint32_t* counts_dev,
+                              void* stream);
+int32_t vdb_kmeans_finalize(const float* sums_dev, const uint32_t* counts_dev, float* centroids_dev,
+                            uint32_t n_centroids, uint32_t dim, void* stream);
+/* merge_results, ivf_flat_index.cpp:474-518, across shards: `parts` blocks of
+ * [nq][k] (as produced by an all-gather of every rank's local top-k) -> [nq][k]
+ * by (distance, id), duplicates removed, padded.  Device pointers. */
+int32_t vdb_merge_topk(const float* dist_parts_dev, const uint64_t* id_parts_dev, uint32_t parts, uint32_t nq,
+                       uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
+
+/* TransferManager rewrite (transfer_manager.h:42-88): one HBM slab and one
+ * pinned slab carved by a best-fit allocator, a stream pool, async copies. */
+int32_t vdb_arena_create(int32_t device, uint64_t device_bytes, uint64_t pinned_bytes, int32_t num_streams,
+                         vdb_arena** out);
+int32_t vdb_arena_destroy(vdb_arena* a);
+void* vdb_arena_allocate_device(vdb_arena* a, uint64_t bytes);  /* allocate_device */
+int32_t vdb_arena_free_device(vdb_arena* a, void* p);           /* free_device */
+void* vdb_arena_allocate_pinned(vdb_arena* a, uint64_t bytes);  /* allocate_pinned */
+int32_t vdb_arena_free_pinned(vdb_arena* a, void* p);           /* free_pinned */
+void* vdb_arena_get_stream(vdb_arena* a);                       /* get_stream */
+int32_t vdb_arena_return_stream(vdb_arena* a, void* stream);    /* return_stream */
+/* enqueue_transfer: kind 1 = H2D, 2 = D2H, 3 = D2D (cudaMemcpyKind values) */
+int32_t vdb_arena_enqueue_transfer(vdb_arena* a, void* dst, const void* src, uint64_t bytes, int32_t kind,
+                                   void* stream);
+int32_t vdb_arena_synchronize(vdb_arena* a);                     /* synchronize */
+int32_t vdb_arena_synchronize_stream(vdb_arena* a, void* stream); /* synchronize_stream */
+/* out[0..3] = device bytes in use, device peak, pinned in use, live allocations */
+int32_t vdb_arena_stats(vdb_arena* a, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDB_B200_H */

@@ -1,0 +1,272 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes
+through the C ABI (libvdb_b200.so); the oracle is only the checker."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from parity import check_search, ip_scale, FLT_MAX, ID_PAD
+
+pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["simple_test", "ctest_gpu_vs_cpu", "small_ip", "config1"]
+
+
+def load_case(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    seed, n, dim, nlist, ntrain, nq, nprobe, k, metric = (int(v) for v in g["params"])
+    x = O.gaussian(seed, n + nq, dim)
+    return g, x[:n], x[n:], dict(dim=dim, nlist=nlist, ntrain=ntrain, nprobe=nprobe, k=k, metric=metric)
+
+
+def new_index(dim, nlist, metric=0, **kw):
+    return pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist, metric=pkg.Metric(metric), **kw))
+
+
+def scale_for(metric, q, db):
+    return ip_scale(q, db) if metric == O.METRIC_IP else None
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_search_with_reference_centroids_matches_golden(name):
+    """centroids imported from the reference, so coarse + add + scan + merge are isolated from training"""
+    g, db, q, p = load_case(name)
+    ix = new_index(p["dim"], p["nlist"], p["metric"])
+    ix.centroids = g["centroids"]
+    ix.add(db)
+    assert np.array_equal(ix.list_sizes(), g["list_sizes"]), "assignment differs from the reference"
+    assert ix.get_total_vectors() == db.shape[0]
+    probes = ix.select_nprobe(q, p["nprobe"])
+    # coarse order is (dist, list id); a swap is only legal between near-equal centroid distances
+    diff = (probes != g["probes"]).any(axis=1).sum()
+    assert diff <= 1, f"{diff} queries with different probe lists"
+    D, I = ix.search(q, pkg.SearchParams(nprobe=p["nprobe"], k=p["k"]))
+    ties = check_search(D, I, g["D"], g["I"], scale=scale_for(p["metric"], q, db))
+    assert ties <= 2
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_is_bit_exact(name):
+    """k-means++ (mt19937(42)) + 10 Lloyd iterations on the device == the reference's CPU train()"""
+    g, db, q, p = load_case(name)
+    ix = new_index(p["dim"], p["nlist"], p["metric"])
+    ix.train(db[: p["ntrain"]])
+    c = ix.centroids
+    assert np.array_equal(c, g["centroids"]), f"max |diff| {np.abs(c - g['centroids']).max()}"
+
+
+def test_full_pipeline_config1():
+    """BASELINE.json configs[0]: train + add + search all on the GPU vs the reference's outputs"""
+    g, db, q, p = load_case("config1")
+    ix = new_index(p["dim"], p["nlist"], p["metric"])
+    ix.train(db[: p["ntrain"]])
+    ix.add(db, np.arange(db.shape[0], dtype=np.uint64))
+    D, I = ix.search(q, pkg.SearchParams(nprobe=p["nprobe"], k=p["k"]))
+    check_search(D, I, g["D"], g["I"])
+    st = ix.last_search_stats()
+    sizes = g["list_sizes"].astype(np.int64)
+    assert st.algorithmic_rows == int(sizes[g["probes"]].sum())
+    assert st.unique_rows == int(sizes[np.unique(g["probes"])].sum())
+    assert ix.get_gpu_memory_usage() > db.nbytes
+
+
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+@pytest.mark.parametrize("dim", [3, 17, 100, 260])
+def test_odd_dimensions_and_multiple_adds(metric, dim):
+    rng = np.random.default_rng(dim)
+    n, nlist, nq = 3000, 12, 20
+    x = O.gaussian(100 + dim, n + nq, dim)
+    db, q = x[:n], x[n:]
+    ora = O.OracleIndex(dim, nlist, metric)
+    ora.train(db[:1500])
+    ix = new_index(dim, nlist, metric)
+    ix.train(db[:1500])
+    assert np.array_equal(ix.centroids, ora.centroids)
+    ids = (rng.permutation(n) + 10_000_000_000).astype(np.uint64)  # ids beyond 32 bits
+    for lo in range(0, n, 700):
+        ora.add(db[lo:lo + 700], ids[lo:lo + 700])
+        ix.add(db[lo:lo + 700], ids[lo:lo + 700])
+    assert np.array_equal(ix.list_sizes(), ora.list_sizes())
+    for l in range(nlist):
+        assert np.array_equal(np.sort(ix.list_ids(l)), np.sort(ora.list_ids(l)))
+    assert np.array_equal(ix.assign(q), ora.assign(q))
+    for nprobe, k in [(1, 1), (4, 10), (nlist, 33), (nlist + 7, 100)]:
+        Dr, Ir = ora.search(q, nprobe, k)
+        D, I = ix.search(q, nprobe, k)
+        check_search(D, I, Dr, Ir, scale=scale_for(metric, q, db))
+
+
+def test_edge_cases():
+    dim, nlist = 8, 6
+    x = O.gaussian(3, 40, dim)
+    cent = O.gaussian(4, nlist, dim)
+    ora = O.OracleIndex(dim, nlist)
+    ora.centroids = cent
+    ix = new_index(dim, nlist)
+    ix.centroids = cent
+    # empty index: everything padded (ivf_flat_index.cpp:514-517)
+    D, I = ix.search(x[:2], 3, 4)
+    assert (I == ID_PAD).all() and (D == FLT_MAX).all()
+    # duplicate ids, inside one list and across lists: merge_results de-duplicates (:496-504)
+    ids = np.arange(40, dtype=np.uint64) % 13
+    ora.add(x, ids)
+    ix.add(x, ids)
+    for nprobe, k in [(6, 5), (6, 40), (2, 3), (1, 1)]:
+        Dr, Ir = ora.search(x[:7], nprobe, k)
+        D, I = ix.search(x[:7], nprobe, k)
+        check_search(D, I, Dr, Ir)
+    with pytest.raises(ValueError):
+        ix.search(x[:1], 3, 0)
+    with pytest.raises(ValueError):
+        ix.search(x[:1], 3, 5000)
+
+
+def test_large_k_and_skewed_lists():
+    """k = 1000 (the server's topk cap, query_service.cpp:77) on lists spanning several pages"""
+    dim, nlist, n, nq = 32, 4, 9000, 6
+    x = O.clustered(11, n + nq, dim, n_centers=3, spread=0.3)
+    db, q = x[:n], x[n:]
+    ora = O.OracleIndex(dim, nlist)
+    ora.train(db[:2000])
+    ix = new_index(dim, nlist, page_rows=256)
+    ix.centroids = ora.centroids
+    ora.add(db)
+    ix.add(db)
+    assert np.array_equal(ix.list_sizes(), ora.list_sizes())
+    for nprobe, k in [(2, 1000), (4, 300), (4, 2048)]:
+        Dr, Ir = ora.search(q, nprobe, k)
+        D, I = ix.search(q, nprobe, k)
+        check_search(D, I, Dr, Ir)
+
+
+def test_clustered_small_distances():
+    """distances much smaller than the vector norms: the exact (q-v)^2 form must keep 1e-5"""
+    dim, nlist, n, nq = 64, 16, 20000, 32
+    x = O.clustered(5, n + nq, dim, n_centers=40, spread=0.01)
+    db, q = x[:n], x[n:]
+    ora = O.OracleIndex(dim, nlist)
+    ora.train(db[:4000])
+    ix = new_index(dim, nlist)
+    ix.centroids = ora.centroids
+    ora.add(db)
+    ix.add(db)
+    Dr, Ir = ora.search(q, 4, 10)
+    D, I = ix.search(q, 4, 10)
+    check_search(D, I, Dr, Ir)
+
+
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+def test_bruteforce_matches_flat_oracle(metric):
+    """launch_bruteforce_search replacement: exact top-k, k = 100 > the reference kernel's cap of 32"""
+    n, dim, nq, k = 10007, 96, 37, 100
+    x = O.gaussian(21, n + nq, dim)
+    db, q = x[:n], x[n:]
+    ids = (np.arange(n, dtype=np.uint64) * 3 + 7)
+    Dr, Ir = O.flat_search(db, q, k, metric, ids)
+    D, I = pkg.bruteforce_search(db, q, k, pkg.Metric(metric), ids)
+    check_search(D, I, Dr, Ir, scale=scale_for(metric, q, db))
+    Dr, Ir = O.flat_search(db, q[:5], 7, metric)
+    D, I = pkg.bruteforce_search(db, q[:5], 7, pkg.Metric(metric))
+    check_search(D, I, Dr, Ir, scale=scale_for(metric, q[:5], db))
+
+
+def test_bruteforce_768d_many_queries():
+    """configs[1] shape at reduced N: 768-D, 256 queries, k = 100"""
+    n, dim, nq, k = 20000, 768, 256, 100
+    x = O.gaussian(33, n + nq, dim)
+    db, q = x[:n], x[n:]
+    Dr, Ir = O.flat_search(db, q[:24], k)
+    D, I = pkg.bruteforce_search(db, q, k)
+    check_search(D[:24], I[:24], Dr, Ir)
+    # every row sorted by (distance, id)
+    assert (np.diff(D, axis=1) >= 0).all()
+
+
+def test_kmeans_assign_entry_point():
+    n, dim, nc = 5000, 40, 50
+    x = O.gaussian(8, n + nc, dim)
+    v, c = x[:n], x[n:]
+    for metric in (O.METRIC_L2, O.METRIC_IP):
+        ora = O.OracleIndex(dim, nc, metric)
+        ora.centroids = c
+        a, d = pkg.kmeans_assign(v, c, pkg.Metric(metric), want_distances=True)
+        assert np.array_equal(a, ora.assign(v))
+        assert np.isfinite(d).all()
+
+
+def test_ivf_full_probe_equals_bruteforce_768d():
+    """size-independent property: nprobe = nlist makes IVF exact; 768-D rows, lists over many pages"""
+    import torch
+    n, dim, nlist, nq, k = 60000, 768, 24, 64, 10
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    db = torch.randn(n, dim, generator=gen, device="cuda")
+    q = torch.randn(nq, dim, generator=gen, device="cuda")
+    ix = new_index(dim, nlist)
+    ix.train(db[:3000])
+    ix.add(db)  # device pointers straight in, ids default to the row number
+    assert int(ix.list_sizes().sum()) == n
+    D, I = ix.search(q, nlist, k)
+    Db, Ib = pkg.bruteforce_search(db, q, k)
+    assert torch.equal(I, Ib)
+    assert torch.allclose(D, Db, rtol=1e-6, atol=0)
+    # oracle spot check on 4 queries
+    Dr, Ir = O.flat_search(db.cpu().numpy(), q[:4].cpu().numpy(), k)
+    check_search(D[:4].cpu().numpy(), I[:4].cpu().numpy(), Dr, Ir)
+    # fewer probes: a subset of the candidates, so distances can only grow
+    D8, _ = ix.search(q, 8, k)
+    assert (D8 >= D - 1e-3).all()
+
+
+def test_merge_topk_entry_point():
+    import torch
+    parts, nq, k = 4, 9, 10
+    rng = np.random.default_rng(0)
+    d = np.sort(rng.random((parts, nq, k)).astype(np.float32), axis=2)
+    i = rng.integers(0, 50, (parts, nq, k)).astype(np.uint64)  # duplicates across parts on purpose
+    d[1, :, 7:] = FLT_MAX
+    i[1, :, 7:] = ID_PAD
+    D, I = pkg.merge_topk(torch.from_numpy(d).cuda(), torch.from_numpy(i.view(np.int64)).cuda())
+    D, I = D.cpu().numpy(), I.cpu().numpy().view(np.uint64)
+    for q in range(nq):
+        cand = sorted((float(dd), int(ii)) for p in range(parts) for dd, ii in zip(d[p, q], i[p, q]) if ii != ID_PAD)
+        seen, out = set(), []
+        for dd, ii in cand:
+            if ii not in seen:
+                seen.add(ii)
+                out.append((dd, ii))
+        out = out[:k]
+        assert [int(v) for v in I[q, :len(out)]] == [o[1] for o in out]
+        assert np.allclose(D[q, :len(out)], [o[0] for o in out])
+
+
+def test_arena():
+    import ctypes as C
+    l = pkg.lib()
+    a = C.c_void_p()
+    assert l.vdb_arena_create(0, 64 << 20, 16 << 20, 4, C.byref(a)) == 0
+    p1 = l.vdb_arena_allocate_device(a, 1000)
+    p2 = l.vdb_arena_allocate_device(a, 1 << 20)
+    h = l.vdb_arena_allocate_pinned(a, 4096)
+    assert p1 and p2 and h and p1 % 256 == 0 and p2 % 256 == 0
+    assert l.vdb_arena_allocate_device(a, 1 << 30) is None  # exhausted pool -> nullptr
+    src = (C.c_float * 256)(*range(256))
+    C.memmove(h, src, 1024)
+    s = l.vdb_arena_get_stream(a)
+    assert l.vdb_arena_enqueue_transfer(a, p1, h, 1024, 1, s) == 0
+    back = l.vdb_arena_allocate_pinned(a, 4096)
+    assert l.vdb_arena_enqueue_transfer(a, back, p1, 1024, 2, s) == 0
+    assert l.vdb_arena_synchronize_stream(a, s) == 0
+    assert l.vdb_arena_return_stream(a, s) == 0
+    out = (C.c_float * 256).from_address(back)
+    assert list(out) == list(range(256))
+    st = (C.c_uint64 * 4)()
+    l.vdb_arena_stats(a, st)
+    assert st[0] == 1024 + (1 << 20) and st[3] == 4
+    assert l.vdb_arena_free_device(a, p1) == 0 and l.vdb_arena_free_device(a, p2) == 0
+    assert l.vdb_arena_free_device(a, p2) != 0  # double free is reported
+    p3 = l.vdb_arena_allocate_device(a, 60 << 20)  # coalesced back into one block
+    assert p3
+    assert l.vdb_arena_destroy(a) == 0
