@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the IVF-Flat search hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    torchrun ... bench.py --gpus N --steps K --warmup W      # lists sharded over N GPUs, NCCL all-gather merge
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path, host cores
+
+A step = one search of one batch of 64 fresh synthetic queries against the
+10M x 768D L2 index (nlist 4096, nprobe 32, k 10) -- BASELINE.json configs[2],
+the configuration the metric is quoted on; it fits one GPU (31 GB of 180).
+Every batch streams far more list data than the 126 MB L2 holds, so no L2
+flush is needed between iterations.
+
+value   device-resident: queries and results in HBM, CUDA events, max over ranks
+e2e     host buffers through the C ABI call a user makes (vdb_index_search):
+        pinned H2D of the queries and D2H of ids+distances inside the timed region
+roofline  list-scan kernel: algorithmic bytes (sum over queries of probed rows x (4D+8),
+        SURVEY.md 8d) / its CUDA-event time, against the measured HBM copy bandwidth
+cpu_baseline  the reference's unmodified CPU search (oracle/_ref) on a bounded sample
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+PKG = "cuda-acceleratedvectordatabaseengine_b200"
+METRIC = "IVF-Flat QPS @10M x 768D nprobe=32 k=10"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--nlist", type=int, default=4096)
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--ntrain", type=int, default=262144)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"IVF-Flat {a.n / 1e6:g}M x {a.dim}D L2 nlist={a.nlist} nprobe={a.nprobe} k={a.k} batch={a.batch} "
+            f"(BASELINE.json configs[2])")
+
+
+# ---------------------------------------------------------------- clocks
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[5 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------- reference CPU arm
+
+def reference_sample(a, steps, warmup, max_seconds=150.0):
+    """The reference's CPU IVFFlatIndex::search (unmodified, oracle/_ref) on a bounded sample of the
+    workload: cpu_sample_n x dim rows, nlist scaled to keep the mean list length, same nprobe/k, every
+    host thread searching its own queries.  Index construction is NOT timed and uses numpy only."""
+    import numpy as np
+    import oracle_lib as O
+
+    ncores = os.cpu_count() or 1
+    ns = min(a.cpu_sample_n, a.n)
+    nlist_s = max(a.nprobe, int(round(a.nlist * ns / a.n)))
+    rng = np.random.default_rng(12345)
+    x = np.empty((ns, a.dim), np.float32)
+    for lo in range(0, ns, 100_000):
+        x[lo:lo + 100_000] = rng.standard_normal((min(100_000, ns - lo), a.dim), dtype=np.float32)
+    # centroids: sampled rows refined by two Lloyd passes on a subsample (BLAS), then one assignment of all rows
+    cent = x[rng.choice(ns, nlist_s, replace=False)].copy()
+    sub = x[: min(ns, 64 * nlist_s)]
+
+    def assign(v, c):
+        out = np.empty(v.shape[0], np.uint32)
+        cn = (c * c).sum(1)
+        for lo in range(0, v.shape[0], 50_000):
+            out[lo:lo + 50_000] = np.argmin(cn[None, :] - 2.0 * (v[lo:lo + 50_000] @ c.T), axis=1)
+        return out
+
+    for _ in range(2):
+        asg = assign(sub, cent)
+        cnt = np.bincount(asg, minlength=nlist_s)
+        sums = np.zeros_like(cent)
+        np.add.at(sums, asg, sub)
+        m = cnt > 0
+        cent[m] = sums[m] / cnt[m, None]
+    asg = assign(x, cent)
+    kind = "reference" if O.ref_lib() is not None else "port"
+    ix = (O.RefIndex if kind == "reference" else O.OracleIndex)(a.dim, nlist_s, O.METRIC_L2)
+    ix.centroids = cent
+    ix.load_assigned(x, np.arange(ns, dtype=np.uint64), asg)
+    sizes = ix.list_sizes().astype(np.int64)
+    nq_pool = a.batch * 4
+    q = rng.standard_normal((nq_pool, a.dim), dtype=np.float32)
+    # calibrate one query on one thread, then size the per-step sample
+    t = time.perf_counter()
+    ix.search(q[:1], a.nprobe, a.k, 1)
+    t_q = max(time.perf_counter() - t, 1e-4)
+    per_step = int(max_seconds * ncores / ((steps + warmup) * t_q))
+    per_step = max(min(per_step, a.batch), min(ncores, a.batch), 1)
+    probes = np.stack([ix.select_nprobe(q[i], a.nprobe) for i in range(min(nq_pool, 32))])
+    rows_per_query = float(sizes[probes].sum(1).mean())
+
+    def step(s, threads):
+        lo = (s * per_step) % (nq_pool - per_step + 1)
+        ix.search(q[lo:lo + per_step], a.nprobe, a.k, threads)
+
+    for s in range(warmup):
+        step(s, ncores)
+    t = time.perf_counter()
+    for s in range(steps):
+        step(warmup + s, ncores)
+    dt = time.perf_counter() - t
+    qps_all = per_step * steps / dt
+    # single-thread figure: the reference path as shipped (it has no threading)
+    n1 = max(1, min(per_step, int(10.0 / t_q)))
+    t = time.perf_counter()
+    ix.search(q[:n1], a.nprobe, a.k, 1)
+    qps_1 = n1 / (time.perf_counter() - t)
+    sample = (f"{ns} x {a.dim}D Gaussian, nlist={nlist_s} (mean list {ns / nlist_s:.0f} rows as in the full workload), "
+              f"nprobe={a.nprobe}, k={a.k}, {per_step} queries/step, {rows_per_query:.0f} probed rows/query; "
+              f"single-thread {qps_1:.2f} QPS")
+    return {"value": qps_all, "unit": "queries/s", "cores": ncores, "kind": kind, "sample": sample,
+            "single_thread_qps": qps_1, "rows_per_query": rows_per_query, "ms_per_step": dt / steps * 1e3,
+            "queries_per_step": per_step}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = reference_sample(a, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a)},
+            "cpu_baseline": {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------- B200 arm
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this implementation has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module(PKG)
+    pkg.lib()
+
+    # ---- build: synthetic N(0,1) rows generated on the device, trained + added by the CUDA path
+    t_build = time.perf_counter()
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, metric=pkg.Metric.L2, device=local,
+                                     shard_rank=rank, shard_count=world))
+    gen = torch.Generator(device=dev).manual_seed(12345)
+    chunk = 1_000_000
+    t_train = t_add = 0.0
+    for lo in range(0, a.n, chunk):
+        x = torch.randn(min(chunk, a.n - lo), a.dim, generator=gen, device=dev)
+        if lo == 0:
+            t = time.perf_counter()
+            ix.train(x[: min(a.ntrain, x.shape[0])])  # every rank trains on the same rows: identical centroids
+            t_train = time.perf_counter() - t
+        t = time.perf_counter()
+        ix.add(x)  # ids = row numbers; a sharded index keeps only the lists it owns
+        t_add += time.perf_counter() - t
+        del x
+    nb = a.warmup + a.steps
+    q_all = torch.randn(nb, a.batch, a.dim, generator=gen, device=dev)
+    t_build = time.perf_counter() - t_build
+    st = ix.stats()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    D = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
+    I = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
+    if world > 1:
+        Dg = torch.empty((world, a.batch, a.k), dtype=torch.float32, device=dev)
+        Ig = torch.empty((world, a.batch, a.k), dtype=torch.int64, device=dev)
+
+    def step_device(s):
+        ix.search_async(q_all[s], a.nprobe, a.k, D, I, stream)
+        if world > 1:  # every rank's local top-k -> all ranks, then merge by (distance, id)
+            dist.all_gather_into_tensor(Dg, D)
+            dist.all_gather_into_tensor(Ig, I)
+            return pkg.merge_topk(Dg, Ig, stream)
+        return D, I
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for s in range(a.warmup):
+        step_device(s)
+    sync_all()
+    ix.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for s in range(a.steps):
+        step_device(a.warmup + s)
+    e1.record()
+    sync_all()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    prof = ix.read_profile()
+    ix.set_profiling(False)
+    qps = a.batch * a.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers through the public call, copies inside the timed region
+    q_host = q_all.cpu().pin_memory()
+    Dh = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+    Ih = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
+
+    def step_e2e(s):
+        if world == 1:
+            ix.search(q_host[s], a.nprobe, a.k, distances=Dh, indices=Ih)  # H2D + search + D2H + sync inside
+        else:
+            qd = q_host[s].to(dev, non_blocking=True)
+            ix.search_async(qd, a.nprobe, a.k, D, I, stream)
+            dist.all_gather_into_tensor(Dg, D)
+            dist.all_gather_into_tensor(Ig, I)
+            Dm, Im = pkg.merge_topk(Dg, Ig, stream)
+            Dh.copy_(Dm, non_blocking=True)
+            Ih.copy_(Im, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for s in range(min(a.warmup, 5)):
+        step_e2e(s)
+    sync_all()
+    te = time.perf_counter()
+    for s in range(a.steps):
+        step_e2e(a.warmup + s)
+    sync_all()
+    te = torch.tensor([time.perf_counter() - te], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_qps = a.batch * a.steps / float(te.item())
+    clocks = sampler.stop(t0, time.time()) if sampler else None
+
+    # ---- byte accounting of the timed batches (untimed replay; stats come from the grouping kernel)
+    alg_rows = uniq_rows = items = 0
+    for s in range(a.steps):
+        ix.search_async(q_all[a.warmup + s], a.nprobe, a.k, D, I, stream)
+        ss = ix.last_search_stats()
+        alg_rows += ss.algorithmic_rows
+        uniq_rows += ss.unique_rows
+        items += ss.scan_items
+    bpr = 4 * a.dim + 8
+    peak, peak_src = measured_peak()
+    scan_ms = prof["scan_ms"] / max(prof["searches"], 1)
+    alg_bytes = alg_rows * bpr / a.steps
+    uniq_bytes = uniq_rows * bpr / a.steps
+    achieved = alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        r = reference_sample(a, steps=3, warmup=1, max_seconds=20.0)
+        cpu = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    line = {
+        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "parallelism": f"lists sharded over {world} GPU(s), l % {world}",
+                   "cache": f"inputs larger than L2: each batch streams {uniq_bytes / 1e9:.2f} GB of distinct list data",
+                   "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
+                   "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
+                   "index_gb": round(st.gpu_memory_bytes / 1e9, 2)},
+        "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "unique_bytes_per_launch": uniq_bytes,
+                     "unique_frac": uniq_bytes / (scan_ms / 1e3) / 1e9 / peak if scan_ms > 0 else 0.0,
+                     "kernel_ms": scan_ms, "scan_items_per_launch": items / a.steps,
+                     "step_breakdown_ms": {k_: prof[k_] / max(prof["searches"], 1)
+                                           for k_ in ("coarse_ms", "group_ms", "scan_ms", "merge_ms")}},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
+                "d2h_bytes_per_step": a.batch * a.k * 12},
+        "gpu_launches": a.steps * (6 + (1 if world > 1 else 0)),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -250,6 +250,21 @@ void oracle_add(oindex* ix, const float* x, const uint64_t* ids, uint64_t n) {
     free(assign);
 }
 
+/* bench set-up helper: add() with the assignment step supplied by the caller */
+void oracle_load_assigned(oindex* ix, const float* x, const uint64_t* ids, const uint32_t* assign, uint64_t n) {
+    for (uint64_t v = 0; v < n; ++v) {
+        olist* l = &ix->lists[assign[v]];
+        if (l->count == l->cap) {
+            l->cap = l->cap ? l->cap * 2 : 16;
+            l->vec = (float*)realloc(l->vec, l->cap * ix->dim * sizeof(float));
+            l->ids = (uint64_t*)realloc(l->ids, l->cap * sizeof(uint64_t));
+        }
+        memcpy(l->vec + l->count * ix->dim, x + v * ix->dim, ix->dim * sizeof(float));
+        l->ids[l->count++] = ids[v];
+    }
+    ix->total += n;
+}
+
 typedef struct {
     float d;
     uint64_t id;

@@ -154,6 +154,30 @@ void ref_list_ids(void* h, uint32_t list, uint64_t* out) {
     std::copy(l->ids.begin(), l->ids.end(), out);
 }
 
+// Benchmark set-up helper: append rows to the reference's own lists_ with
+// caller-provided assignments -- what add() does after its assignment step
+// (ivf_flat_index.cpp:160-200) -- so that the O(n * nlist * dim) CPU assignment
+// is not part of bench.py's set-up time.  search() is then the reference's,
+// untouched.
+void ref_load_assigned(void* h, const float* x, const uint64_t* ids, const uint32_t* assign, uint64_t n) {
+    auto* idx = static_cast<vdb::IVFFlatIndex*>(h);
+    const uint32_t dim = idx->config_.dimension;
+    std::vector<uint64_t> cnt(idx->lists_.size(), 0);
+    for (uint64_t v = 0; v < n; ++v) cnt[assign[v]]++;
+    for (size_t l = 0; l < cnt.size(); ++l) {
+        auto& L = idx->lists_[l];
+        L->vectors.reserve((L->count + cnt[l]) * dim);
+        L->ids.reserve(L->count + cnt[l]);
+    }
+    for (uint64_t v = 0; v < n; ++v) {
+        auto& L = idx->lists_[assign[v]];
+        L->vectors.insert(L->vectors.end(), x + v * dim, x + (v + 1) * dim);
+        L->ids.push_back(ids[v]);
+        L->count++;
+    }
+    idx->total_vectors_ += n;
+}
+
 uint64_t ref_total_vectors(void* h) {
     return static_cast<vdb::IVFFlatIndex*>(h)->get_total_vectors();
 }

@@ -50,6 +50,7 @@ def _load_port():
     lib.oracle_train.argtypes = [C.c_void_p, _f32p, C.c_uint64]
     lib.oracle_add.argtypes = [C.c_void_p, _f32p, _u64p, C.c_uint64]
     lib.oracle_assign.argtypes = [C.c_void_p, _f32p, C.c_uint64, _u32p]
+    lib.oracle_load_assigned.argtypes = [C.c_void_p, _f32p, _u64p, _u32p, C.c_uint64]
     lib.oracle_select_nprobe.restype = C.c_uint32
     lib.oracle_select_nprobe.argtypes = [C.c_void_p, _f32p, C.c_uint32, _u32p]
     lib.oracle_search.argtypes = [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _u64p, C.c_int]
@@ -77,6 +78,7 @@ def _load_ref():
     lib.ref_train.argtypes = [C.c_void_p, _f32p, C.c_uint64]
     lib.ref_add.argtypes = [C.c_void_p, _f32p, _u64p, C.c_uint64]
     lib.ref_assign.argtypes = [C.c_void_p, _f32p, C.c_uint64, _u32p]
+    lib.ref_load_assigned.argtypes = [C.c_void_p, _f32p, _u64p, _u32p, C.c_uint64]
     lib.ref_select_nprobe.argtypes = [C.c_void_p, _f32p, C.c_uint32, _u32p]
     lib.ref_search.argtypes = [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _u64p, C.c_int]
     lib.ref_search_batched.argtypes = [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _u64p]
@@ -150,6 +152,12 @@ class _Index:
         if ids is None:
             ids = np.arange(x.shape[0], dtype=np.uint64)
         self._f("add")(self._h, x, np.ascontiguousarray(ids, np.uint64), x.shape[0])
+
+    def load_assigned(self, x, ids, assign):
+        """bench set-up: append rows with caller-provided list assignments (add() minus its assign step)"""
+        x = np.ascontiguousarray(x, np.float32)
+        self._f("load_assigned")(self._h, x, np.ascontiguousarray(ids, np.uint64),
+                                 np.ascontiguousarray(assign, np.uint32), x.shape[0])
 
     def assign(self, x):
         x = np.ascontiguousarray(x, np.float32)

@@ -110,3 +110,19 @@ def test_invalid_config_rejected():
         O.OracleIndex(0, 4)
     with pytest.raises(ValueError):
         O.OracleIndex(4, 0)
+
+
+@needs_ref
+def test_load_assigned_equals_add():
+    x = O.gaussian(9, 600, 12)
+    for cls in (O.OracleIndex, O.RefIndex):
+        a, b = cls(12, 5), cls(12, 5)
+        cent = O.gaussian(10, 5, 12)
+        a.centroids = cent
+        b.centroids = cent
+        ids = np.arange(600, dtype=np.uint64) + 5
+        a.add(x, ids)
+        b.load_assigned(x, ids, a.assign(x))
+        Da, Ia = a.search(x[:9], 3, 10)
+        Db, Ib = b.search(x[:9], 3, 10)
+        assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db) and a.ntotal == b.ntotal
