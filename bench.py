@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--ntrain", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
+    ap.add_argument("--dump-groups", action="store_true", help="stderr: probed-row work by queries-per-list")
     return ap.parse_args()
 
 
@@ -233,6 +234,19 @@ def run_b200(a):
     q_all = torch.randn(nb, a.batch, a.dim, generator=gen, device=dev)
     t_build = time.perf_counter() - t_build
     st = ix.stats()
+
+    if a.dump_groups and rank == 0:
+        pr = ix.select_nprobe(q_all[0], a.nprobe)
+        sizes = ix.list_sizes().astype(np.int64)
+        g = np.bincount(pr.ravel(), minlength=a.nlist)
+        edges = [1, 2, 3, 5, 9, 17, 33, 65]
+        tot = float((sizes * g).sum())
+        print("list sizes: min %d med %d mean %.0f max %d" % (sizes.min(), np.median(sizes), sizes.mean(), sizes.max()),
+              file=sys.stderr)
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            m = (g >= lo) & (g < hi)
+            print(f"queries/list in [{lo},{hi}): lists {int(m.sum())}, unique rows {int(sizes[m].sum())}, "
+                  f"pair-rows share {float((sizes[m] * g[m]).sum()) / tot:.3f}", file=sys.stderr)
 
     stream = torch.cuda.current_stream().cuda_stream
     D = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)

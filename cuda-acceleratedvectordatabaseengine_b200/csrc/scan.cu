@@ -41,7 +41,19 @@ struct WorkList {
     ScanItem* items;
     uint32_t* totals;
     unsigned long long* stats;
+    uint32_t* qthr;  // [nq] running upper bound of each query's k-th distance, as an ordered key
+    uint32_t nq;
 };
+
+// order-preserving float <-> uint32 so that atomicMin works on distances of either sign
+constexpr uint32_t KEY_INF = 0xFF800000u;  // key of +inf
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
 // ---------------------------------------------------------------- utilities
 
@@ -95,6 +107,7 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
         wl.stats[0] = 0;
         wl.stats[1] = 0;
     }
+    for (uint32_t q = tid; q < wl.nq; q += NT) wl.qthr[q] = KEY_INF;
     __syncthreads();
     for (uint32_t p = tid; p < npairs; p += NT) {
         uint32_t l = probes[p];
@@ -243,18 +256,22 @@ struct ScanParams {
     const uint32_t* pair_slot;
     float* part_d;
     uint64_t* part_i;
+    uint32_t* part_cnt;  // [nslots] valid entries of each partial
+    uint32_t* qthr;      // [nq] ordered keys, see f2key
     uint32_t k, P, QT, ppi, S, np, check_interval;
     int metric;
 };
 
 struct ScanSmem {
     float* stages;
+    uint64_t* stage_ids;  // [S][STAGE_ROWS] ids of the staged rows (pages that carry ids)
     float* sq;
     uint64_t* pool_i;
     float* pool_d;
     uint32_t* cnt;
     float* thr;
     uint32_t* spair;
+    uint32_t* sqidx;
     uint64_t* full;
     uint64_t* empty;
 };
@@ -265,6 +282,8 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     uint8_t* q = base;
     s.stages = (float*)q;
     q += (size_t)p.S * stage_bytes;
+    s.stage_ids = (uint64_t*)q;
+    q += (size_t)p.S * STAGE_ROWS * 8;
     s.sq = (float*)q;
     q += (size_t)p.QT * p.lt.ld * 4;
     s.pool_i = (uint64_t*)q;
@@ -277,6 +296,8 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     q += MAX_QT * 4;
     s.spair = (uint32_t*)q;
     q += MAX_QT * 4;
+    s.sqidx = (uint32_t*)q;
+    q += MAX_QT * 4;
     q = (uint8_t*)(((uintptr_t)q + 7) & ~(uintptr_t)7);
     s.full = (uint64_t*)q;
     q += 8 * 8;
@@ -285,11 +306,16 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
 }
 
 static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P) {
-    return S * STAGE_ROWS * ld * 4 + QT * ld * 4 + QT * P * 12 + 3 * MAX_QT * 4 + 8 + 16 * 8;
+    return S * STAGE_ROWS * ld * 4 + S * STAGE_ROWS * 8 + QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 8 + 16 * 8;
 }
 
 // One warp sorts query j's pool and keeps the best k (multiset: duplicates of
 // an id inside one list survive, exactly like search_list_cpu's partial_sort).
+// When the best k carry k distinct ids, their k-th distance bounds the query's
+// final k-th distance from above whatever the other lists hold, so it is
+// published to the per-query global threshold that every later item starts from
+// (with duplicate ids among them the bound would be unsound: merge_results
+// drops duplicates, ivf_flat_index.cpp:496-504).
 __device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams& p, uint32_t j, uint32_t lane) {
     float* d = s.pool_d + (size_t)j * p.P;
     uint64_t* id = s.pool_i + (size_t)j * p.P;
@@ -302,9 +328,44 @@ __device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams
     __syncwarp();
     bitonic_sort_pairs(d, id, n2, lane, 32, [] { __syncwarp(); });
     const uint32_t nc = min(c, p.k);
+    bool publish = false;
+    if (nc >= p.k) {
+        const uint32_t k = p.k;
+        bool dup = false;
+        if (k <= 64) {
+            for (uint32_t i = lane; i < k; i += 32) {
+                const uint64_t me = id[i];
+                for (uint32_t t = 0; t < i; ++t) dup |= (id[t] == me);
+            }
+        } else {
+            // sort a copy of the k ids in the free upper half of the pool, then compare neighbours
+            uint64_t* sc = id + (p.P >> 1);
+            const uint32_t m2 = dev_next_pow2(k);
+            for (uint32_t i = lane; i < m2; i += 32) sc[i] = i < k ? id[i] : ID_PAD;
+            __syncwarp();
+            for (uint32_t size = 2; size <= m2; size <<= 1)
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t t = lane; t < (m2 >> 1); t += 32) {
+                        const uint32_t a = ((t / stride) * (stride << 1)) + (t % stride), b = a + stride;
+                        const uint64_t x = sc[a], y = sc[b];
+                        if (((a & size) == 0) ? (y < x) : (x < y)) {
+                            sc[a] = y;
+                            sc[b] = x;
+                        }
+                    }
+                    __syncwarp();
+                }
+            for (uint32_t i = lane; i + 1 < k; i += 32) dup |= (sc[i] == sc[i + 1]);
+        }
+        publish = !__any_sync(0xffffffffu, dup);
+    }
     if (lane == 0) {
         s.cnt[j] = nc;
-        s.thr[j] = (nc >= p.k) ? d[p.k - 1] : INFINITY;
+        if (nc >= p.k) {
+            const float kth = d[p.k - 1];
+            s.thr[j] = fminf(s.thr[j], kth);
+            if (publish) atomicMin(&p.qthr[s.sqidx[j]], f2key(kth));
+        }
     }
     __syncwarp();
 }
@@ -329,9 +390,12 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                 __ldg(reinterpret_cast<const float4*>(p.queries) + (size_t)q * ld4 + c);
         }
         if (ctid < qcount) {
+            const uint32_t pair = p.gpairs[it.gbase + ctid];
+            const uint32_t q = pair / p.np;
             s.cnt[ctid] = 0;
-            s.thr[ctid] = INFINITY;
-            s.spair[ctid] = p.gpairs[it.gbase + ctid];
+            s.spair[ctid] = pair;
+            s.sqidx[ctid] = q;
+            s.thr[ctid] = key2f(__ldcg(&p.qthr[q]));  // start from what earlier items already proved
         }
         consumer_bar();
 
@@ -360,6 +424,17 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                     for (int jj = 0; jj < NJ; ++jj) {
                         const uint32_t c4 = lane + 32 * jj;
                         v[i][jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                uint64_t rid[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const uint32_t r = warp + CONSUMER_WARPS * i;
+                    const uint32_t lr = row_base + r0 + r;  // list-relative row
+                    rid[i] = lr;
+                    if (r < nr) {
+                        if (page_ids) rid[i] = s.stage_ids[stage * STAGE_ROWS + r];
+                        else if (p.lt.ids_flat) rid[i] = __ldg(&p.lt.ids_flat[lr]);
                     }
                 }
                 __syncwarp();
@@ -407,13 +482,11 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
                         if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
                         if (tot <= thr && lane == 0) {
-                            const uint32_t lr = row_base + r0 + r;  // list-relative row
-                            uint64_t id = page_ids ? page_ids[r0 + r] : (p.lt.ids_flat ? p.lt.ids_flat[lr] : lr);
                             uint32_t pos = atomicAdd(&s.cnt[j], 1u);
                             over |= (pos >= limit);
                             if (pos < p.P) {
                                 s.pool_d[(size_t)j * p.P + pos] = tot;
-                                s.pool_i[(size_t)j * p.P + pos] = id;
+                                s.pool_i[(size_t)j * p.P + pos] = rid[i];
                             }
                         }
                     }
@@ -429,6 +502,8 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                             if (s.cnt[j] > limit) compact_pool(s, p, j, lane);
                         consumer_bar();
                     }
+                    // pick up bounds other CTAs published meanwhile (monotone, so a racy read is still a valid bound)
+                    if (ctid < qcount) s.thr[ctid] = fminf(s.thr[ctid], key2f(__ldcg(&p.qthr[s.sqidx[ctid]])));
                 }
             }
         }
@@ -439,10 +514,11 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
             compact_pool(s, p, j, lane);
             const uint32_t nc = s.cnt[j];
             const size_t slot = (size_t)p.pair_slot[s.spair[j]] + it.range;
-            for (uint32_t i = lane; i < p.k; i += 32) {
-                p.part_d[slot * p.k + i] = i < nc ? s.pool_d[(size_t)j * p.P + i] : FLT_MAX;
-                p.part_i[slot * p.k + i] = i < nc ? s.pool_i[(size_t)j * p.P + i] : ID_PAD;
+            for (uint32_t i = lane; i < nc; i += 32) {
+                p.part_d[slot * p.k + i] = s.pool_d[(size_t)j * p.P + i];
+                p.part_i[slot * p.k + i] = s.pool_i[(size_t)j * p.P + i];
             }
+            if (lane == 0) p.part_cnt[slot] = nc;
         }
         consumer_bar();
     }
@@ -463,13 +539,17 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
             const uint32_t row_base = (pg - pg_first) * p.lt.page_rows;
             const uint32_t rows_in_page = min(p.lt.page_rows, rows - row_base);
             const float* src = reinterpret_cast<const float*>(p.lt.page_vec[pg]);
+            const uint64_t* ids = reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]);
             for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
                 const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
                 const uint32_t bytes = nr * ld * 4;
+                // bulk copies move multiples of 16 bytes: an odd tail reads one id slot further, still inside the page
+                const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
                 mbar_wait(&s.empty[stage], phase ^ 1);
-                mbar_expect_tx(&s.full[stage], bytes);
+                mbar_expect_tx(&s.full[stage], bytes + id_bytes);
                 tma_bulk_g2s(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
                              &s.full[stage]);
+                if (ids) tma_bulk_g2s(s.stage_ids + stage * STAGE_ROWS, ids + r0, id_bytes, &s.full[stage]);
                 if (++stage == p.S) {
                     stage = 0;
                     phase ^= 1;
@@ -505,6 +585,7 @@ struct MergeParams {
     const float* part_d;
     const uint64_t* part_i;
     const uint32_t* pair_slot;  // null: `parts` mode, slot(q, p) = p * nq + q, one slot per pair
+    const uint32_t* part_cnt;   // valid entries per slot; null: k, padding skipped
     uint32_t nq, np, k, P;
     float* out_d;
     uint64_t* out_i;
@@ -640,6 +721,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
     }
     __syncthreads();
 
+    __shared__ uint32_t s_tot;
     for (uint32_t pr = 0; pr < p.np; ++pr) {
         uint32_t slot0, ns;
         if (p.pair_slot) {
@@ -651,27 +733,44 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
             ns = 1;
         }
         if (ns == 0) continue;
-        const float* src_d = p.part_d + (size_t)slot0 * k;
-        const uint64_t* src_i = p.part_i + (size_t)slot0 * k;
-        if (ns > 1) {
-            // level 1: the list's page partials -> its top-k, duplicates kept
+        // entries this (query, list) pair produced over all its page ranges
+        uint32_t tot = ns * k;
+        if (p.part_cnt) {
+            if (tid == 0) s_tot = 0;
+            __syncthreads();
+            uint32_t mine = 0;
+            for (uint32_t sidx = tid; sidx < ns; sidx += MERGE_THREADS) mine += p.part_cnt[slot0 + sidx];
+            if (mine) atomicAdd(&s_tot, mine);
+            __syncthreads();
+            tot = s_tot;
+            __syncthreads();
+        }
+        if (tot == 0) continue;
+        const bool direct = (ns == 1) || (tot <= k);  // already the list's top-k: no per-list selection needed
+        const MergePool& dst = direct ? L2 : L1;
+        if (!direct) {
             if (tid == 0) {
                 cnt1 = 0;
                 thr1 = INFINITY;
             }
             __syncthreads();
-            for (uint32_t sidx = 0; sidx < ns; ++sidx) {
-                if (cnt1 + k > P) pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
-                pool_push_block(L1, P, src_d + (size_t)sidx * k, src_i + (size_t)sidx * k, k);
-            }
-            pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
-            src_d = d1;
-            src_i = i1;
         }
-        // level 2
-        const uint32_t n = (ns > 1) ? cnt1 : k;
-        if (cnt2 + n > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
-        pool_push_block(L2, P, src_d, src_i, n);
+        for (uint32_t sidx = 0; sidx < ns; ++sidx) {
+            const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+            if (n == 0) continue;
+            if (*dst.cnt + n > P) {
+                if (direct) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+                else pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+            }
+            pool_push_block(dst, P, p.part_d + (size_t)(slot0 + sidx) * k, p.part_i + (size_t)(slot0 + sidx) * k, n);
+        }
+        if (!direct) {
+            // level 1 done: the list's top-k (duplicates kept) joins the cross-list pool
+            pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+            const uint32_t n = cnt1;
+            if (cnt2 + n > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+            pool_push_block(L2, P, d1, i1, n);
+        }
     }
     pool_compact_block(L2, P, k, true, d3, i3, s_scan);
     const uint32_t nc = cnt2;
@@ -684,7 +783,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
     }
 }
 
-uint32_t merge_pool_size(uint32_t k) { return next_pow2(k * 2 < 64 ? 64 : k * 2); }
+uint32_t merge_pool_size(uint32_t k) { return next_pow2(k * 2 < 1024 ? 1024 : k * 2); }
 
 template <int NJ>
 int32_t launch_scan(const ScanParams& sp, uint32_t grid, uint32_t smem, cudaStream_t stream) {
@@ -722,9 +821,16 @@ int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots
         VDB_CUDA_TRY(cudaMalloc(&pair_slot, (size_t)cap_pairs * 4));
     }
     if (nslots > cap_slots) {
-        cudaFree(items);
+        cudaFree(items); cudaFree(part_cnt);
         cap_slots = nslots + nslots / 4 + 64;
         VDB_CUDA_TRY(cudaMalloc(&items, cap_slots * sizeof(ScanItem)));
+        VDB_CUDA_TRY(cudaMalloc(&part_cnt, cap_slots * 4));
+    }
+    const uint32_t nq_need = npairs + 1;  // nq <= npairs
+    if (nq_need > cap_q) {
+        cudaFree(qthr);
+        cap_q = nq_need;
+        VDB_CUDA_TRY(cudaMalloc(&qthr, (size_t)cap_q * 4));
     }
     if (cap_slots * k > cap_part) {
         cudaFree(part_d); cudaFree(part_i);
@@ -743,7 +849,7 @@ int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots
 
 void ScanWorkspace::release() {
     cudaFree(gcount); cudaFree(gfill); cudaFree(goff); cudaFree(ioff);
-    cudaFree(gpairs); cudaFree(pair_slot); cudaFree(items);
+    cudaFree(gpairs); cudaFree(pair_slot); cudaFree(items); cudaFree(part_cnt); cudaFree(qthr);
     cudaFree(part_d); cudaFree(part_i); cudaFree(totals); cudaFree(stats);
     *this = ScanWorkspace();
 }
@@ -775,7 +881,8 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
 
     VDB_TRY(ws.reserve(lt.nlist, npairs, std::max<uint64_t>(max_slots, 1), k));
 
-    WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats};
+    WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats,
+                ws.qthr, nq};
     if (ev) cudaEventRecord(ev[0], stream);
     build_groups_kernel<<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, QT, ppi, wl);
     VDB_CUDA_TRY(cudaGetLastError());
@@ -789,6 +896,8 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     sp.pair_slot = ws.pair_slot;
     sp.part_d = ws.part_d;
     sp.part_i = ws.part_i;
+    sp.part_cnt = ws.part_cnt;
+    sp.qthr = ws.qthr;
     sp.k = k; sp.P = P; sp.QT = QT; sp.ppi = ppi; sp.S = S; sp.np = np;
     sp.check_interval = check_interval;
     sp.metric = metric;
@@ -810,7 +919,7 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
 
     if (ev) cudaEventRecord(ev[2], stream);
     MergeParams mp;
-    mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot;
+    mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot; mp.part_cnt = ws.part_cnt;
     mp.nq = nq; mp.np = np; mp.k = k; mp.P = merge_pool_size(k);
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = out_u32;
     const uint32_t msmem = mp.P * 36;
@@ -830,7 +939,7 @@ int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts,
                     float* out_d, uint64_t* out_i, cudaStream_t stream) {
     VDB_REQUIRE(k >= 1 && k <= MAX_K && parts >= 1 && nq >= 1, "merge: bad shape");
     MergeParams mp;
-    mp.part_d = dparts; mp.part_i = iparts; mp.pair_slot = nullptr;
+    mp.part_d = dparts; mp.part_i = iparts; mp.pair_slot = nullptr; mp.part_cnt = nullptr;
     mp.nq = nq; mp.np = parts; mp.k = k; mp.P = merge_pool_size(k);
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = nullptr;
     int dev = 0;

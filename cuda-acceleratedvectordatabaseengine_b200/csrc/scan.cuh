@@ -22,6 +22,9 @@ struct ScanWorkspace {
     uint32_t cap_pairs = 0;
     // items / partial results
     ScanItem* items = nullptr;
+    uint32_t* part_cnt = nullptr;  // [cap_slots]
+    uint32_t* qthr = nullptr;      // [cap_q]
+    uint32_t cap_q = 0;
     float* part_d = nullptr;
     uint64_t* part_i = nullptr;
     uint64_t cap_slots = 0, cap_part = 0;

@@ -1,0 +1,184 @@
+// C++ host mirror of the reference's engine interface, implemented on the C
+// ABI (include/vdb_b200.h) and nothing else -- no CUDA headers, no torch.
+//
+// A caller of the reference (server/query_service.cpp:134, bench/benchmark.cpp:
+// 63-96, test/simple_test.cpp:111-196) compiles against this header unchanged:
+//   vdb::IVFFlatIndex            engine/ivf_flat_index.h:14-67
+//   vdb::IVFFlatIndex::Config    :16-22   (same field names and defaults)
+//   vdb::IVFFlatIndex::SearchParams :38-42
+//   vdb::kernels::Metric         engine/kernels.cuh:24-28
+//   vdb::TransferManager         engine/transfer_manager.h:22-88 (subset the index and server use)
+// plus the methods the reference's server calls but its engine never defined:
+//   get_dimension()  query_service.cpp:112,   warmup_lists()/warmup_all() :191,195.
+//
+// Error behaviour follows the reference: the constructor throws
+// std::invalid_argument on dimension == 0 || nlist == 0 (ivf_flat_index.cpp:17-19);
+// every other failure surfaces as std::runtime_error, which the server's
+// catch (std::exception&) turns into grpc INTERNAL (query_service.cpp:164-167).
+// There is no CPU fallback: Config::use_gpu = false is rejected.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <mutex>
+#include <shared_mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vdb_b200.h"
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2,
+                      cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+#endif
+
+namespace vdb {
+namespace kernels {
+enum class Metric { L2, InnerProduct, Cosine };
+}  // namespace kernels
+
+namespace detail {
+inline void check(int32_t st, const char* what) {
+    if (st == VDB_OK) return;
+    std::string msg = std::string(what) + ": " + vdb_last_error_string() + " [" + vdb_status_string(st) + "]";
+    if (st == VDB_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+}  // namespace detail
+
+class TransferManager {
+public:
+    struct Config {
+        size_t pinned_pool_size = 1ULL << 30;
+        size_t device_pool_size = 4ULL << 30;
+        int num_streams = 4;
+        bool use_async = true;
+        int device = 0;
+    };
+    struct Transfer {
+        void* src;
+        void* dst;
+        size_t size;
+        cudaMemcpyKind kind;
+        cudaStream_t stream;
+        std::function<void()> callback;  // invoked after the copy has been enqueued AND completed
+    };
+    explicit TransferManager(const Config& config) : config_(config) {
+        detail::check(vdb_arena_create(config.device, config.device_pool_size, config.pinned_pool_size,
+                                       config.num_streams, &arena_), "TransferManager");
+    }
+    ~TransferManager() { vdb_arena_destroy(arena_); }
+    TransferManager(const TransferManager&) = delete;
+    TransferManager& operator=(const TransferManager&) = delete;
+
+    void* allocate_pinned(size_t size) { return vdb_arena_allocate_pinned(arena_, size); }
+    void free_pinned(void* p) { vdb_arena_free_pinned(arena_, p); }
+    void* allocate_device(size_t size) { return vdb_arena_allocate_device(arena_, size); }
+    void free_device(void* p) { vdb_arena_free_device(arena_, p); }
+    cudaStream_t get_stream() { return static_cast<cudaStream_t>(vdb_arena_get_stream(arena_)); }
+    void return_stream(cudaStream_t s) { vdb_arena_return_stream(arena_, s); }
+    void enqueue_transfer(const Transfer& t) {
+        detail::check(vdb_arena_enqueue_transfer(arena_, t.dst, t.src, t.size, static_cast<int32_t>(t.kind), t.stream),
+                      "enqueue_transfer");
+        if (t.callback) {
+            if (t.stream) synchronize_stream(t.stream); else synchronize();
+            t.callback();
+        }
+    }
+    void enqueue_batch(const std::vector<Transfer>& ts) { for (const auto& t : ts) enqueue_transfer(t); }
+    void synchronize() { detail::check(vdb_arena_synchronize(arena_), "synchronize"); }
+    void synchronize_stream(cudaStream_t s) { detail::check(vdb_arena_synchronize_stream(arena_, s), "synchronize_stream"); }
+    struct MemoryStats {
+        size_t total_device_allocated = 0, total_pinned_allocated = 0, active_allocations = 0,
+               peak_device_usage = 0, peak_pinned_usage = 0;
+    };
+    MemoryStats get_memory_stats() const {
+        uint64_t s[4] = {0, 0, 0, 0};
+        vdb_arena_stats(arena_, s);
+        MemoryStats m;
+        m.total_device_allocated = s[0]; m.peak_device_usage = s[1]; m.total_pinned_allocated = s[2];
+        m.active_allocations = s[3];
+        return m;
+    }
+
+private:
+    Config config_;
+    vdb_arena* arena_ = nullptr;
+};
+
+class IVFFlatIndex {
+public:
+    struct Config {
+        uint32_t dimension;
+        uint32_t nlist;
+        kernels::Metric metric;
+        bool use_gpu = true;
+        size_t max_gpu_memory = 0;  // 0 = uncapped (the reference's 8 GiB default cannot hold the headline index)
+        int device = 0;
+        uint32_t shard_rank = 0, shard_count = 1;
+    };
+    struct SearchParams {
+        uint32_t nprobe = 10;
+        uint32_t k = 10;
+        bool use_exact_rerank = false;  // unused by the reference as well
+    };
+
+    IVFFlatIndex(const Config& config, TransferManager* tm) : config_(config), tm_(tm) {
+        if (config.dimension == 0 || config.nlist == 0)
+            throw std::invalid_argument("Invalid configuration: dimension and nlist must be > 0");
+        if (!config.use_gpu) throw std::invalid_argument("use_gpu = false: this build has no CPU path");
+        vdb_config c;
+        vdb_config_default(&c);
+        c.dimension = config.dimension;
+        c.nlist = config.nlist;
+        c.metric = static_cast<int32_t>(config.metric);
+        c.device = config.device;
+        c.max_gpu_memory = config.max_gpu_memory;
+        c.shard_rank = config.shard_rank;
+        c.shard_count = config.shard_count;
+        detail::check(vdb_index_create(&c, &ix_), "IVFFlatIndex");
+    }
+    ~IVFFlatIndex() { vdb_index_destroy(ix_); }
+    IVFFlatIndex(const IVFFlatIndex&) = delete;
+    IVFFlatIndex& operator=(const IVFFlatIndex&) = delete;
+
+    // train/add are exclusive with search (SURVEY.md 8b threading): writers take the lock exclusively
+    void train(const float* vectors, uint64_t n_vectors) {
+        std::unique_lock<std::shared_mutex> l(mu_);
+        detail::check(vdb_index_train(ix_, vectors, n_vectors), "train");
+    }
+    void add(const float* vectors, const uint64_t* ids, uint64_t n_vectors) {
+        std::unique_lock<std::shared_mutex> l(mu_);
+        detail::check(vdb_index_add(ix_, vectors, ids, n_vectors), "add");
+    }
+    void search(const float* queries, uint32_t n_queries, const SearchParams& params, float* distances,
+                uint64_t* indices) {
+        std::shared_lock<std::shared_mutex> l(mu_);
+        detail::check(vdb_index_search(ix_, queries, n_queries, params.nprobe, params.k, distances, indices), "search");
+    }
+    void warmup_lists(const std::vector<uint32_t>& list_ids) {
+        detail::check(vdb_index_warmup(ix_, list_ids.data(), static_cast<uint32_t>(list_ids.size())), "warmup_lists");
+    }
+    void warmup_all() {}
+    void evict_list(uint32_t) {}  // lists are HBM-resident by construction
+    size_t get_gpu_memory_usage() const { return stats().gpu_memory_bytes; }
+    size_t get_total_vectors() const { return stats().total_vectors; }
+    uint32_t get_dimension() const { return config_.dimension; }
+    const Config& config() const { return config_; }
+    vdb_index* handle() { return ix_; }
+
+private:
+    vdb_stats stats() const {
+        vdb_stats s;
+        detail::check(vdb_index_stats(ix_, &s), "stats");
+        return s;
+    }
+    Config config_;
+    TransferManager* tm_;  // borrowed, must outlive the index (as in the reference); not needed by the kernels
+    vdb_index* ix_ = nullptr;
+    mutable std::shared_mutex mu_;
+};
+
+}  // namespace vdb

@@ -1,0 +1,83 @@
+"""Multi-GPU host side: inverted lists partitioned by list over the ranks of one
+torch.distributed process group (one process per GPU), per-rank top-k merged
+after an all-gather (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The reference has no multi-GPU path at all ("Parallelism"); the
+partitioning follows from merge_results (ivf_flat_index.cpp:474-518): a query's
+answer is the top-k of the union of per-list top-k's, so lists are independent
+units and the only exchange step is the final merge.
+
+    rank r owns list l  <=>  l % world == r          (owner_of)
+    every rank: same centroids, same coarse selection on the full query batch,
+                scan of the probed lists it owns -> local [nq][k] padded FLT_MAX/UINT64_MAX
+    all_gather of the local (distances, ids)         (gather_topk)
+    merge by (distance, id), duplicates dropped      (vdb_merge_topk kernel)
+
+The result is independent of the number of ranks by construction (same
+tie-break everywhere); tests/test_sharded_gloo.py checks exactly that.
+"""
+import torch
+import torch.distributed as dist
+
+
+def owner_of(list_id, world):
+    """Rank that owns inverted list `list_id` (must match the `l % shard_count` test in the add kernels)."""
+    return int(list_id) % int(world)
+
+
+def gather_topk(D, I, group=None):
+    """all_gather of every rank's local top-k: [nq][k] -> [world][nq][k] (same order on every rank)."""
+    world = dist.get_world_size(group)
+    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+    dist.all_gather_into_tensor(Dg, D.contiguous(), group=group)
+    dist.all_gather_into_tensor(Ig, I.contiguous(), group=group)
+    return Dg, Ig
+
+
+class ShardedIVFFlatIndex:
+    """vdb::IVFFlatIndex surface over `world` list shards, one per rank.
+
+    train(): every rank trains on the same rows (deterministic -> identical centroids);
+    add():   every rank sees the batch, assigns it, and keeps only the rows of the lists it owns;
+    search(): local search + all-gather + merge; every rank returns the full answer."""
+
+    def __init__(self, pkg, config, group=None):
+        self.pkg, self.group = pkg, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        config.shard_rank, config.shard_count = self.rank, self.world
+        self.local = pkg.IVFFlatIndex(config)
+        self.config = config
+
+    def train(self, vectors):
+        self.local.train(vectors)
+
+    def add(self, vectors, ids=None):
+        self.local.add(vectors, ids)
+
+    def search_device(self, queries, nprobe, k, stream=None):
+        """queries: CUDA tensor [nq][dim]; returns CUDA tensors ([nq][k] f32, [nq][k] i64 view of u64 ids)."""
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        nq = queries.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+        self.local.search_async(queries, nprobe, k, D, I, s)
+        if self.world == 1:
+            return D, I
+        Dg, Ig = gather_topk(D, I, self.group)
+        return self.pkg.merge_topk(Dg, Ig, s)
+
+    def search(self, queries, nprobe, k):
+        """host or device queries in, numpy out on every rank"""
+        q = queries if hasattr(queries, "data_ptr") else torch.from_numpy(queries)
+        D, I = self.search_device(q.cuda(non_blocking=True), nprobe, k)
+        return D.cpu().numpy(), I.cpu().numpy().view("uint64")
+
+    def get_total_vectors(self):
+        return self.local.get_total_vectors()
+
+    def get_gpu_memory_usage(self):
+        t = torch.tensor([self.local.get_gpu_memory_usage()], dtype=torch.int64,
+                         device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.all_reduce(t, group=self.group)
+        return int(t.item())

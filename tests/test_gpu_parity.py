@@ -270,3 +270,18 @@ def test_arena():
     p3 = l.vdb_arena_allocate_device(a, 60 << 20)  # coalesced back into one block
     assert p3
     assert l.vdb_arena_destroy(a) == 0
+
+
+def test_cpp_host_mirror_simple_test():
+    """the C++ vdb::IVFFlatIndex mirror (host/ivf_flat_index.h) driven like test/simple_test.cpp"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "host", "simple_test")
+    if not os.path.exists(exe):
+        pkg.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "PASSED" in out.stdout, out.stdout + out.stderr
+    g = np.load(os.path.join(GOLD, "simple_test.npz"))
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("R ")]
+    I = np.array([int(r[2]) for r in rows], np.uint64).reshape(g["I"].shape)
+    D = np.array([float(r[3]) for r in rows], np.float32).reshape(g["D"].shape)
+    check_search(D, I, g["D"], g["I"])
