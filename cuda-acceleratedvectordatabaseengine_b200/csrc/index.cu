@@ -267,7 +267,7 @@ int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t n
     while ((uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi) * np * 12 > (64ull << 20)) ppi *= 2;
     const uint64_t slots = (uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi);
     return scan_search(centroid_table(ix), q_dev, nq, ix->zero_probes.p, 1, np, ix->cfg.metric, ppi, slots,
-                       ix->ws_coarse, ix->coarse_d.p, ix->coarse_i.p, ix->probes.p, stream);
+                       ix->ws_coarse, false, ix->coarse_d.p, ix->coarse_i.p, ix->probes.p, stream);
 }
 
 int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t nq, uint32_t nprobe, uint32_t k,
@@ -285,7 +285,7 @@ int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t
     while (slot_bound(ix, nq, np, ppi) * k * 12 > (1ull << 30)) ppi *= 2;
     const uint64_t slots = slot_bound(ix, nq, np, ppi);
     VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,
-                        out_d, out_i, nullptr, stream, &ix->last_scan_info, ev));
+                        true, out_d, out_i, nullptr, stream, &ix->last_scan_info, ev));
     ix->have_search = true;
     return VDB_OK;
 }
@@ -753,7 +753,7 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
         VDB_TRY(zero.reserve(nq));
         VDB_CUDA_TRY(cudaMemsetAsync(zero.p, 0, (size_t)nq * 4, s));
         // items ~ tiles x ranges: aim at a few per SM, and keep the partial buffer modest
-        const uint64_t tiles = (nq + 15) / 16;
+        const uint64_t tiles = (nq + 3) / 4;
         uint32_t ppi = (uint32_t)std::max<uint64_t>(1, (uint64_t)npages * tiles / (NUM_SMS_B200 * 6));
         while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (1ull << 30)) ppi *= 2;
         const uint64_t slots = (uint64_t)nq * ((npages + ppi - 1) / ppi);
@@ -765,7 +765,7 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
             dd = od.p;
             di = oi.p;
         }
-        VDB_TRY(scan_search(lt, q, nq, zero.p, 1, k, metric, ppi, slots, ws, dd, di, nullptr, s));
+        VDB_TRY(scan_search(lt, q, nq, zero.p, 1, k, metric, ppi, slots, ws, false, dd, di, nullptr, s));
         if (!o_dev) {
             VDB_CUDA_TRY(cudaMemcpyAsync(distances, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
             VDB_CUDA_TRY(cudaMemcpyAsync(indices, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));

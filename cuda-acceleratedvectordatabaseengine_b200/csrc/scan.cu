@@ -10,14 +10,19 @@
 //   1. build_groups_kernel  groups the (query, probe) pairs by list, so that a
 //      list probed by several queries of the batch is streamed from HBM once,
 //      and cuts the work into items (list page range x tile of <= QT queries).
-//   2. scan_kernel          persistent, one CTA per SM.  A producer warp
-//      streams the item's rows HBM -> shared memory with 1-D bulk TMA copies
-//      (cp.async.bulk + mbarrier complete_tx) through an S-stage ring; eight
-//      consumer warps hold one row slice per lane in registers (128-bit,
-//      conflict-free shared loads), stream the tile's queries from shared
-//      memory, accumulate exact fp32 (q-v)^2 or q.v, and push candidates that
-//      beat the running k-th distance into a per-query shared pool that is
-//      bitonic-compacted to the best k (the fused top-k).
+//   2. scan_kernel          persistent, one CTA per SM.  A producer thread
+//      streams the item's rows (and their ids, and the next item's queries)
+//      HBM -> shared memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier
+//      complete_tx) through an S-stage ring; eight consumer warps keep the
+//      tile's queries in REGISTERS for the whole item (lane l owns float4
+//      columns l, l+32, ...), read each staged row with 128-bit conflict-free
+//      shared loads, accumulate exact fp32 (q-v)^2 or q.v for rows x queries,
+//      reduce across lanes with a transposed butterfly (~1 shuffle per pair),
+//      and push candidates that beat the running k-th distance into a
+//      per-query shared pool that is bitonic-compacted to the best k (the
+//      fused top-k).  A per-query bound on the final k-th distance is shared
+//      between CTAs through global memory (atomicMin), so later items admit
+//      almost nothing.
 //   3. merge_kernel         per query: page partials -> per-list top-k
 //      (multiset, as search_list_cpu returns it) -> sort by (dist,id), drop
 //      duplicate ids, pad: merge_results.
@@ -32,7 +37,7 @@ constexpr int STAGE_ROWS = 16;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int SCAN_THREADS = CONSUMER_THREADS + 32;
-constexpr int MAX_QT = 16;
+constexpr int MAX_QT = 8;
 constexpr uint32_t MAX_K = 2048;
 constexpr uint32_t SMEM_BUDGET = 227 * 1024;
 
@@ -179,19 +184,26 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
             wl.gpairs[pos] = p;
         }
     }
+    // items, range-major: the query tiles of one page range are neighbours in the work list, so the
+    // CTAs that re-read those rows do it at about the same time and hit L2
     for (uint32_t l = tid; l < nlist; l += NT) {
         uint32_t c = wl.gcount[l];
         if (!c) continue;
-        uint32_t nr = n_ranges(lt, l, ppi), nt = (c + QT - 1) / QT;
-        uint32_t o = wl.ioff[l], g0 = wl.goff[l];
-        for (uint32_t t = 0; t < nt; ++t)
-            for (uint32_t r = 0; r < nr; ++r) {
+        const uint32_t nr = n_ranges(lt, l, ppi), nt = (c + QT - 1) / QT;
+        const uint32_t o = wl.ioff[l], g0 = wl.goff[l];
+        const uint32_t pg_first = lt.page_off[l], npages = lt.page_off[l + 1] - pg_first, rows = lt.rows[l];
+        for (uint32_t r = 0; r < nr; ++r)
+            for (uint32_t t = 0; t < nt; ++t) {
                 ScanItem it;
-                it.list = l;
                 it.gbase = g0 + t * QT;
                 it.qcount = min(QT, c - t * QT);
                 it.range = r;
-                wl.items[o + t * nr + r] = it;
+                it.pg0 = pg_first + r * ppi;
+                it.npg = min(ppi, npages - r * ppi);
+                it.row_base = r * ppi * lt.page_rows;
+                it.rows_left = rows - it.row_base;
+                it.list = l;
+                wl.items[o + r * nt + t] = it;
             }
     }
 }
@@ -258,38 +270,39 @@ struct ScanParams {
     uint64_t* part_i;
     uint32_t* part_cnt;  // [nslots] valid entries of each partial
     uint32_t* qthr;      // [nq] ordered keys, see f2key
-    uint32_t k, P, QT, ppi, S, np, check_interval;
+    uint32_t k, P, S, np, check_interval, has_ids;
     int metric;
 };
 
 struct ScanSmem {
-    float* stages;
-    uint64_t* stage_ids;  // [S][STAGE_ROWS] ids of the staged rows (pages that carry ids)
-    float* sq;
-    uint64_t* pool_i;
-    float* pool_d;
+    float* stages;        // [S][STAGE_ROWS][ld]
+    uint64_t* stage_ids;  // [S][STAGE_ROWS] ids of the staged rows (lists that carry ids)
+    float* sq;            // [2][QT][ld] the tile's queries, double-buffered across items
+    uint64_t* pool_i;     // [QT][P]
+    float* pool_d;        // [QT][P]
     uint32_t* cnt;
     float* thr;
     uint32_t* spair;
     uint32_t* sqidx;
-    uint64_t* full;
-    uint64_t* empty;
+    uint64_t* full;    // [S]
+    uint64_t* empty;   // [S]
+    uint64_t* qfull;   // [2]
+    uint64_t* qempty;  // [2]
 };
 
-__device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
+__device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p, uint32_t QT) {
     ScanSmem s;
-    const uint32_t stage_bytes = STAGE_ROWS * p.lt.ld * 4;
     uint8_t* q = base;
     s.stages = (float*)q;
-    q += (size_t)p.S * stage_bytes;
+    q += (size_t)p.S * STAGE_ROWS * p.lt.ld * 4;
     s.stage_ids = (uint64_t*)q;
     q += (size_t)p.S * STAGE_ROWS * 8;
     s.sq = (float*)q;
-    q += (size_t)p.QT * p.lt.ld * 4;
+    q += (size_t)2 * QT * p.lt.ld * 4;
     s.pool_i = (uint64_t*)q;
-    q += (size_t)p.QT * p.P * 8;
+    q += (size_t)QT * p.P * 8;
     s.pool_d = (float*)q;
-    q += (size_t)p.QT * p.P * 4;
+    q += (size_t)QT * p.P * 4;
     s.cnt = (uint32_t*)q;
     q += MAX_QT * 4;
     s.thr = (float*)q;
@@ -298,16 +311,22 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     q += MAX_QT * 4;
     s.sqidx = (uint32_t*)q;
     q += MAX_QT * 4;
-    q = (uint8_t*)(((uintptr_t)q + 7) & ~(uintptr_t)7);
     s.full = (uint64_t*)q;
     q += 8 * 8;
     s.empty = (uint64_t*)q;
+    q += 8 * 8;
+    s.qfull = (uint64_t*)q;
+    q += 2 * 8;
+    s.qempty = (uint64_t*)q;
     return s;
 }
 
 static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P) {
-    return S * STAGE_ROWS * ld * 4 + S * STAGE_ROWS * 8 + QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 8 + 16 * 8;
+    return S * STAGE_ROWS * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8;
 }
+
+// queries held in registers per tile, by the number of float4 columns a lane owns
+__host__ __device__ constexpr int tile_queries(int NJ) { return NJ <= 2 ? 8 : NJ <= 6 ? 4 : NJ <= 12 ? 2 : 1; }
 
 // One warp sorts query j's pool and keeps the best k (multiset: duplicates of
 // an id inside one list survive, exactly like search_list_cpu's partial_sort).
@@ -320,7 +339,8 @@ __device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams
     float* d = s.pool_d + (size_t)j * p.P;
     uint64_t* id = s.pool_i + (size_t)j * p.P;
     const uint32_t c = min(s.cnt[j], p.P);
-    const uint32_t n2 = dev_next_pow2(max(c, 1u));
+    if (c == 0) return;
+    const uint32_t n2 = dev_next_pow2(c);
     for (uint32_t i = c + lane; i < n2; i += 32) {
         d[i] = FLT_MAX;
         id[i] = ID_PAD;
@@ -370,24 +390,121 @@ __device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams
     __syncwarp();
 }
 
+// Sum V per-lane partials across the warp: log2(V) "halving" exchanges leave
+// each lane with one value (index = its top log2(V) lane bits), the remaining
+// butterfly steps complete it.  V + log2(32/V) - 1 shuffles instead of 5 V.
+template <int V>
+__device__ __forceinline__ float transposed_reduce(float (&x)[V], uint32_t lane) {
+#pragma unroll
+    for (int half = V / 2, step = 16; half >= 1; half >>= 1, step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? x[i] : x[i + half];
+            const float keep = up ? x[i + half] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    float r = x[0];
+#pragma unroll
+    for (int step = 16 / V; step >= 1; step >>= 1) r += __shfl_xor_sync(0xffffffffu, r, step);
+    return r;
+}
+
+constexpr int R = STAGE_ROWS / CONSUMER_WARPS;  // rows of a stage per consumer warp
+
+// distances of this warp's R staged rows to the first QC queries of the tile; pushes the survivors
+template <int NJ, int QT, int QC>
+__device__ __forceinline__ void score_rows(const ScanParams& p, const ScanSmem& s, const float4 (&v)[R][NJ],
+                                           const float4 (&qv)[QT][NJ], const uint64_t (&rid)[R], uint32_t nr,
+                                           uint32_t qcount, uint32_t warp, uint32_t lane, uint32_t limit,
+                                           bool& over) {
+    constexpr int V = R * QC;
+    float acc[V];
+#pragma unroll
+    for (int t = 0; t < V; ++t) acc[t] = 0.f;
+    if (p.metric == VDB_METRIC_L2) {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int j = 0; j < QC; ++j) {
+                    const float dx = qv[j][jj].x - v[i][jj].x, dy = qv[j][jj].y - v[i][jj].y;
+                    const float dz = qv[j][jj].z - v[i][jj].z, dw = qv[j][jj].w - v[i][jj].w;
+                    float a = acc[i * QC + j];
+                    a = fmaf(dx, dx, a);
+                    a = fmaf(dy, dy, a);
+                    a = fmaf(dz, dz, a);
+                    a = fmaf(dw, dw, a);
+                    acc[i * QC + j] = a;
+                }
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int j = 0; j < QC; ++j) {
+                    float a = acc[i * QC + j];
+                    a = fmaf(qv[j][jj].x, v[i][jj].x, a);
+                    a = fmaf(qv[j][jj].y, v[i][jj].y, a);
+                    a = fmaf(qv[j][jj].z, v[i][jj].z, a);
+                    a = fmaf(qv[j][jj].w, v[i][jj].w, a);
+                    acc[i * QC + j] = a;
+                }
+    }
+    float tot = transposed_reduce<V>(acc, lane);
+    if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
+    // lane's value: index = top log2(V) lane bits; the lanes sharing them hold copies, one of them pushes
+    constexpr int COPIES = 32 / V;
+    const uint32_t vidx = lane / COPIES;
+    const uint32_t i = vidx / QC, j = vidx % QC;
+    const uint32_t r = warp + CONSUMER_WARPS * i;
+    if ((lane % COPIES) == 0 && r < nr && j < qcount && tot <= s.thr[j]) {
+        uint64_t id = rid[0];
+#pragma unroll
+        for (int t = 1; t < R; ++t)
+            if (i == (uint32_t)t) id = rid[t];
+        const uint32_t pos = atomicAdd(&s.cnt[j], 1u);
+        over |= (pos >= limit);
+        if (pos < p.P) {
+            s.pool_d[(size_t)j * p.P + pos] = tot;
+            s.pool_i[(size_t)j * p.P + pos] = id;
+        }
+    }
+}
+
 template <int NJ>
 __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSmem& s) {
+    constexpr int QT = tile_queries(NJ);
     const uint32_t ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
     const uint32_t ld = p.lt.ld, ld4 = ld >> 2;
     const uint32_t total = *p.totals;
     const uint32_t limit = p.P - p.check_interval * STAGE_ROWS;
-    constexpr int R = STAGE_ROWS / CONSUMER_WARPS;  // rows of a stage per warp
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, qbuf = 0, qphase = 0;
 
     for (uint32_t ii = blockIdx.x; ii < total; ii += gridDim.x) {
         const ScanItem it = p.items[ii];
         const uint32_t qcount = it.qcount;
-        // the tile's queries -> shared memory
-        for (uint32_t idx = ctid; idx < qcount * ld4; idx += CONSUMER_THREADS) {
-            uint32_t j = idx / ld4, c = idx - j * ld4;
-            uint32_t q = p.gpairs[it.gbase + j] / p.np;
-            reinterpret_cast<float4*>(s.sq)[j * ld4 + c] =
-                __ldg(reinterpret_cast<const float4*>(p.queries) + (size_t)q * ld4 + c);
+        // the tile's queries: staged by the producer while the previous item was scanned -> registers
+        mbar_wait(&s.qfull[qbuf], qphase);
+        float4 qv[QT][NJ];
+        {
+            const float4* q4 = reinterpret_cast<const float4*>(s.sq) + (size_t)qbuf * QT * ld4;
+#pragma unroll
+            for (int j = 0; j < QT; ++j)
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    const uint32_t c4 = lane + 32 * jj;
+                    qv[j][jj] = ((uint32_t)j < qcount && c4 < ld4) ? q4[j * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.qempty[qbuf]);
+        if (++qbuf == 2) {
+            qbuf = 0;
+            qphase ^= 1;
         }
         if (ctid < qcount) {
             const uint32_t pair = p.gpairs[it.gbase + ctid];
@@ -399,24 +516,18 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         }
         consumer_bar();
 
-        const uint32_t l = it.list;
-        const uint32_t rows = p.lt.rows[l];
-        const uint32_t pg_first = p.lt.page_off[l];
-        const uint32_t pg0 = pg_first + it.range * p.ppi;
-        const uint32_t pgN = min(pg0 + p.ppi, p.lt.page_off[l + 1]);
         uint32_t since_check = 0;
         bool over = false;  // this thread pushed a candidate at or beyond the compaction mark
-
-        for (uint32_t pg = pg0; pg < pgN; ++pg) {
-            const uint32_t row_base = (pg - pg_first) * p.lt.page_rows;  // list-relative row of the page start
-            const uint32_t rows_in_page = min(p.lt.page_rows, rows - row_base);
-            const uint64_t* page_ids = reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]);
+        for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
+            const uint32_t row_base = it.row_base + pgi * p.lt.page_rows;  // list-relative row of the page start
+            const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
             for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
                 const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
                 mbar_wait(&s.full[stage], phase);
                 // this warp's rows of the stage -> registers (lane owns float4 columns lane, lane+32, ...)
                 const float4* st4 = reinterpret_cast<const float4*>(s.stages + (size_t)stage * STAGE_ROWS * ld);
                 float4 v[R][NJ];
+                uint64_t rid[R];
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
                     const uint32_t r = warp + CONSUMER_WARPS * i;
@@ -425,15 +536,10 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                         const uint32_t c4 = lane + 32 * jj;
                         v[i][jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                }
-                uint64_t rid[R];
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    const uint32_t r = warp + CONSUMER_WARPS * i;
                     const uint32_t lr = row_base + r0 + r;  // list-relative row
                     rid[i] = lr;
                     if (r < nr) {
-                        if (page_ids) rid[i] = s.stage_ids[stage * STAGE_ROWS + r];
+                        if (p.has_ids) rid[i] = s.stage_ids[stage * STAGE_ROWS + r];
                         else if (p.lt.ids_flat) rid[i] = __ldg(&p.lt.ids_flat[lr]);
                     }
                 }
@@ -444,52 +550,11 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                     phase ^= 1;
                 }
 
-                for (uint32_t j = 0; j < qcount; ++j) {
-                    const float4* q4 = reinterpret_cast<const float4*>(s.sq) + j * ld4;
-                    float4 qv[NJ];
-#pragma unroll
-                    for (int jj = 0; jj < NJ; ++jj) {
-                        const uint32_t c4 = lane + 32 * jj;
-                        qv[jj] = (c4 < ld4) ? q4[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    const float thr = s.thr[j];
-#pragma unroll
-                    for (int i = 0; i < R; ++i) {
-                        const uint32_t r = warp + CONSUMER_WARPS * i;
-                        if (r >= nr) continue;  // warp-uniform
-                        float a0 = 0.f, a1 = 0.f;
-                        if (p.metric == VDB_METRIC_L2) {
-#pragma unroll
-                            for (int jj = 0; jj < NJ; ++jj) {
-                                float dx = qv[jj].x - v[i][jj].x, dy = qv[jj].y - v[i][jj].y;
-                                float dz = qv[jj].z - v[i][jj].z, dw = qv[jj].w - v[i][jj].w;
-                                a0 = fmaf(dx, dx, a0);
-                                a1 = fmaf(dy, dy, a1);
-                                a0 = fmaf(dz, dz, a0);
-                                a1 = fmaf(dw, dw, a1);
-                            }
-                        } else {
-#pragma unroll
-                            for (int jj = 0; jj < NJ; ++jj) {
-                                a0 = fmaf(qv[jj].x, v[i][jj].x, a0);
-                                a1 = fmaf(qv[jj].y, v[i][jj].y, a1);
-                                a0 = fmaf(qv[jj].z, v[i][jj].z, a0);
-                                a1 = fmaf(qv[jj].w, v[i][jj].w, a1);
-                            }
-                        }
-                        float tot = a0 + a1;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                        if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
-                        if (tot <= thr && lane == 0) {
-                            uint32_t pos = atomicAdd(&s.cnt[j], 1u);
-                            over |= (pos >= limit);
-                            if (pos < p.P) {
-                                s.pool_d[(size_t)j * p.P + pos] = tot;
-                                s.pool_i[(size_t)j * p.P + pos] = rid[i];
-                            }
-                        }
-                    }
+                if (warp < nr) {  // rows warp, warp+8: at least the first is real
+                    if (QT >= 8 && qcount > 4) score_rows<NJ, QT, (QT >= 8 ? 8 : QT)>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
+                    else if (QT >= 4 && qcount > 2) score_rows<NJ, QT, (QT >= 4 ? 4 : QT)>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
+                    else if (QT >= 2 && qcount > 1) score_rows<NJ, QT, (QT >= 2 ? 2 : QT)>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
+                    else score_rows<NJ, QT, 1>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
                 }
 
                 if (++since_check == p.check_interval) {
@@ -524,22 +589,30 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
     }
 }
 
+template <int NJ>
 __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSmem& s) {
+    constexpr int QT = tile_queries(NJ);
     const uint32_t total = *p.totals;
     const uint32_t ld = p.lt.ld;
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, qbuf = 0, qphase = 0;
     for (uint32_t ii = blockIdx.x; ii < total; ii += gridDim.x) {
         const ScanItem it = p.items[ii];
-        const uint32_t l = it.list;
-        const uint32_t rows = p.lt.rows[l];
-        const uint32_t pg_first = p.lt.page_off[l];
-        const uint32_t pg0 = pg_first + it.range * p.ppi;
-        const uint32_t pgN = min(pg0 + p.ppi, p.lt.page_off[l + 1]);
-        for (uint32_t pg = pg0; pg < pgN; ++pg) {
-            const uint32_t row_base = (pg - pg_first) * p.lt.page_rows;
-            const uint32_t rows_in_page = min(p.lt.page_rows, rows - row_base);
+        // the item's queries first (consumers need them before the first row)
+        mbar_wait(&s.qempty[qbuf], qphase ^ 1);
+        mbar_expect_tx(&s.qfull[qbuf], it.qcount * ld * 4);
+        for (uint32_t j = 0; j < it.qcount; ++j) {
+            const uint32_t q = p.gpairs[it.gbase + j] / p.np;
+            tma_bulk_g2s(s.sq + ((size_t)qbuf * QT + j) * ld, p.queries + (size_t)q * ld, ld * 4, &s.qfull[qbuf]);
+        }
+        if (++qbuf == 2) {
+            qbuf = 0;
+            qphase ^= 1;
+        }
+        for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
+            const uint32_t pg = it.pg0 + pgi;
+            const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
             const float* src = reinterpret_cast<const float*>(p.lt.page_vec[pg]);
-            const uint64_t* ids = reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]);
+            const uint64_t* ids = p.has_ids ? reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]) : nullptr;
             for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
                 const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
                 const uint32_t bytes = nr * ld * 4;
@@ -562,11 +635,15 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
 template <int NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const ScanSmem s = carve(smem_raw, p);
+    const ScanSmem s = carve(smem_raw, p, tile_queries(NJ));
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < p.S; ++i) {
             mbar_init(&s.full[i], 1);
             mbar_init(&s.empty[i], CONSUMER_WARPS);
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(&s.qfull[i], 1);
+            mbar_init(&s.qempty[i], CONSUMER_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -575,7 +652,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     if (threadIdx.x < CONSUMER_THREADS) {
         consumer_loop<NJ>(p, s);
     } else if (threadIdx.x == CONSUMER_THREADS) {
-        producer_loop(p, s);
+        producer_loop<NJ>(p, s);
     }
 }
 
@@ -747,22 +824,50 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
         }
         if (tot == 0) continue;
         const bool direct = (ns == 1) || (tot <= k);  // already the list's top-k: no per-list selection needed
-        const MergePool& dst = direct ? L2 : L1;
-        if (!direct) {
+        if (direct || tot <= P) {
+            // one parallel pass: thread t takes slots t, t+256, ... and pushes their entries
+            const MergePool& dst = direct ? L2 : L1;
+            if (direct) {
+                if (cnt2 + min(tot, ns * k) > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+            } else {
+                if (tid == 0) {
+                    cnt1 = 0;
+                    thr1 = INFINITY;
+                }
+                __syncthreads();
+            }
+            const float thr = *dst.thr;
+            for (uint32_t sidx = tid; sidx < ns; sidx += MERGE_THREADS) {
+                const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                const float* sd = p.part_d + (size_t)(slot0 + sidx) * k;
+                const uint64_t* si = p.part_i + (size_t)(slot0 + sidx) * k;
+                for (uint32_t e = 0; e < n; ++e) {
+                    const float d = sd[e];
+                    const uint64_t id = si[e];
+                    if (id == ID_PAD && d == FLT_MAX) continue;
+                    if (d <= thr) {
+                        const uint32_t pos = atomicAdd(dst.cnt, 1u);
+                        if (pos < P) {
+                            dst.d[pos] = d;
+                            dst.id[pos] = id;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        } else {
+            // rare: more survivors than the pool holds -> slot by slot with intermediate compactions
             if (tid == 0) {
                 cnt1 = 0;
                 thr1 = INFINITY;
             }
             __syncthreads();
-        }
-        for (uint32_t sidx = 0; sidx < ns; ++sidx) {
-            const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
-            if (n == 0) continue;
-            if (*dst.cnt + n > P) {
-                if (direct) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
-                else pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+            for (uint32_t sidx = 0; sidx < ns; ++sidx) {
+                const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                if (n == 0) continue;
+                if (cnt1 + n > P) pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+                pool_push_block(L1, P, p.part_d + (size_t)(slot0 + sidx) * k, p.part_i + (size_t)(slot0 + sidx) * k, n);
             }
-            pool_push_block(dst, P, p.part_d + (size_t)(slot0 + sidx) * k, p.part_i + (size_t)(slot0 + sidx) * k, n);
         }
         if (!direct) {
             // level 1 done: the list's top-k (duplicates kept) joins the cross-list pool
@@ -856,7 +961,7 @@ void ScanWorkspace::release() {
 
 int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
                     uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
-                    float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
+                    bool has_ids, float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
                     ScanLaunchInfo* info, cudaEvent_t* ev) {
     VDB_REQUIRE(k >= 1 && k <= MAX_K, "k must be in [1, 2048]");
     VDB_REQUIRE(lt.ld % 4 == 0 && lt.ld >= 4 && lt.ld <= 2048, "row stride must be a multiple of 4 floats, <= 2048");
@@ -867,15 +972,16 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     VDB_REQUIRE(npairs64 < (1ull << 31) && max_slots < (1ull << 31), "search too large for one call");
     const uint32_t npairs = (uint32_t)npairs64;
 
-    // shared-memory plan: pool size P, query tile QT, ring depth S
+    // shared-memory plan: pool size P (per query), query tile QT (fixed by the row width), ring depth S
+    const uint32_t nj_need = (lt.ld / 4 + 31) / 32;
+    const uint32_t NJ = nj_need <= 1 ? 1 : nj_need <= 2 ? 2 : nj_need <= 4 ? 4 : nj_need <= 6 ? 6 : nj_need <= 8 ? 8
+                        : nj_need <= 12 ? 12 : 16;
+    const uint32_t QT = (uint32_t)tile_queries((int)NJ);
     uint32_t P = next_pow2(std::max(k + 64, 2 * k));
-    uint32_t S = 4, QT = MAX_QT;
-    auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P) <= SMEM_BUDGET; };
-    while (QT > 1 && !fits(2, QT)) QT >>= 1;
-    VDB_REQUIRE(fits(2, QT), "dimension * k too large for the scan kernel's shared memory");
-    while (S > 2 && !fits(S, QT)) --S;
-    // prefer a deeper ring over a wider tile when the tile is large anyway
-    while (S < 3 && QT > 4 && fits(S + 1, QT / 2)) { QT >>= 1; ++S; }
+    uint32_t S = 6;
+    auto fits = [&](uint32_t s_) { return scan_smem_bytes(lt.ld, s_, QT, P) <= SMEM_BUDGET; };
+    while (S > 2 && !fits(S)) --S;
+    VDB_REQUIRE(fits(S), "dimension * k too large for the scan kernel's shared memory");
     const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
     const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P);
 
@@ -898,7 +1004,8 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     sp.part_i = ws.part_i;
     sp.part_cnt = ws.part_cnt;
     sp.qthr = ws.qthr;
-    sp.k = k; sp.P = P; sp.QT = QT; sp.ppi = ppi; sp.S = S; sp.np = np;
+    sp.k = k; sp.P = P; sp.S = S; sp.np = np;
+    sp.has_ids = has_ids ? 1u : 0u;
     sp.check_interval = check_interval;
     sp.metric = metric;
 
@@ -906,16 +1013,16 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, std::max<uint64_t>(max_slots, 1));
-    const uint32_t nj_need = (lt.ld / 4 + 31) / 32;
-    uint32_t NJ;
     if (ev) cudaEventRecord(ev[1], stream);
-    if (nj_need <= 1) { NJ = 1; VDB_TRY(launch_scan<1>(sp, grid, smem, stream)); }
-    else if (nj_need <= 2) { NJ = 2; VDB_TRY(launch_scan<2>(sp, grid, smem, stream)); }
-    else if (nj_need <= 4) { NJ = 4; VDB_TRY(launch_scan<4>(sp, grid, smem, stream)); }
-    else if (nj_need <= 6) { NJ = 6; VDB_TRY(launch_scan<6>(sp, grid, smem, stream)); }
-    else if (nj_need <= 8) { NJ = 8; VDB_TRY(launch_scan<8>(sp, grid, smem, stream)); }
-    else if (nj_need <= 12) { NJ = 12; VDB_TRY(launch_scan<12>(sp, grid, smem, stream)); }
-    else { NJ = 16; VDB_TRY(launch_scan<16>(sp, grid, smem, stream)); }
+    switch (NJ) {
+        case 1: VDB_TRY(launch_scan<1>(sp, grid, smem, stream)); break;
+        case 2: VDB_TRY(launch_scan<2>(sp, grid, smem, stream)); break;
+        case 4: VDB_TRY(launch_scan<4>(sp, grid, smem, stream)); break;
+        case 6: VDB_TRY(launch_scan<6>(sp, grid, smem, stream)); break;
+        case 8: VDB_TRY(launch_scan<8>(sp, grid, smem, stream)); break;
+        case 12: VDB_TRY(launch_scan<12>(sp, grid, smem, stream)); break;
+        default: VDB_TRY(launch_scan<16>(sp, grid, smem, stream)); break;
+    }
 
     if (ev) cudaEventRecord(ev[2], stream);
     MergeParams mp;

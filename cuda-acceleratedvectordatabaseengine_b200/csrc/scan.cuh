@@ -8,7 +8,12 @@ namespace vdb {
 // One unit of scan work: `qcount` queries (pairs gpairs[gbase..gbase+qcount))
 // against page range `range` of list `list`.
 struct ScanItem {
-    uint32_t list, gbase, qcount, range;
+    uint32_t gbase, qcount;  // the tile's pairs
+    uint32_t range;          // index of the page range inside the list (selects the partial-result slot)
+    uint32_t pg0, npg;       // absolute first page in the page tables, pages in this item
+    uint32_t row_base;       // list-relative row of the first page
+    uint32_t rows_left;      // rows from row_base to the end of the list
+    uint32_t list;
 };
 
 // Device scratch of one search call.  Grown on demand, reused across calls.
@@ -42,11 +47,12 @@ struct ScanLaunchInfo {
 
 // probes_dev: [nq][np] list ids (entries >= nlist or naming empty lists are
 // skipped).  max_slots: caller's upper bound on sum over pairs of page ranges.
-// ppi: pages per scan item.  Results (device): out_d/out_i [nq][k]; optional
+// ppi: pages per scan item.  has_ids: every page of `lt` carries an id block
+// (false for flat views, whose ids are implicit or in lt.ids_flat).  Results (device): out_d/out_i [nq][k]; optional
 // out_u32 receives the ids narrowed to 32 bits (probe lists).
 int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
                     uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
-                    float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
+                    bool has_ids, float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
                     ScanLaunchInfo* info = nullptr, cudaEvent_t* ev = nullptr);  // ev[0..3]: start, scan start, scan end, merge end
 
 // merge_results across `parts` blocks of [nq][k]
