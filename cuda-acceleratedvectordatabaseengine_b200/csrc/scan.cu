@@ -98,8 +98,7 @@ __device__ __forceinline__ uint32_t n_ranges(const ListTable& lt, uint32_t l, ui
 // ------------------------------------------------------- 1. probe grouping
 
 __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const uint32_t* __restrict__ probes,
-                                                            uint32_t npairs, uint32_t QT, uint32_t ppi,
-                                                            WorkList wl) {
+                                                            uint32_t npairs, uint32_t ppi, WorkList wl) {
     __shared__ uint32_t s_warp[33];
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
     const uint32_t nlist = lt.nlist;
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
             uint32_t c = wl.gcount[l];
             if (c) {
                 g += c;
-                it += ((c + QT - 1) / QT) * n_ranges(lt, l, ppi);
+                it += n_ranges(lt, l, ppi);
                 alg += (unsigned long long)lt.rows[l] * c;
                 uniq += lt.rows[l];
             }
@@ -144,13 +143,14 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
             uint32_t c = wl.gcount[l];
             if (c) {
                 base_g += c;
-                base_it += ((c + QT - 1) / QT) * n_ranges(lt, l, ppi);
+                base_it += n_ranges(lt, l, ppi);
             }
         }
         if (tid == 0) {
             wl.goff[nlist] = tot_g;
             wl.ioff[nlist] = tot_it;
             wl.totals[0] = tot_it;
+            wl.totals[2] = 0;  // dynamic work counter of the scan kernel
         }
         if (alg) atomicAdd(&wl.stats[0], alg);
         if (uniq) atomicAdd(&wl.stats[1], uniq);
@@ -184,27 +184,26 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
             wl.gpairs[pos] = p;
         }
     }
-    // items, range-major: the query tiles of one page range are neighbours in the work list, so the
-    // CTAs that re-read those rows do it at about the same time and hit L2
+    // one item per (list, page range); the scan loops over the list's query tiles inside the item, so the
+    // second and later tiles re-read the same rows from L2 right after the first brought them in
     for (uint32_t l = tid; l < nlist; l += NT) {
         uint32_t c = wl.gcount[l];
         if (!c) continue;
-        const uint32_t nr = n_ranges(lt, l, ppi), nt = (c + QT - 1) / QT;
+        const uint32_t nr = n_ranges(lt, l, ppi);
         const uint32_t o = wl.ioff[l], g0 = wl.goff[l];
         const uint32_t pg_first = lt.page_off[l], npages = lt.page_off[l + 1] - pg_first, rows = lt.rows[l];
-        for (uint32_t r = 0; r < nr; ++r)
-            for (uint32_t t = 0; t < nt; ++t) {
-                ScanItem it;
-                it.gbase = g0 + t * QT;
-                it.qcount = min(QT, c - t * QT);
-                it.range = r;
-                it.pg0 = pg_first + r * ppi;
-                it.npg = min(ppi, npages - r * ppi);
-                it.row_base = r * ppi * lt.page_rows;
-                it.rows_left = rows - it.row_base;
-                it.list = l;
-                wl.items[o + r * nt + t] = it;
-            }
+        for (uint32_t r = 0; r < nr; ++r) {
+            ScanItem it;
+            it.gbase = g0;
+            it.gcount = c;
+            it.range = r;
+            it.pg0 = pg_first + r * ppi;
+            it.npg = min(ppi, npages - r * ppi);
+            it.row_base = r * ppi * lt.page_rows;
+            it.rows_left = rows - it.row_base;
+            it.list = l;
+            wl.items[o + r] = it;
+        }
     }
 }
 
@@ -270,7 +269,9 @@ struct ScanParams {
     uint64_t* part_i;
     uint32_t* part_cnt;  // [nslots] valid entries of each partial
     uint32_t* qthr;      // [nq] ordered keys, see f2key
+    uint32_t* work_counter;
     uint32_t k, P, S, np, check_interval, has_ids;
+    uint32_t qt;  // queries per tile at run time (<= the kernel's register tile)
     int metric;
 };
 
@@ -288,9 +289,11 @@ struct ScanSmem {
     uint64_t* empty;   // [S]
     uint64_t* qfull;   // [2]
     uint64_t* qempty;  // [2]
+    uint32_t* tile;    // [2][8] {item | END, first pair, queries, range, pages, row_base, rows_left, -}: producer -> consumers
 };
 
-__device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p, uint32_t QT) {
+__device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
+    const uint32_t QT = p.qt;
     ScanSmem s;
     uint8_t* q = base;
     s.stages = (float*)q;
@@ -318,11 +321,13 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p, ui
     s.qfull = (uint64_t*)q;
     q += 2 * 8;
     s.qempty = (uint64_t*)q;
+    q += 2 * 8;
+    s.tile = (uint32_t*)q;
     return s;
 }
 
 static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P) {
-    return S * STAGE_ROWS * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8;
+    return S * STAGE_ROWS * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64;
 }
 
 // queries held in registers per tile, by the number of float4 columns a lane owns
@@ -480,18 +485,20 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
     constexpr int QT = tile_queries(NJ);
     const uint32_t ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
     const uint32_t ld = p.lt.ld, ld4 = ld >> 2;
-    const uint32_t total = *p.totals;
     const uint32_t limit = p.P - p.check_interval * STAGE_ROWS;
     uint32_t stage = 0, phase = 0, qbuf = 0, qphase = 0;
+    constexpr uint32_t END = 0xffffffffu;
 
-    for (uint32_t ii = blockIdx.x; ii < total; ii += gridDim.x) {
-        const ScanItem it = p.items[ii];
-        const uint32_t qcount = it.qcount;
-        // the tile's queries: staged by the producer while the previous item was scanned -> registers
+    for (;;) {
+        // next tile: announced by the producer together with its queries (staged while the previous tile was scanned)
         mbar_wait(&s.qfull[qbuf], qphase);
+        const uint32_t* tw = s.tile + qbuf * 8;
+        if (tw[0] == END) break;
+        const uint32_t gbase = tw[1], qcount = tw[2];
+        struct { uint32_t range, npg, row_base, rows_left; } it = {tw[3], tw[4], tw[5], tw[6]};
         float4 qv[QT][NJ];
         {
-            const float4* q4 = reinterpret_cast<const float4*>(s.sq) + (size_t)qbuf * QT * ld4;
+            const float4* q4 = reinterpret_cast<const float4*>(s.sq) + (size_t)qbuf * p.qt * ld4;
 #pragma unroll
             for (int j = 0; j < QT; ++j)
 #pragma unroll
@@ -507,7 +514,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
             qphase ^= 1;
         }
         if (ctid < qcount) {
-            const uint32_t pair = p.gpairs[it.gbase + ctid];
+            const uint32_t pair = p.gpairs[gbase + ctid];
             const uint32_t q = pair / p.np;
             s.cnt[ctid] = 0;
             s.spair[ctid] = pair;
@@ -589,53 +596,70 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
     }
 }
 
-template <int NJ>
 __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSmem& s) {
-    constexpr int QT = tile_queries(NJ);
     const uint32_t total = *p.totals;
     const uint32_t ld = p.lt.ld;
+    constexpr uint32_t END = 0xffffffffu;
     uint32_t stage = 0, phase = 0, qbuf = 0, qphase = 0;
-    for (uint32_t ii = blockIdx.x; ii < total; ii += gridDim.x) {
+    for (;;) {
+        const uint32_t ii = atomicAdd(p.work_counter, 1u);  // items are handed out dynamically
+        if (ii >= total) break;
         const ScanItem it = p.items[ii];
-        // the item's queries first (consumers need them before the first row)
-        mbar_wait(&s.qempty[qbuf], qphase ^ 1);
-        mbar_expect_tx(&s.qfull[qbuf], it.qcount * ld * 4);
-        for (uint32_t j = 0; j < it.qcount; ++j) {
-            const uint32_t q = p.gpairs[it.gbase + j] / p.np;
-            tma_bulk_g2s(s.sq + ((size_t)qbuf * QT + j) * ld, p.queries + (size_t)q * ld, ld * 4, &s.qfull[qbuf]);
-        }
-        if (++qbuf == 2) {
-            qbuf = 0;
-            qphase ^= 1;
-        }
-        for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
-            const uint32_t pg = it.pg0 + pgi;
-            const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
-            const float* src = reinterpret_cast<const float*>(p.lt.page_vec[pg]);
-            const uint64_t* ids = p.has_ids ? reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]) : nullptr;
-            for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
-                const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
-                const uint32_t bytes = nr * ld * 4;
-                // bulk copies move multiples of 16 bytes: an odd tail reads one id slot further, still inside the page
-                const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
-                mbar_wait(&s.empty[stage], phase ^ 1);
-                mbar_expect_tx(&s.full[stage], bytes + id_bytes);
-                tma_bulk_g2s(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
-                             &s.full[stage]);
-                if (ids) tma_bulk_g2s(s.stage_ids + stage * STAGE_ROWS, ids + r0, id_bytes, &s.full[stage]);
-                if (++stage == p.S) {
-                    stage = 0;
-                    phase ^= 1;
+        for (uint32_t g0 = 0; g0 < it.gcount; g0 += p.qt) {
+            const uint32_t qcount = min(p.qt, it.gcount - g0);
+            // announce the tile and stage its queries (consumers need them before the first row)
+            mbar_wait(&s.qempty[qbuf], qphase ^ 1);
+            uint32_t* tw = s.tile + qbuf * 8;
+            tw[0] = ii;
+            tw[1] = it.gbase + g0;
+            tw[2] = qcount;
+            tw[3] = it.range;
+            tw[4] = it.npg;
+            tw[5] = it.row_base;
+            tw[6] = it.rows_left;
+            mbar_expect_tx(&s.qfull[qbuf], qcount * ld * 4);  // release: publishes s.tile too
+            for (uint32_t j = 0; j < qcount; ++j) {
+                const uint32_t q = p.gpairs[it.gbase + g0 + j] / p.np;
+                tma_bulk_g2s(s.sq + ((size_t)qbuf * p.qt + j) * ld, p.queries + (size_t)q * ld, ld * 4,
+                             &s.qfull[qbuf]);
+            }
+            if (++qbuf == 2) {
+                qbuf = 0;
+                qphase ^= 1;
+            }
+            // the item's rows; from the second tile on they come back from L2
+            for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
+                const uint32_t pg = it.pg0 + pgi;
+                const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
+                const float* src = reinterpret_cast<const float*>(p.lt.page_vec[pg]);
+                const uint64_t* ids = p.has_ids ? reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]) : nullptr;
+                for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
+                    const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
+                    const uint32_t bytes = nr * ld * 4;
+                    // bulk copies move multiples of 16 bytes: an odd tail reads one id slot further, inside the page
+                    const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
+                    mbar_wait(&s.empty[stage], phase ^ 1);
+                    mbar_expect_tx(&s.full[stage], bytes + id_bytes);
+                    tma_bulk_g2s(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
+                                 &s.full[stage]);
+                    if (ids) tma_bulk_g2s(s.stage_ids + stage * STAGE_ROWS, ids + r0, id_bytes, &s.full[stage]);
+                    if (++stage == p.S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
     }
+    mbar_wait(&s.qempty[qbuf], qphase ^ 1);
+    s.tile[qbuf * 8 + 0] = END;
+    mbar_arrive(&s.qfull[qbuf]);
 }
 
 template <int NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const ScanSmem s = carve(smem_raw, p, tile_queries(NJ));
+    const ScanSmem s = carve(smem_raw, p);
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < p.S; ++i) {
             mbar_init(&s.full[i], 1);
@@ -652,7 +676,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     if (threadIdx.x < CONSUMER_THREADS) {
         consumer_loop<NJ>(p, s);
     } else if (threadIdx.x == CONSUMER_THREADS) {
-        producer_loop<NJ>(p, s);
+        producer_loop(p, s);
     }
 }
 
@@ -976,12 +1000,13 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     const uint32_t nj_need = (lt.ld / 4 + 31) / 32;
     const uint32_t NJ = nj_need <= 1 ? 1 : nj_need <= 2 ? 2 : nj_need <= 4 ? 4 : nj_need <= 6 ? 6 : nj_need <= 8 ? 8
                         : nj_need <= 12 ? 12 : 16;
-    const uint32_t QT = (uint32_t)tile_queries((int)NJ);
+    uint32_t QT = (uint32_t)tile_queries((int)NJ);  // register tile; shrunk at run time when the pools of a large k need the room
     uint32_t P = next_pow2(std::max(k + 64, 2 * k));
     uint32_t S = 6;
-    auto fits = [&](uint32_t s_) { return scan_smem_bytes(lt.ld, s_, QT, P) <= SMEM_BUDGET; };
-    while (S > 2 && !fits(S)) --S;
-    VDB_REQUIRE(fits(S), "dimension * k too large for the scan kernel's shared memory");
+    auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P) <= SMEM_BUDGET; };
+    while (QT > 1 && !fits(3, QT)) QT >>= 1;
+    while (S > 2 && !fits(S, QT)) --S;
+    VDB_REQUIRE(fits(S, QT), "dimension * k too large for the scan kernel's shared memory");
     const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
     const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P);
 
@@ -990,7 +1015,7 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats,
                 ws.qthr, nq};
     if (ev) cudaEventRecord(ev[0], stream);
-    build_groups_kernel<<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, QT, ppi, wl);
+    build_groups_kernel<<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, ppi, wl);
     VDB_CUDA_TRY(cudaGetLastError());
 
     ScanParams sp;
@@ -1006,6 +1031,8 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     sp.qthr = ws.qthr;
     sp.k = k; sp.P = P; sp.S = S; sp.np = np;
     sp.has_ids = has_ids ? 1u : 0u;
+    sp.qt = QT;
+    sp.work_counter = ws.totals + 2;
     sp.check_interval = check_interval;
     sp.metric = metric;
 

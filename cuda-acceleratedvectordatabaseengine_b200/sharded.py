@@ -30,8 +30,12 @@ def gather_topk(D, I, group=None):
     world = dist.get_world_size(group)
     Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
     Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-    dist.all_gather_into_tensor(Dg, D.contiguous(), group=group)
-    dist.all_gather_into_tensor(Ig, I.contiguous(), group=group)
+    if D.is_cuda:  # NCCL: one fused collective per tensor, straight into the [world][nq][k] buffer
+        dist.all_gather_into_tensor(Dg, D.contiguous(), group=group)
+        dist.all_gather_into_tensor(Ig, I.contiguous(), group=group)
+    else:  # gloo (CPU tests): list form, views of the same buffer
+        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=group)
+        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=group)
     return Dg, Ig
 
 
