@@ -281,7 +281,9 @@ int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t
         ++ev;
     }
     VDB_TRY(coarse_select(ix, q_dev, nq, np, stream));
-    uint32_t ppi = 1;
+    // pages per scan item: large indexes hand out longer runs of a list, so the per-item costs (tile
+    // announcement, barriers, final selection, partial write-out) are paid once per ~3 MB instead of per page
+    uint32_t ppi = ix->pages_used > NUM_SMS_B200 * 256u ? 4 : ix->pages_used > NUM_SMS_B200 * 64u ? 2 : 1;
     while (slot_bound(ix, nq, np, ppi) * k * 12 > (1ull << 30)) ppi *= 2;
     const uint64_t slots = slot_bound(ix, nq, np, ppi);
     VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,
@@ -753,7 +755,7 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
         VDB_TRY(zero.reserve(nq));
         VDB_CUDA_TRY(cudaMemsetAsync(zero.p, 0, (size_t)nq * 4, s));
         // items ~ tiles x ranges: aim at a few per SM, and keep the partial buffer modest
-        const uint64_t tiles = (nq + 3) / 4;
+        const uint64_t tiles = (nq + 7) / 8;
         uint32_t ppi = (uint32_t)std::max<uint64_t>(1, (uint64_t)npages * tiles / (NUM_SMS_B200 * 6));
         while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (1ull << 30)) ppi *= 2;
         const uint64_t slots = (uint64_t)nq * ((npages + ppi - 1) / ppi);

@@ -36,8 +36,8 @@ namespace {
 constexpr int STAGE_ROWS = 16;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
-constexpr int SCAN_THREADS = CONSUMER_THREADS + 32;
-constexpr int MAX_QT = 8;
+constexpr int SCAN_THREADS = CONSUMER_THREADS + 128;  // 2 consumer warpgroups + the producer's warpgroup
+constexpr int MAX_QT = 32;  // queries per CTA tile: register tile (tile_queries) x up to 8 warp groups
 constexpr uint32_t MAX_K = 2048;
 constexpr uint32_t SMEM_BUDGET = 227 * 1024;
 
@@ -241,6 +241,25 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// same, with an L2 eviction-priority hint (createpolicy) on the global read
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
 // consumer barrier that also ORs a per-thread flag across the 256 consumer threads
 __device__ __forceinline__ bool consumer_bar_or(bool flag) {
@@ -416,61 +435,81 @@ __device__ __forceinline__ float transposed_reduce(float (&x)[V], uint32_t lane)
     return r;
 }
 
-constexpr int R = STAGE_ROWS / CONSUMER_WARPS;  // rows of a stage per consumer warp
-
-// distances of this warp's R staged rows to the first QC queries of the tile; pushes the survivors
-template <int NJ, int QT, int QC>
-__device__ __forceinline__ void score_rows(const ScanParams& p, const ScanSmem& s, const float4 (&v)[R][NJ],
-                                           const float4 (&qv)[QT][NJ], const uint64_t (&rid)[R], uint32_t nr,
-                                           uint32_t qcount, uint32_t warp, uint32_t lane, uint32_t limit,
-                                           bool& over) {
-    constexpr int V = R * QC;
-    float acc[V];
+// Distances of RB staged rows (r_first, r_first + r_stride, ...) to the first QC queries of this warp's
+// group, then ONE transposed reduction for the RB x QC per-lane partials and the pushes of the survivors.
+// Packed fp32x2 FMAs (sm_100): a (row, query) pair costs 2 instructions per float2 of the row --
+// d = v * (-1) + q (exactly q - v), acc += d * d -- instead of 4.
+template <int NJ, int QT, int QC, int RB>
+__device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem& s, const float4* __restrict__ st4,
+                                            uint32_t ld4, uint32_t cur, uint32_t r_first, uint32_t r_stride,
+                                            uint32_t nr, uint32_t row0, const float4 (&qv)[QT][NJ], uint32_t myq,
+                                            uint32_t g, uint32_t ng, uint32_t lane, uint32_t limit, bool& over,
+                                            bool release) {
+    constexpr int V = RB * QC;
+    float part[V];
+    uint64_t rid[RB];
+    const float2 neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
-    for (int t = 0; t < V; ++t) acc[t] = 0.f;
-    if (p.metric == VDB_METRIC_L2) {
+    for (int b = 0; b < RB; ++b) {
+        const uint32_t r = r_first + r_stride * b;
+        float4 v[NJ];
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj)
+        for (int jj = 0; jj < NJ; ++jj) {
+            const uint32_t c4 = lane + 32 * jj;
+            v[jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const uint32_t lr = row0 + r;  // list-relative row
+        rid[b] = lr;
+        if (r < nr) {
+            if (p.has_ids) rid[b] = s.stage_ids[cur * STAGE_ROWS + r];
+            else if (p.lt.ids_flat) rid[b] = __ldg(&p.lt.ids_flat[lr]);
+        }
+        if (release && b == RB - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty[cur]);  // slot free: this warp's last row now lives in registers
+        }
+        float2 acc2[QC];
 #pragma unroll
-            for (int i = 0; i < R; ++i)
+        for (int t = 0; t < QC; ++t) acc2[t] = make_float2(0.f, 0.f);
+        if (p.metric == VDB_METRIC_L2) {
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float2 vlo = make_float2(v[jj].x, v[jj].y), vhi = make_float2(v[jj].z, v[jj].w);
 #pragma unroll
                 for (int j = 0; j < QC; ++j) {
-                    const float dx = qv[j][jj].x - v[i][jj].x, dy = qv[j][jj].y - v[i][jj].y;
-                    const float dz = qv[j][jj].z - v[i][jj].z, dw = qv[j][jj].w - v[i][jj].w;
-                    float a = acc[i * QC + j];
-                    a = fmaf(dx, dx, a);
-                    a = fmaf(dy, dy, a);
-                    a = fmaf(dz, dz, a);
-                    a = fmaf(dw, dw, a);
-                    acc[i * QC + j] = a;
+                    const float2 dlo = __ffma2_rn(vlo, neg1, make_float2(qv[j][jj].x, qv[j][jj].y));
+                    const float2 dhi = __ffma2_rn(vhi, neg1, make_float2(qv[j][jj].z, qv[j][jj].w));
+                    acc2[j] = __ffma2_rn(dlo, dlo, acc2[j]);
+                    acc2[j] = __ffma2_rn(dhi, dhi, acc2[j]);
                 }
-    } else {
+            }
+        } else {
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj)
-#pragma unroll
-            for (int i = 0; i < R; ++i)
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float2 vlo = make_float2(v[jj].x, v[jj].y), vhi = make_float2(v[jj].z, v[jj].w);
 #pragma unroll
                 for (int j = 0; j < QC; ++j) {
-                    float a = acc[i * QC + j];
-                    a = fmaf(qv[j][jj].x, v[i][jj].x, a);
-                    a = fmaf(qv[j][jj].y, v[i][jj].y, a);
-                    a = fmaf(qv[j][jj].z, v[i][jj].z, a);
-                    a = fmaf(qv[j][jj].w, v[i][jj].w, a);
-                    acc[i * QC + j] = a;
+                    acc2[j] = __ffma2_rn(make_float2(qv[j][jj].x, qv[j][jj].y), vlo, acc2[j]);
+                    acc2[j] = __ffma2_rn(make_float2(qv[j][jj].z, qv[j][jj].w), vhi, acc2[j]);
                 }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < QC; ++t) part[b * QC + t] = acc2[t].x + acc2[t].y;
     }
-    float tot = transposed_reduce<V>(acc, lane);
+    float tot = transposed_reduce<V>(part, lane);
     if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
-    // lane's value: index = top log2(V) lane bits; the lanes sharing them hold copies, one of them pushes
+    // lane's value: index = top log2(V) lane bits = (row in batch, query in group); copies in the other lanes
     constexpr int COPIES = 32 / V;
     const uint32_t vidx = lane / COPIES;
-    const uint32_t i = vidx / QC, j = vidx % QC;
-    const uint32_t r = warp + CONSUMER_WARPS * i;
-    if ((lane % COPIES) == 0 && r < nr && j < qcount && tot <= s.thr[j]) {
+    const uint32_t b = vidx / QC, jl = vidx % QC;
+    const uint32_t r = r_first + r_stride * b;
+    const uint32_t j = g + ng * jl;  // the query's slot in the CTA tile
+    if ((lane % COPIES) == 0 && r < nr && jl < myq && tot <= s.thr[j]) {
         uint64_t id = rid[0];
 #pragma unroll
-        for (int t = 1; t < R; ++t)
-            if (i == (uint32_t)t) id = rid[t];
+        for (int t = 1; t < RB; ++t)
+            if (b == (uint32_t)t) id = rid[t];
         const uint32_t pos = atomicAdd(&s.cnt[j], 1u);
         over |= (pos >= limit);
         if (pos < p.P) {
@@ -478,6 +517,22 @@ __device__ __forceinline__ void score_rows(const ScanParams& p, const ScanSmem& 
             s.pool_i[(size_t)j * p.P + pos] = id;
         }
     }
+}
+
+// QC = register-tile width actually needed (next power of two of the group's query count)
+template <int NJ, int QT, int RB>
+__device__ __forceinline__ void score_dispatch(const ScanParams& p, const ScanSmem& s, const float4* st4, uint32_t ld4,
+                                               uint32_t cur, uint32_t r_first, uint32_t r_stride, uint32_t nr,
+                                               uint32_t row0, const float4 (&qv)[QT][NJ], uint32_t myq, uint32_t g,
+                                               uint32_t ng, uint32_t lane, uint32_t limit, bool& over, bool release) {
+    if (QT >= 8 && myq > 4)
+        score_batch<NJ, QT, (QT >= 8 ? 8 : QT), (RB > 4 ? 4 : RB)>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+    else if (QT >= 4 && myq > 2)
+        score_batch<NJ, QT, (QT >= 4 ? 4 : QT), RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+    else if (QT >= 2 && myq > 1)
+        score_batch<NJ, QT, (QT >= 2 ? 2 : QT), RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+    else
+        score_batch<NJ, QT, 1, RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
 }
 
 template <int NJ>
@@ -496,6 +551,13 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         if (tw[0] == END) break;
         const uint32_t gbase = tw[1], qcount = tw[2];
         struct { uint32_t range, npg, row_base, rows_left; } it = {tw[3], tw[4], tw[5], tw[6]};
+        // a tile wider than the register tile is split over warp groups: group g keeps queries g, g+ng, ...
+        // and every group reads every staged row, so the rows are still brought in from HBM once
+        uint32_t ng = 1;
+        while (ng * QT < qcount) ng <<= 1;
+        const uint32_t g = warp & (ng - 1), wg = warp / ng, nwg = CONSUMER_WARPS / ng;
+        const uint32_t myq = qcount > g ? (qcount - g + ng - 1) / ng : 0;
+        const uint32_t rows_per_warp = STAGE_ROWS / nwg;
         float4 qv[QT][NJ];
         {
             const float4* q4 = reinterpret_cast<const float4*>(s.sq) + (size_t)qbuf * p.qt * ld4;
@@ -504,7 +566,8 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
                     const uint32_t c4 = lane + 32 * jj;
-                    qv[j][jj] = ((uint32_t)j < qcount && c4 < ld4) ? q4[j * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[j][jj] = ((uint32_t)j < myq && c4 < ld4) ? q4[(g + ng * j) * ld4 + c4]
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         }
         __syncwarp();
@@ -517,7 +580,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
             const uint32_t pair = p.gpairs[gbase + ctid];
             const uint32_t q = pair / p.np;
             s.cnt[ctid] = 0;
-            s.spair[ctid] = pair;
+            s.spair[ctid] = p.pair_slot[pair] + it.range;  // the partial-result slot of (pair, range)
             s.sqidx[ctid] = q;
             s.thr[ctid] = key2f(__ldcg(&p.qthr[q]));  // start from what earlier items already proved
         }
@@ -531,37 +594,23 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
             for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
                 const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
                 mbar_wait(&s.full[stage], phase);
-                // this warp's rows of the stage -> registers (lane owns float4 columns lane, lane+32, ...)
+                // this warp's rows of the stage, one at a time: row slice -> registers (lane owns float4 columns
+                // lane, lane+32, ...), score against the tile; the slot is handed back once the last row is read
                 const float4* st4 = reinterpret_cast<const float4*>(s.stages + (size_t)stage * STAGE_ROWS * ld);
-                float4 v[R][NJ];
-                uint64_t rid[R];
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    const uint32_t r = warp + CONSUMER_WARPS * i;
-#pragma unroll
-                    for (int jj = 0; jj < NJ; ++jj) {
-                        const uint32_t c4 = lane + 32 * jj;
-                        v[i][jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    const uint32_t lr = row_base + r0 + r;  // list-relative row
-                    rid[i] = lr;
-                    if (r < nr) {
-                        if (p.has_ids) rid[i] = s.stage_ids[stage * STAGE_ROWS + r];
-                        else if (p.lt.ids_flat) rid[i] = __ldg(&p.lt.ids_flat[lr]);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s.empty[stage]);  // slot free: the rows now live in registers
+                const uint32_t cur = stage;
                 if (++stage == p.S) {
                     stage = 0;
                     phase ^= 1;
                 }
-
-                if (warp < nr) {  // rows warp, warp+8: at least the first is real
-                    if (QT >= 8 && qcount > 4) score_rows<NJ, QT, (QT >= 8 ? 8 : QT)>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
-                    else if (QT >= 4 && qcount > 2) score_rows<NJ, QT, (QT >= 4 ? 4 : QT)>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
-                    else if (QT >= 2 && qcount > 1) score_rows<NJ, QT, (QT >= 2 ? 2 : QT)>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
-                    else score_rows<NJ, QT, 1>(p, s, v, qv, rid, nr, qcount, warp, lane, limit, over);
+                // this warp's rows of the stage (wg, wg + nwg, ...), RB at a time
+                if (ng == 1) {
+                    score_dispatch<NJ, QT, 2>(p, s, st4, ld4, cur, wg, nwg, nr, row_base + r0, qv, myq, g, ng, lane,
+                                              limit, over, true);
+                } else {
+#pragma unroll 1
+                    for (uint32_t i0 = 0; i0 < rows_per_warp; i0 += 4)
+                        score_dispatch<NJ, QT, 4>(p, s, st4, ld4, cur, wg + nwg * i0, nwg, nr, row_base + r0, qv, myq,
+                                                  g, ng, lane, limit, over, i0 + 4 >= rows_per_warp);
                 }
 
                 if (++since_check == p.check_interval) {
@@ -585,7 +634,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         for (uint32_t j = warp; j < qcount; j += CONSUMER_WARPS) {
             compact_pool(s, p, j, lane);
             const uint32_t nc = s.cnt[j];
-            const size_t slot = (size_t)p.pair_slot[s.spair[j]] + it.range;
+            const size_t slot = s.spair[j];
             for (uint32_t i = lane; i < nc; i += 32) {
                 p.part_d[slot * p.k + i] = s.pool_d[(size_t)j * p.P + i];
                 p.part_i[slot * p.k + i] = s.pool_i[(size_t)j * p.P + i];
@@ -600,13 +649,22 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
     const uint32_t total = *p.totals;
     const uint32_t ld = p.lt.ld;
     constexpr uint32_t END = 0xffffffffu;
+    // rows that a later query tile of the same item will read again should stay in L2; the last (or only)
+    // pass streams and must not push them out
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
     uint32_t stage = 0, phase = 0, qbuf = 0, qphase = 0;
-    for (;;) {
-        const uint32_t ii = atomicAdd(p.work_counter, 1u);  // items are handed out dynamically
-        if (ii >= total) break;
-        const ScanItem it = p.items[ii];
+    // items are handed out dynamically; the next one is claimed and its descriptor fetched while the
+    // current one streams, so the ring never waits on that round trip
+    uint32_t ii = atomicAdd(p.work_counter, 1u);
+    ScanItem it = p.items[min(ii, total ? total - 1 : 0)];
+    while (ii < total) {
+        const uint32_t ii_next = atomicAdd(p.work_counter, 1u);
+        const ScanItem it_next = p.items[min(ii_next, total - 1)];
+        const uint64_t src0 = p.lt.page_vec[it.pg0];
+        const uint64_t ids0 = p.has_ids ? p.lt.page_ids[it.pg0] : 0;
         for (uint32_t g0 = 0; g0 < it.gcount; g0 += p.qt) {
             const uint32_t qcount = min(p.qt, it.gcount - g0);
+            const uint64_t policy = (g0 + p.qt < it.gcount) ? keep : stream;
             // announce the tile and stage its queries (consumers need them before the first row)
             mbar_wait(&s.qempty[qbuf], qphase ^ 1);
             uint32_t* tw = s.tile + qbuf * 8;
@@ -631,8 +689,9 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
             for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
                 const uint32_t pg = it.pg0 + pgi;
                 const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
-                const float* src = reinterpret_cast<const float*>(p.lt.page_vec[pg]);
-                const uint64_t* ids = p.has_ids ? reinterpret_cast<const uint64_t*>(p.lt.page_ids[pg]) : nullptr;
+                const float* src = reinterpret_cast<const float*>(pgi ? p.lt.page_vec[pg] : src0);
+                const uint64_t* ids =
+                    p.has_ids ? reinterpret_cast<const uint64_t*>(pgi ? p.lt.page_ids[pg] : ids0) : nullptr;
                 for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
                     const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
                     const uint32_t bytes = nr * ld * 4;
@@ -640,8 +699,8 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
                     const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
                     mbar_wait(&s.empty[stage], phase ^ 1);
                     mbar_expect_tx(&s.full[stage], bytes + id_bytes);
-                    tma_bulk_g2s(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
-                                 &s.full[stage]);
+                    tma_bulk_g2s_hint(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
+                                      &s.full[stage], policy);
                     if (ids) tma_bulk_g2s(s.stage_ids + stage * STAGE_ROWS, ids + r0, id_bytes, &s.full[stage]);
                     if (++stage == p.S) {
                         stage = 0;
@@ -650,6 +709,8 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
                 }
             }
         }
+        ii = ii_next;
+        it = it_next;
     }
     mbar_wait(&s.qempty[qbuf], qphase ^ 1);
     s.tile[qbuf * 8 + 0] = END;
@@ -673,10 +734,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    // register reallocation between warpgroups: the producer's warpgroup (one busy thread) shrinks to 40
+    // registers per thread, the two consumer warpgroups grow to 232 = (384 * 168 - 128 * 40) / 256
     if (threadIdx.x < CONSUMER_THREADS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
         consumer_loop<NJ>(p, s);
-    } else if (threadIdx.x == CONSUMER_THREADS) {
-        producer_loop(p, s);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
+        if (threadIdx.x == CONSUMER_THREADS) producer_loop(p, s);
     }
 }
 
@@ -1000,11 +1065,16 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     const uint32_t nj_need = (lt.ld / 4 + 31) / 32;
     const uint32_t NJ = nj_need <= 1 ? 1 : nj_need <= 2 ? 2 : nj_need <= 4 ? 4 : nj_need <= 6 ? 6 : nj_need <= 8 ? 8
                         : nj_need <= 12 ? 12 : 16;
-    uint32_t QT = (uint32_t)tile_queries((int)NJ);  // register tile; shrunk at run time when the pools of a large k need the room
+    // CTA tile = register tile (tile_queries) x warp groups, as wide as shared memory allows with a 3-deep
+    // ring; shrunk below the register tile when the pools of a large k need the room
+    const uint32_t QTreg = (uint32_t)tile_queries((int)NJ);
     uint32_t P = next_pow2(std::max(k + 64, 2 * k));
-    uint32_t S = 6;
     auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P) <= SMEM_BUDGET; };
+    uint32_t ngroups = CONSUMER_WARPS;
+    while (ngroups > 1 && (QTreg * ngroups > MAX_QT || !fits(3, QTreg * ngroups))) ngroups >>= 1;
+    uint32_t QT = QTreg * ngroups;
     while (QT > 1 && !fits(3, QT)) QT >>= 1;
+    uint32_t S = 4;
     while (S > 2 && !fits(S, QT)) --S;
     VDB_REQUIRE(fits(S, QT), "dimension * k too large for the scan kernel's shared memory");
     const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
