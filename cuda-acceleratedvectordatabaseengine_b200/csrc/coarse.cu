@@ -1,0 +1,470 @@
+// Coarse selection on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces select_nprobe_lists (ivf_flat_index.cpp:298-336) for a whole query
+// batch:
+//   1. score_gemm_kernel   S = Q * C^T as a dense TF32 contraction: tcgen05.mma
+//      (cta_group::1, kind::tf32, M=128 x N=64 x K=8 per instruction) issued by
+//      one thread, operands staged by 2-D TMA (cp.async.bulk.tensor, 128-byte
+//      swizzle) through a 4-stage mbarrier ring, the fp32 accumulator in TMEM,
+//      read back with tcgen05.ld for the epilogue.  fp32 rows are fed as they
+//      are (the MMA reads the top 19 bits), so there is no conversion pass.
+//   2. coarse_select_kernel  per query: approximate scores |c|^2 - 2 q.c (or
+//      -q.c), radix-select of the nprobe-th smallest, every centroid within the
+//      TF32 rounding bound of it becomes a candidate, candidates are re-scored
+//      in exact fp32, and the best nprobe by (distance, list id) are returned.
+//
+// Error bound: TF32 keeps 10 mantissa bits and the unit truncates, so each
+// input carries a relative error < 2^-10 and |q.c - tf32(q).tf32(c)| <
+// 2^-9 |q||c| (Cauchy-Schwarz; the fp32 accumulation error is three orders of
+// magnitude below).  With E = 2^-8 |q| max|c| (covers the factor 2 of the L2
+// score, and both metrics), the true nprobe-th score S* satisfies
+// T - E <= S* <= T + E for the approximate nprobe-th score T, hence every true
+// member has an approximate score <= T + 2E: the candidate set is a superset
+// of the exact answer, and the exact re-check makes the result independent of
+// the tensor-core rounding.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "coarse.cuh"
+#include "topk.cuh"
+
+namespace vdb {
+namespace {
+
+// ------------------------------------------------------------------ PTX glue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tcgen05.commit: arrives on the mbarrier when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major tile
+// whose rows are 128 bytes apart, 128-byte swizzle, 8-row groups 1024 bytes
+// apart, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                  // leading byte offset (unused with swizzle), [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset, [32,46)
+    d |= (uint64_t)1 << 46;                                  // version, [46,48)
+    d |= (uint64_t)2 << 61;                                  // layout type SWIZZLE_128B, [61,64)
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulator,
+// TF32 x TF32, both operands K-major, N and M encoded >>3 and >>4.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------ 1. score GEMM
+
+constexpr int GM = 128;      // rows of A per CTA (UMMA M)
+constexpr int GK = 32;       // fp32 elements per stage row = 128 bytes = one swizzle atom
+constexpr int GSTAGES = 4;
+constexpr int GEMM_THREADS = 192;  // warps 0-3 epilogue (TMEM lane quadrants), 4 TMA producer, 5 MMA issuer + TMEM owner
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+score_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  float* __restrict__ out, uint32_t M, uint32_t N, uint32_t ldo, uint32_t num_kb) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 128-byte-swizzled tiles must start on a 1024-byte boundary of the shared window
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr uint32_t A_BYTES = GM * GK * 4, B_BYTES = BN * GK * 4;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + GSTAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sb + GSTAGES * B_BYTES);
+    uint64_t* empty = full + GSTAGES;
+    uint64_t* acc_full = empty + GSTAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t m0 = blockIdx.y * GM, n0 = blockIdx.x * BN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GSTAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 5) {  // one warp owns the TMEM allocation: BN fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 4 && lane == 0) {
+        // TMA producer: one A box [128 rows][32 k] and one B box [BN rows][32 k] per stage
+        uint32_t s = 0, ph = 0;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+            tma_load_2d(sa + s * A_BYTES, &map_a, (int32_t)(kb * GK), (int32_t)m0, &full[s]);
+            tma_load_2d(sb + s * B_BYTES, &map_b, (int32_t)(kb * GK), (int32_t)n0, &full[s]);
+            if (++s == GSTAGES) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    } else if (warp == 5 && lane == 0) {
+        // MMA issuer: 4 instructions of K = 8 per stage, advancing 32 bytes inside the swizzle atom
+        constexpr uint32_t idesc = umma_idesc_tf32(GM, BN);
+        uint32_t s = 0, ph = 0;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(sa + s * A_BYTES), db = umma_desc_sw128(sb + s * B_BYTES);
+#pragma unroll
+            for (uint32_t k = 0; k < GK / 8; ++k)
+                umma_tf32(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit(&empty[s]);  // the stage is free once these MMAs have read it
+            if (++s == GSTAGES) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+        umma_commit(acc_full);  // accumulator complete
+    } else if (warp < 4) {
+        // epilogue: warp w reads TMEM lanes [32w, 32w+32) = rows m0+32w.. of the tile
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const uint32_t row = m0 + warp * 32 + lane;
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + ((warp * 32u) << 16) + c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                  "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                  "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* o = out + (size_t)row * ldo + n0 + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + c0 + i < N) o[i] = __uint_as_float(r[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// [rows][cols] fp32, row stride ld floats -> boxes of [box_rows][32 floats], 128-byte swizzle, zero fill out of bounds
+int32_t make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled is not available from this driver");
+        return VDB_CUDA_ERROR;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)GK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return VDB_CUDA_ERROR;
+    }
+    return VDB_OK;
+}
+
+constexpr int BN_COARSE = 64;
+
+// ------------------------------------------------------ 2. select + re-check
+
+constexpr int SEL_THREADS = 256;
+constexpr uint32_t SEL_CAND = 2048;  // sort capacity: running best np + one index chunk of candidates
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void centroid_norms_kernel(const float* __restrict__ c, uint32_t n, uint32_t ld, float* __restrict__ norms,
+                                      uint32_t* __restrict__ max_bits) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    float s = 0.f;
+    for (uint32_t d = lane; d < ld; d += 32) {
+        const float v = c[(size_t)w * ld + d];
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        norms[w] = s;
+        atomicMax(max_bits, __float_as_uint(s));  // non-negative floats order like their bit patterns
+    }
+}
+
+struct SelectParams {
+    const float* dots;     // [nq][ldd] q.c from the tensor cores
+    const float* queries;  // [nq][ld]
+    const float* centroids;// [N][ld]
+    const float* cnorm;    // [N] |c|^2
+    const uint32_t* cmax_bits;
+    uint32_t N, ld, ldd, np;
+    int metric;
+    uint32_t* probes;      // [nq][np]
+    float* out_d;          // [nq][np] exact coarse distances (optional)
+    uint32_t* cand_count;  // [nq] candidates re-checked (diagnostic, optional)
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const SelectParams p) {
+    extern __shared__ __align__(16) uint8_t ssm[];
+    float* score = reinterpret_cast<float*>(ssm);                       // [N]
+    uint64_t* cid = reinterpret_cast<uint64_t*>(score + ((p.N + 1) & ~1u));  // [SEL_CAND]
+    float* cd = reinterpret_cast<float*>(cid + SEL_CAND);               // [SEL_CAND]
+    __shared__ uint32_t hist[256];
+    __shared__ float s_red[SEL_THREADS / 32];
+    __shared__ uint32_t s_prefix, s_rank, s_ncand, s_nbest;
+    __shared__ float s_qnorm;
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* qv = p.queries + (size_t)q * p.ld;
+
+    // approximate scores and |q|
+    for (uint32_t n = tid; n < p.N; n += SEL_THREADS) {
+        const float dot = p.dots[(size_t)q * p.ldd + n];
+        score[n] = (p.metric == VDB_METRIC_L2) ? fmaf(-2.f, dot, p.cnorm[n]) : -dot;
+    }
+    float qq = 0.f;
+    for (uint32_t d = tid; d < p.ld; d += SEL_THREADS) qq = fmaf(qv[d], qv[d], qq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    if (lane == 0) s_red[warp] = qq;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < SEL_THREADS / 32; ++i) t += s_red[i];
+        s_qnorm = sqrtf(t);
+        s_prefix = 0;
+        s_rank = p.np - 1;  // 0-based rank of the score we are after
+    }
+    __syncthreads();
+
+    // radix select (4 x 8 bits, most significant first) of the np-th smallest ordered key
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (uint32_t i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (uint32_t n = tid; n < p.N; n += SEL_THREADS) {
+            const uint32_t key = f2key(score[n]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t rank = s_rank, b = 0;
+            for (; b < 256; ++b) {
+                if (rank < hist[b]) break;
+                rank -= hist[b];
+            }
+            s_rank = rank;
+            s_prefix = prefix | (b << shift);
+        }
+        __syncthreads();
+    }
+    const float T = key2f(s_prefix);
+    // rounding bound of the tensor-core scores (see the file header); the relative slack also
+    // covers the fp32 rounding of the bound itself and of |c|^2 - 2 q.c
+    const float cmax = sqrtf(__uint_as_float(*p.cmax_bits));
+    const float E = 1.05f * 0.00390625f * s_qnorm * cmax + 1e-30f;
+    const float admit = T + 2.f * E + 1e-6f * fabsf(T);
+
+    // candidates, one index chunk at a time so that a chunk plus the running best always fit the sorter
+    if (tid == 0) s_nbest = 0;
+    uint32_t total_cand = 0;
+    const uint32_t chunk = SEL_CAND - p.np;
+    for (uint32_t n0 = 0; n0 < p.N; n0 += chunk) {
+        __syncthreads();
+        if (tid == 0) s_ncand = s_nbest;  // entries [0, nbest) hold the best so far
+        __syncthreads();
+        const uint32_t n1 = min(p.N, n0 + chunk);
+        for (uint32_t n = n0 + tid; n < n1; n += SEL_THREADS)
+            if (score[n] <= admit) {
+                const uint32_t pos = atomicAdd(&s_ncand, 1u);
+                cid[pos] = n;
+            }
+        __syncthreads();
+        const uint32_t nb = s_nbest, nc = s_ncand;
+        total_cand += nc - nb;
+        // exact fp32 distance of every new candidate: one warp per candidate
+        for (uint32_t i = nb + warp; i < nc; i += SEL_THREADS / 32) {
+            const float* cv = p.centroids + (size_t)cid[i] * p.ld;
+            float a = 0.f;
+            if (p.metric == VDB_METRIC_L2) {
+                for (uint32_t d = lane; d < p.ld; d += 32) {
+                    const float diff = qv[d] - cv[d];
+                    a = fmaf(diff, diff, a);
+                }
+            } else {
+                for (uint32_t d = lane; d < p.ld; d += 32) a = fmaf(qv[d], cv[d], a);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) cd[i] = (p.metric == VDB_METRIC_L2) ? a : -a;
+        }
+        __syncthreads();
+        const uint32_t n2 = dev_next_pow2(max(nc, 1u));
+        for (uint32_t i = nc + tid; i < n2; i += SEL_THREADS) {
+            cd[i] = FLT_MAX;
+            cid[i] = ID_PAD;
+        }
+        __syncthreads();
+        bitonic_sort_pairs(cd, cid, n2, tid, SEL_THREADS, [] { __syncthreads(); });
+        if (tid == 0) s_nbest = min(nc, p.np);
+    }
+    __syncthreads();
+    const uint32_t nb = s_nbest;
+    for (uint32_t i = tid; i < p.np; i += SEL_THREADS) {
+        p.probes[(size_t)q * p.np + i] = i < nb ? (uint32_t)cid[i] : 0xffffffffu;
+        if (p.out_d) p.out_d[(size_t)q * p.np + i] = i < nb ? cd[i] : FLT_MAX;
+    }
+    if (p.cand_count && tid == 0) p.cand_count[q] = total_cand;
+}
+
+}  // namespace
+
+size_t coarse_select_smem(uint32_t N) { return (size_t)((N + 1) & ~1u) * 4 + (size_t)SEL_CAND * 12; }
+
+bool coarse_tensor_supported(uint32_t N, uint32_t ld, uint32_t np) {
+    return encode_tiled() != nullptr && coarse_select_smem(N) <= 200 * 1024 && np < SEL_CAND / 2 && ld % 4 == 0;
+}
+
+int32_t centroid_norms(const float* centroids, uint32_t n, uint32_t ld, float* norms, uint32_t* max_bits,
+                       cudaStream_t stream) {
+    VDB_CUDA_TRY(cudaMemsetAsync(max_bits, 0, 4, stream));
+    centroid_norms_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(centroids, n, ld, norms, max_bits);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t score_gemm(const float* A, uint32_t M, uint32_t lda, const float* B, uint32_t N, uint32_t ldb, uint32_t K,
+                   float* out, uint32_t ldo, cudaStream_t stream) {
+    CUtensorMap ma, mb;
+    VDB_TRY(make_map(&ma, A, M, K, lda, GM));
+    VDB_TRY(make_map(&mb, B, N, K, ldb, BN_COARSE));
+    constexpr uint32_t smem = GSTAGES * (GM * GK * 4 + BN_COARSE * GK * 4) + (2 * GSTAGES + 1) * 8 + 16 + 1024;
+    static bool conf[8] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && !conf[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(score_gemm_kernel<BN_COARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        conf[dev] = true;
+    }
+    dim3 grid((N + BN_COARSE - 1) / BN_COARSE, (M + GM - 1) / GM);
+    score_gemm_kernel<BN_COARSE><<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, out, M, N, ldo, (K + GK - 1) / GK);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t coarse_select(const float* dots, uint32_t ldd, const float* queries, uint32_t nq, const float* centroids,
+                      const float* cnorm, const uint32_t* cmax_bits, uint32_t N, uint32_t ld, uint32_t np, int metric,
+                      uint32_t* probes, float* out_d, uint32_t* cand_count, cudaStream_t stream) {
+    SelectParams p;
+    p.dots = dots; p.queries = queries; p.centroids = centroids; p.cnorm = cnorm; p.cmax_bits = cmax_bits;
+    p.N = N; p.ld = ld; p.ldd = ldd; p.np = np; p.metric = metric;
+    p.probes = probes; p.out_d = out_d; p.cand_count = cand_count;
+    const size_t smem = coarse_select_smem(N);
+    static bool conf[8] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && !conf[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        conf[dev] = true;
+    }
+    coarse_select_kernel<<<nq, SEL_THREADS, smem, stream>>>(p);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+}  // namespace vdb

@@ -14,6 +14,7 @@
 #include <numeric>
 #include <vector>
 
+#include "coarse.cuh"
 #include "common.cuh"
 #include "kmeans.cuh"
 #include "scan.cuh"
@@ -85,6 +86,10 @@ struct vdb_index {
     std::mutex mu;
 
     DevBuf<float> centroids;  // [nlist][ld]
+    DevBuf<float> cnorm;      // [nlist] |c|^2 (tensor-core coarse path)
+    DevBuf<uint32_t> cmax_bits;
+    DevBuf<float> dots;       // [nq][nlist] q.c from the tensor cores
+    bool tensor_ok = false;
     // flat paged view of the centroid table (the coarse step scans it like a list)
     DevBuf<uint32_t> c_rows, c_page_off;
     DevBuf<uint64_t> c_page_vec, c_page_ids;
@@ -116,7 +121,7 @@ struct vdb_index {
     uint32_t prof_used = 0;
 
     uint64_t hbm_bytes() const {
-        return slab_bytes_total + centroids.bytes() + c_rows.bytes() + c_page_off.bytes() + c_page_vec.bytes() +
+        return slab_bytes_total + centroids.bytes() + cnorm.bytes() + dots.bytes() + c_rows.bytes() + c_page_off.bytes() + c_page_vec.bytes() +
                c_page_ids.bytes() + d_rows.bytes() + d_page_off.bytes() + d_page_vec.bytes() + d_page_ids.bytes() +
                ws_coarse.bytes + ws_scan.bytes + q_buf.bytes() + coarse_d.bytes() + out_d.bytes() +
                coarse_i.bytes() + out_i.bytes() + probes.bytes() + zero_probes.bytes() + assign_buf.bytes() +
@@ -171,6 +176,12 @@ int32_t build_flat_view(const float* base, uint64_t n, uint32_t ld, uint32_t pag
     VDB_CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors die here
     *npages_out = npages;
     return VDB_OK;
+}
+
+int32_t refresh_centroid_aux(vdb_index* ix) {
+    VDB_TRY(ix->cnorm.reserve(ix->nlist));
+    VDB_TRY(ix->cmax_bits.reserve(1));
+    return centroid_norms(ix->centroids.p, ix->nlist, ix->ld, ix->cnorm.p, ix->cmax_bits.p, ix->stream);
 }
 
 int32_t refresh_centroid_view(vdb_index* ix) {
@@ -257,6 +268,21 @@ uint64_t slot_bound(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t ppi)
 
 // coarse: top-np centroids of every query = select_nprobe_lists (ivf_flat_index.cpp:298-336)
 int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t np, cudaStream_t stream) {
+    const bool tensor = ix->cfg.coarse_mode == VDB_COARSE_TENSOR ||
+                        (ix->cfg.coarse_mode == VDB_COARSE_AUTO && ix->nlist >= 256);
+    if (tensor && coarse_tensor_supported(ix->nlist, ix->ld, np)) {
+        const uint32_t ldd = round_up(ix->nlist, 4);
+        VDB_TRY(ix->dots.reserve((size_t)nq * ldd));
+        VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
+        VDB_TRY(ix->probes.reserve((size_t)nq * np));
+        VDB_TRY(score_gemm(q_dev, nq, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->ld, ix->dots.p, ldd, stream));
+        return vdb::coarse_select(ix->dots.p, ldd, q_dev, nq, ix->centroids.p, ix->cnorm.p, ix->cmax_bits.p, ix->nlist,
+                                  ix->ld, np, ix->cfg.metric, ix->probes.p, ix->coarse_d.p, nullptr, stream);
+    }
+    if (ix->cfg.coarse_mode == VDB_COARSE_TENSOR) {
+        set_last_error("coarse_mode TENSOR requested but the tensor-core path does not support this shape/driver");
+        return VDB_INVALID_ARGUMENT;
+    }
     VDB_TRY(ix->zero_probes.reserve(nq));
     VDB_CUDA_TRY(cudaMemsetAsync(ix->zero_probes.p, 0, (size_t)nq * 4, stream));
     VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
@@ -368,6 +394,7 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     VDB_TRY(ix->centroids.reserve((size_t)ix->nlist * ix->ld));
     VDB_CUDA_TRY(cudaMemsetAsync(ix->centroids.p, 0, ix->centroids.bytes(), ix->stream));  // centroids_ value-init (:22)
     VDB_TRY(refresh_centroid_view(ix.get()));
+    VDB_TRY(refresh_centroid_aux(ix.get()));
     VDB_TRY(upload_list_tables(ix.get()));
     *out = ix.release();
     return VDB_OK;
@@ -379,7 +406,7 @@ int32_t vdb_index_destroy(vdb_index* ix) {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
         for (void* s : ix->slabs) cudaFree(s);
-        ix->centroids.release(); ix->c_rows.release(); ix->c_page_off.release(); ix->c_page_vec.release();
+        ix->centroids.release(); ix->cnorm.release(); ix->cmax_bits.release(); ix->dots.release(); ix->c_rows.release(); ix->c_page_off.release(); ix->c_page_vec.release();
         ix->c_page_ids.release(); ix->d_rows.release(); ix->d_page_off.release(); ix->d_page_vec.release();
         ix->d_page_ids.release(); ix->q_buf.release(); ix->coarse_d.release(); ix->out_d.release();
         ix->coarse_i.release(); ix->out_i.release(); ix->probes.release(); ix->zero_probes.release();
@@ -417,6 +444,7 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
             st = kmeans_update_exact(x, (uint32_t)n, ldx, sc.assign, ix->nlist, ix->ld, ix->centroids.p, sc,
                                      ix->stream);
     }
+    if (st == VDB_OK) st = refresh_centroid_aux(ix);
     if (st == VDB_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) {
         set_last_error(std::string("train: ") + cudaGetErrorString(cudaGetLastError()));
         st = VDB_CUDA_ERROR;
@@ -591,6 +619,7 @@ int32_t vdb_index_set_centroids(vdb_index* ix, const float* in) {
     VDB_CUDA_TRY(cudaMemsetAsync(ix->centroids.p, 0, (size_t)ix->nlist * ix->ld * 4, ix->stream));
     VDB_CUDA_TRY(cudaMemcpy2DAsync(ix->centroids.p, (size_t)ix->ld * 4, in, (size_t)ix->dim * 4, (size_t)ix->dim * 4,
                                    ix->nlist, cudaMemcpyDefault, ix->stream));
+    VDB_TRY(refresh_centroid_aux(ix));
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
     ix->trained = true;
     return VDB_OK;

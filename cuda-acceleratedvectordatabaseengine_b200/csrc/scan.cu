@@ -887,9 +887,14 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
     }
     __syncthreads();
 
-    __shared__ uint32_t s_tot;
-    for (uint32_t pr = 0; pr < p.np; ++pr) {
-        uint32_t slot0, ns;
+    // Pairs are handled 256 at a time.  A: one warp per pair adds up the entries its page ranges
+    // produced.  B: pairs that are already a list's top-k (one range, or <= k entries in all) go
+    // straight to the cross-list pool, all at once (warp per pair, lane per slot).  C: the few pairs
+    // with more than k survivors get the per-list selection first.
+    constexpr uint32_t CH = 256;
+    __shared__ uint32_t s_ptot[CH];
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    auto pair_slots = [&](uint32_t pr, uint32_t& slot0, uint32_t& ns) {
         if (p.pair_slot) {
             const uint32_t pair = q * p.np + pr;
             slot0 = p.pair_slot[pair];
@@ -898,73 +903,104 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
             slot0 = pr * p.nq + q;
             ns = 1;
         }
-        if (ns == 0) continue;
-        // entries this (query, list) pair produced over all its page ranges
-        uint32_t tot = ns * k;
-        if (p.part_cnt) {
-            if (tid == 0) s_tot = 0;
-            __syncthreads();
-            uint32_t mine = 0;
-            for (uint32_t sidx = tid; sidx < ns; sidx += MERGE_THREADS) mine += p.part_cnt[slot0 + sidx];
-            if (mine) atomicAdd(&s_tot, mine);
-            __syncthreads();
-            tot = s_tot;
-            __syncthreads();
-        }
-        if (tot == 0) continue;
-        const bool direct = (ns == 1) || (tot <= k);  // already the list's top-k: no per-list selection needed
-        if (direct || tot <= P) {
-            // one parallel pass: thread t takes slots t, t+256, ... and pushes their entries
-            const MergePool& dst = direct ? L2 : L1;
-            if (direct) {
-                if (cnt2 + min(tot, ns * k) > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+    };
+    for (uint32_t pr0 = 0; pr0 < p.np; pr0 += CH) {
+        const uint32_t npc = min(CH, p.np - pr0);
+        for (uint32_t pl = warp; pl < npc; pl += MERGE_THREADS / 32) {
+            uint32_t slot0, ns;
+            pair_slots(pr0 + pl, slot0, ns);
+            uint32_t t = 0;
+            if (p.part_cnt) {
+                for (uint32_t sidx = lane; sidx < ns; sidx += 32) t += p.part_cnt[slot0 + sidx];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             } else {
-                if (tid == 0) {
-                    cnt1 = 0;
-                    thr1 = INFINITY;
-                }
-                __syncthreads();
+                t = ns * k;
             }
-            const float thr = *dst.thr;
-            for (uint32_t sidx = tid; sidx < ns; sidx += MERGE_THREADS) {
-                const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
-                const float* sd = p.part_d + (size_t)(slot0 + sidx) * k;
-                const uint64_t* si = p.part_i + (size_t)(slot0 + sidx) * k;
-                for (uint32_t e = 0; e < n; ++e) {
-                    const float d = sd[e];
-                    const uint64_t id = si[e];
-                    if (id == ID_PAD && d == FLT_MAX) continue;
-                    if (d <= thr) {
-                        const uint32_t pos = atomicAdd(dst.cnt, 1u);
-                        if (pos < P) {
-                            dst.d[pos] = d;
-                            dst.id[pos] = id;
+            if (lane == 0) s_ptot[pl] = t;
+        }
+        __syncthreads();
+        // room for every direct pair of the chunk at once?
+        const bool bulk = (uint64_t)npc * k + k <= P;
+        if (bulk) {
+            if (cnt2 + npc * k > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+            const float thr = thr2;
+            for (uint32_t pl = warp; pl < npc; pl += MERGE_THREADS / 32) {
+                uint32_t slot0, ns;
+                pair_slots(pr0 + pl, slot0, ns);
+                const uint32_t tot = s_ptot[pl];
+                if (tot == 0 || !((ns == 1) || (tot <= k))) continue;
+                for (uint32_t sidx = lane; sidx < ns; sidx += 32) {
+                    const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                    const float* sd = p.part_d + (size_t)(slot0 + sidx) * k;
+                    const uint64_t* si = p.part_i + (size_t)(slot0 + sidx) * k;
+                    for (uint32_t e = 0; e < n; ++e) {
+                        const float d = sd[e];
+                        const uint64_t id = si[e];
+                        if (id == ID_PAD && d == FLT_MAX) continue;
+                        if (d <= thr) {
+                            const uint32_t pos = atomicAdd(&cnt2, 1u);
+                            if (pos < P) {
+                                d2[pos] = d;
+                                i2[pos] = id;
+                            }
                         }
                     }
                 }
             }
             __syncthreads();
-        } else {
-            // rare: more survivors than the pool holds -> slot by slot with intermediate compactions
+        }
+        for (uint32_t pl = 0; pl < npc; ++pl) {
+            const uint32_t tot = s_ptot[pl];
+            if (tot == 0) continue;
+            uint32_t slot0, ns;
+            pair_slots(pr0 + pl, slot0, ns);
+            const bool direct = (ns == 1) || (tot <= k);
+            if (direct && bulk) continue;  // done in B
+            if (direct) {
+                // (large k) one pair at a time into the cross-list pool
+                for (uint32_t sidx = 0; sidx < ns; ++sidx) {
+                    const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                    if (n == 0) continue;
+                    if (cnt2 + n > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
+                    pool_push_block(L2, P, p.part_d + (size_t)(slot0 + sidx) * k, p.part_i + (size_t)(slot0 + sidx) * k, n);
+                }
+                continue;
+            }
+            // level 1: the list's page-range partials -> its top-k, duplicates kept (search_list_cpu)
             if (tid == 0) {
                 cnt1 = 0;
                 thr1 = INFINITY;
             }
             __syncthreads();
-            for (uint32_t sidx = 0; sidx < ns; ++sidx) {
-                const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
-                if (n == 0) continue;
-                if (cnt1 + n > P) pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
-                pool_push_block(L1, P, p.part_d + (size_t)(slot0 + sidx) * k, p.part_i + (size_t)(slot0 + sidx) * k, n);
+            if (tot <= P) {
+                for (uint32_t sidx = tid; sidx < ns; sidx += MERGE_THREADS) {
+                    const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                    const float* sd = p.part_d + (size_t)(slot0 + sidx) * k;
+                    const uint64_t* si = p.part_i + (size_t)(slot0 + sidx) * k;
+                    for (uint32_t e = 0; e < n; ++e) {
+                        const uint32_t pos = atomicAdd(&cnt1, 1u);
+                        if (pos < P) {
+                            d1[pos] = sd[e];
+                            i1[pos] = si[e];
+                        }
+                    }
+                }
+                __syncthreads();
+            } else {
+                for (uint32_t sidx = 0; sidx < ns; ++sidx) {
+                    const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                    if (n == 0) continue;
+                    if (cnt1 + n > P) pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
+                    pool_push_block(L1, P, p.part_d + (size_t)(slot0 + sidx) * k, p.part_i + (size_t)(slot0 + sidx) * k, n);
+                }
             }
-        }
-        if (!direct) {
-            // level 1 done: the list's top-k (duplicates kept) joins the cross-list pool
             pool_compact_block(L1, P, k, false, nullptr, nullptr, s_scan);
             const uint32_t n = cnt1;
             if (cnt2 + n > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
             pool_push_block(L2, P, d1, i1, n);
         }
+        __syncthreads();
     }
     pool_compact_block(L2, P, k, true, d3, i3, s_scan);
     const uint32_t nc = cnt2;

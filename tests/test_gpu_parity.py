@@ -220,6 +220,36 @@ def test_ivf_full_probe_equals_bruteforce_768d():
     assert (D8 >= D - 1e-3).all()
 
 
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+@pytest.mark.parametrize("dim,nlist,nq,nprobe", [(768, 1024, 70, 32), (100, 300, 9, 64), (128, 4096, 64, 16)])
+def test_tensor_core_coarse_matches_oracle(metric, dim, nlist, nq, nprobe):
+    """tcgen05 TF32 contraction + fp32 re-check == select_nprobe_lists; must not depend on tensor rounding"""
+    x = O.gaussian(1000 + dim, nlist + nq, dim)
+    cent, q = x[:nlist] * np.linspace(0.2, 1.5, nlist, dtype=np.float32)[:, None], x[nlist:]
+    ora = O.OracleIndex(dim, nlist, metric)
+    ora.centroids = cent
+    ref = np.stack([ora.select_nprobe(q[i], nprobe) for i in range(nq)])
+    got = {}
+    for mode in (1, 2):  # SIMT scan, tensor cores
+        ix = new_index(dim, nlist, metric, coarse_mode=mode)
+        ix.centroids = cent
+        got[mode] = ix.select_nprobe(q, nprobe)
+        bad = int((got[mode] != ref).any(axis=1).sum())
+        assert bad <= 1, f"mode {mode}: {bad} of {nq} probe lists differ from the reference"
+    assert int((got[1] != got[2]).any(axis=1).sum()) <= 1
+
+
+def test_search_same_under_both_coarse_modes():
+    g, db, q, p = load_case("config1")
+    out = {}
+    for mode in (1, 2):
+        ix = new_index(p["dim"], p["nlist"], p["metric"], coarse_mode=mode)
+        ix.centroids = g["centroids"]
+        ix.add(db)
+        out[mode] = ix.search(q, pkg.SearchParams(nprobe=p["nprobe"], k=p["k"]))
+        check_search(out[mode][0], out[mode][1], g["D"], g["I"])
+
+
 def test_merge_topk_entry_point():
     import torch
     parts, nq, k = 4, 9, 10
