@@ -16,12 +16,13 @@
 // Error bound: TF32 keeps 10 mantissa bits and the unit truncates, so each
 // input carries a relative error < 2^-10 and |q.c - tf32(q).tf32(c)| <
 // 2^-9 |q||c| (Cauchy-Schwarz; the fp32 accumulation error is three orders of
-// magnitude below).  With E = 2^-8 |q| max|c| (covers the factor 2 of the L2
-// score, and both metrics), the true nprobe-th score S* satisfies
-// T - E <= S* <= T + E for the approximate nprobe-th score T, hence every true
-// member has an approximate score <= T + 2E: the candidate set is a superset
-// of the exact answer, and the exact re-check makes the result independent of
-// the tensor-core rounding.
+// magnitude below).  With E_n = 2^-8 |q| |c_n| (covers the factor 2 of the L2
+// score, and both metrics) the true score of centroid n lies in
+// [s_n - E_n, s_n + E_n].  Let U be the nprobe-th smallest upper bound
+// s_n + E_n: at least nprobe centroids truly score <= U, so a centroid whose
+// lower bound s_n - E_n exceeds U cannot be among the nprobe best.  Everything
+// else is a candidate and is re-scored in exact fp32, which makes the result
+// independent of the tensor-core rounding.
 #include <cuda.h>
 
 #include <mutex>
@@ -309,11 +310,7 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
     const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* qv = p.queries + (size_t)q * p.ld;
 
-    // approximate scores and |q|
-    for (uint32_t n = tid; n < p.N; n += SEL_THREADS) {
-        const float dot = p.dots[(size_t)q * p.ldd + n];
-        score[n] = (p.metric == VDB_METRIC_L2) ? fmaf(-2.f, dot, p.cnorm[n]) : -dot;
-    }
+    // |q|
     float qq = 0.f;
     for (uint32_t d = tid; d < p.ld; d += SEL_THREADS) qq = fmaf(qv[d], qv[d], qq);
 #pragma unroll
@@ -325,11 +322,29 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
         for (int i = 0; i < SEL_THREADS / 32; ++i) t += s_red[i];
         s_qnorm = sqrtf(t);
         s_prefix = 0;
-        s_rank = p.np - 1;  // 0-based rank of the score we are after
+        s_rank = p.np - 1;  // 0-based rank of the bound we are after
+    }
+    __syncthreads();
+    // per-centroid rounding bound of the tensor-core score (see the file header): E_n = 2^-8 |q| |c_n|, with
+    // 5% + 1e-6 relative slack for the fp32 rounding of the bound and of |c|^2 - 2 q.c themselves
+    const float eq = 1.05f * 0.00390625f * s_qnorm;
+    auto approx = [&](uint32_t n, float& e) {
+        const float dot = p.dots[(size_t)q * p.ldd + n];
+        const float cn = p.cnorm[n];
+        const float sc = (p.metric == VDB_METRIC_L2) ? fmaf(-2.f, dot, cn) : -dot;
+        e = eq * sqrtf(cn) + 1e-6f * fabsf(sc) + 1e-30f;
+        return sc;
+    };
+    // upper bounds of the true scores
+    for (uint32_t n = tid; n < p.N; n += SEL_THREADS) {
+        float e;
+        const float sc = approx(n, e);
+        score[n] = sc + e;
     }
     __syncthreads();
 
-    // radix select (4 x 8 bits, most significant first) of the np-th smallest ordered key
+    // radix select (4 x 8 bits, most significant first) of the np-th smallest upper bound U: at least np
+    // centroids truly score <= U, so the true np-th score is <= U
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         for (uint32_t i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
@@ -352,12 +367,14 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
         }
         __syncthreads();
     }
-    const float T = key2f(s_prefix);
-    // rounding bound of the tensor-core scores (see the file header); the relative slack also
-    // covers the fp32 rounding of the bound itself and of |c|^2 - 2 q.c
-    const float cmax = sqrtf(__uint_as_float(*p.cmax_bits));
-    const float E = 1.05f * 0.00390625f * s_qnorm * cmax + 1e-30f;
-    const float admit = T + 2.f * E + 1e-6f * fabsf(T);
+    const float U = key2f(s_prefix);
+    // a centroid whose lower bound exceeds U cannot be among the np best: lower bound = upper bound - 2 E_n
+    for (uint32_t n = tid; n < p.N; n += SEL_THREADS) {
+        float e;
+        const float sc = approx(n, e);
+        score[n] = sc - e;
+    }
+    const float admit = U;
 
     // candidates, one index chunk at a time so that a chunk plus the running best always fit the sorter
     if (tid == 0) s_nbest = 0;

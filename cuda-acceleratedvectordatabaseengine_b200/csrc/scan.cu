@@ -633,7 +633,16 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         consumer_bar();
         for (uint32_t j = warp; j < qcount; j += CONSUMER_WARPS) {
             compact_pool(s, p, j, lane);
-            const uint32_t nc = s.cnt[j];
+            // entries beyond the bound the whole grid has proved by now cannot reach the final top-k: drop them
+            // here, so that most partials leave the kernel (nearly) empty and the merge has little to do
+            const float bound = key2f(__ldcg(&p.qthr[s.sqidx[j]]));
+            const uint32_t kept = s.cnt[j];
+            uint32_t nc = 0;
+            for (uint32_t i0 = 0; i0 < kept; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool ok = i < kept && s.pool_d[(size_t)j * p.P + i] <= bound;
+                nc += __popc(__ballot_sync(0xffffffffu, ok));  // sorted ascending: survivors are a prefix
+            }
             const size_t slot = s.spair[j];
             for (uint32_t i = lane; i < nc; i += 32) {
                 p.part_d[slot * p.k + i] = s.pool_d[(size_t)j * p.P + i];
@@ -759,6 +768,7 @@ struct MergeParams {
 };
 
 constexpr int MERGE_THREADS = 256;
+constexpr uint32_t MERGE_W = 256;  // per-warp scratch entries for the per-list selection
 
 struct MergePool {
     float* d;
@@ -872,9 +882,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
     uint64_t* i1 = (uint64_t*)msmem;
     uint64_t* i2 = i1 + P;
     uint64_t* i3 = i2 + P;  // scratch of the de-duplicating compaction
-    float* d1 = (float*)(i3 + P);
+    uint64_t* wi = i3 + P;  // [8 warps][MERGE_W]
+    float* d1 = (float*)(wi + (MERGE_THREADS / 32) * MERGE_W);
     float* d2 = d1 + P;
     float* d3 = d2 + P;
+    float* wd = d3 + P;
     __shared__ uint32_t cnt1, cnt2;
     __shared__ float thr1, thr2;
     __shared__ uint32_t s_scan[MERGE_THREADS / 32 + 1];
@@ -920,32 +932,77 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
             if (lane == 0) s_ptot[pl] = t;
         }
         __syncthreads();
-        // room for every direct pair of the chunk at once?
+        // room for every pair's (at most k) contributions of the chunk at once?
         const bool bulk = (uint64_t)npc * k + k <= P;
         if (bulk) {
             if (cnt2 + npc * k > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
             const float thr = thr2;
+            float* wd_ = wd + warp * MERGE_W;
+            uint64_t* wi_ = wi + warp * MERGE_W;
             for (uint32_t pl = warp; pl < npc; pl += MERGE_THREADS / 32) {
                 uint32_t slot0, ns;
                 pair_slots(pr0 + pl, slot0, ns);
                 const uint32_t tot = s_ptot[pl];
-                if (tot == 0 || !((ns == 1) || (tot <= k))) continue;
-                for (uint32_t sidx = lane; sidx < ns; sidx += 32) {
-                    const uint32_t n = p.part_cnt ? p.part_cnt[slot0 + sidx] : k;
+                if (tot == 0) continue;
+                const bool direct = (ns == 1) || (tot <= k);
+                if (!direct && tot > MERGE_W) continue;  // left to the block-wide path below
+                // lane per slot: gather the pair's entries, straight into the cross-list pool when they already
+                // are the list's top-k, else into this warp's scratch for the per-list selection
+                uint32_t wcnt = 0;
+                for (uint32_t s0 = 0; s0 < ns; s0 += 32) {
+                    const uint32_t sidx = s0 + lane;
+                    const uint32_t n = sidx < ns ? (p.part_cnt ? p.part_cnt[slot0 + sidx] : k) : 0;
                     const float* sd = p.part_d + (size_t)(slot0 + sidx) * k;
                     const uint64_t* si = p.part_i + (size_t)(slot0 + sidx) * k;
-                    for (uint32_t e = 0; e < n; ++e) {
-                        const float d = sd[e];
-                        const uint64_t id = si[e];
-                        if (id == ID_PAD && d == FLT_MAX) continue;
-                        if (d <= thr) {
+                    if (direct) {
+                        for (uint32_t e = 0; e < n; ++e) {
+                            const float d = sd[e];
+                            const uint64_t id = si[e];
+                            if (id == ID_PAD && d == FLT_MAX) continue;
+                            if (d <= thr) {
+                                const uint32_t pos = atomicAdd(&cnt2, 1u);
+                                if (pos < P) {
+                                    d2[pos] = d;
+                                    i2[pos] = id;
+                                }
+                            }
+                        }
+                    } else {
+                        // exclusive prefix of n over the lanes = where this slot's entries go in the scratch
+                        uint32_t x = n;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                            if (lane >= (uint32_t)o) x += y;
+                        }
+                        const uint32_t base = wcnt + x - n;
+                        for (uint32_t e = 0; e < n; ++e) {
+                            wd_[base + e] = sd[e];
+                            wi_[base + e] = si[e];
+                        }
+                        wcnt += __shfl_sync(0xffffffffu, x, 31);
+                    }
+                }
+                if (!direct) {
+                    // level 1 by one warp: the list's top-k, duplicates kept (search_list_cpu), then on to the pool
+                    const uint32_t n2 = dev_next_pow2(max(wcnt, 1u));
+                    for (uint32_t i = wcnt + lane; i < n2; i += 32) {
+                        wd_[i] = FLT_MAX;
+                        wi_[i] = ID_PAD;
+                    }
+                    __syncwarp();
+                    bitonic_sort_pairs(wd_, wi_, n2, lane, 32, [] { __syncwarp(); });
+                    const uint32_t take = min(wcnt, k);
+                    for (uint32_t i = lane; i < take; i += 32) {
+                        if (wd_[i] <= thr) {
                             const uint32_t pos = atomicAdd(&cnt2, 1u);
                             if (pos < P) {
-                                d2[pos] = d;
-                                i2[pos] = id;
+                                d2[pos] = wd_[i];
+                                i2[pos] = wi_[i];
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
             __syncthreads();
@@ -956,7 +1013,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
             uint32_t slot0, ns;
             pair_slots(pr0 + pl, slot0, ns);
             const bool direct = (ns == 1) || (tot <= k);
-            if (direct && bulk) continue;  // done in B
+            if (bulk && (direct || tot <= MERGE_W)) continue;  // done by the warps above
             if (direct) {
                 // (large k) one pair at a time into the cross-list pool
                 for (uint32_t sidx = 0; sidx < ns; ++sidx) {
@@ -1162,10 +1219,10 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot; mp.part_cnt = ws.part_cnt;
     mp.nq = nq; mp.np = np; mp.k = k; mp.P = merge_pool_size(k);
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = out_u32;
-    const uint32_t msmem = mp.P * 36;
+    const uint32_t msmem = mp.P * 36 + (MERGE_THREADS / 32) * MERGE_W * 12;
     static bool mconf[8] = {false};
     if (dev < 8 && !mconf[dev]) {
-        VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36));
+        VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36 + (MERGE_THREADS / 32) * MERGE_W * 12));
         mconf[dev] = true;
     }
     merge_kernel<<<nq, MERGE_THREADS, msmem, stream>>>(mp);
@@ -1184,8 +1241,8 @@ int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts,
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
-    VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36));
-    merge_kernel<<<nq, MERGE_THREADS, mp.P * 36, stream>>>(mp);
+    VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36 + (MERGE_THREADS / 32) * MERGE_W * 12));
+    merge_kernel<<<nq, MERGE_THREADS, mp.P * 36 + (MERGE_THREADS / 32) * MERGE_W * 12, stream>>>(mp);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
 }

@@ -60,3 +60,28 @@ def ip_scale(queries, db):
     qn = np.linalg.norm(np.asarray(queries, np.float64), axis=1)
     vn = np.linalg.norm(np.asarray(db, np.float64), axis=1).max()
     return qn * vn
+
+
+def check_probes(got, ref, queries, centroids, metric, rtol=RTOL):
+    """Probe lists vs select_nprobe_lists: equal, or different only where the centroid distances tie within
+    the tolerance (rank swaps, or a swap across the nprobe-th boundary).  Returns the number of such ties."""
+    got = np.asarray(got).astype(np.int64)
+    ref = np.asarray(ref).astype(np.int64)
+    assert got.shape == ref.shape
+    q = np.asarray(queries, np.float64)
+    c = np.asarray(centroids, np.float64)
+    ties = 0
+    for i in np.argwhere((got != ref).any(axis=1)).ravel():
+        if metric == 0:
+            d = ((q[i][None, :] - c) ** 2).sum(1)
+            tol = 2 * rtol * d
+        else:
+            d = -(c @ q[i])
+            tol = np.full_like(d, 2 * rtol * np.linalg.norm(q[i]) * np.linalg.norm(c, axis=1).max())
+        assert len(set(got[i].tolist())) == got.shape[1], "duplicate list id in a probe list"
+        for pos in np.argwhere(got[i] != ref[i]).ravel():
+            a, b = got[i, pos], ref[i, pos]
+            assert abs(d[a] - d[b]) <= max(tol[a], tol[b]), \
+                f"query {i} rank {pos}: list {a} (d={d[a]}) vs reference list {b} (d={d[b]})"
+            ties += 1
+    return ties

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from parity import check_search, ip_scale, FLT_MAX, ID_PAD
+from parity import check_search, check_probes, ip_scale, FLT_MAX, ID_PAD
 
 pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
 pytestmark = pytest.mark.gpu
@@ -41,8 +41,7 @@ def test_search_with_reference_centroids_matches_golden(name):
     assert ix.get_total_vectors() == db.shape[0]
     probes = ix.select_nprobe(q, p["nprobe"])
     # coarse order is (dist, list id); a swap is only legal between near-equal centroid distances
-    diff = (probes != g["probes"]).any(axis=1).sum()
-    assert diff <= 1, f"{diff} queries with different probe lists"
+    check_probes(probes, g["probes"], q, g["centroids"], p["metric"])
     D, I = ix.search(q, pkg.SearchParams(nprobe=p["nprobe"], k=p["k"]))
     ties = check_search(D, I, g["D"], g["I"], scale=scale_for(p["metric"], q, db))
     assert ties <= 2
@@ -234,9 +233,8 @@ def test_tensor_core_coarse_matches_oracle(metric, dim, nlist, nq, nprobe):
         ix = new_index(dim, nlist, metric, coarse_mode=mode)
         ix.centroids = cent
         got[mode] = ix.select_nprobe(q, nprobe)
-        bad = int((got[mode] != ref).any(axis=1).sum())
-        assert bad <= 1, f"mode {mode}: {bad} of {nq} probe lists differ from the reference"
-    assert int((got[1] != got[2]).any(axis=1).sum()) <= 1
+        ties = check_probes(got[mode], ref, q, cent, metric)
+        assert ties <= nq // 8 + 2, f"mode {mode}: {ties} tie-explained differences"
 
 
 def test_search_same_under_both_coarse_modes():
