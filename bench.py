@@ -95,6 +95,16 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan_kernel launch from the committed ncu --set full
+    capture of this same workload (profiles/scan_traffic.json, written from the .ncu-rep by tools/ncu_summary.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -354,7 +364,7 @@ def run_b200(a):
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
                    "index_gb": round(st.gpu_memory_bytes / 1e9, 2)},
         "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "unique_bytes_per_launch": uniq_bytes,
                      "unique_frac": uniq_bytes / (scan_ms / 1e3) / 1e9 / peak if scan_ms > 0 else 0.0,
                      "kernel_ms": scan_ms, "scan_items_per_launch": items / a.steps,
@@ -363,7 +373,8 @@ def run_b200(a):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
                 "d2h_bytes_per_step": a.batch * a.k * 12},
-        "gpu_launches": a.steps * (6 + (1 if world > 1 else 0)),
+        # per step: score_gemm (tcgen05) + coarse_select + build_groups + scan + merge (+ the cross-rank merge)
+        "gpu_launches": a.steps * (5 + (1 if world > 1 else 0)),
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
