@@ -356,14 +356,35 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t rank = s_rank, b = 0;
-            for (; b < 256; ++b) {
-                if (rank < hist[b]) break;
-                rank -= hist[b];
+        if (warp == 0) {
+            // bin holding the wanted rank: inclusive prefix over 256 bins, 8 per lane
+            uint32_t h8[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                h8[i] = hist[lane * 8 + i];
+                sum += h8[i];
             }
-            s_rank = rank;
-            s_prefix = prefix | (b << shift);
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += y;
+            }
+            const uint32_t rank = s_rank;
+            uint32_t before = incl - sum;  // keys in the bins of lower lanes
+            const bool mine = rank >= before && rank < incl;
+            if (mine) {
+                uint32_t b = 0, r = rank - before;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (r >= h8[i] && b == (uint32_t)i) {
+                        r -= h8[i];
+                        b = i + 1;
+                    }
+                }
+                s_rank = r;
+                s_prefix = prefix | ((lane * 8 + b) << shift);
+            }
         }
         __syncthreads();
     }
@@ -375,11 +396,21 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
         score[n] = sc - e;
     }
     const float admit = U;
+    __shared__ uint32_t s_total;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    {
+        uint32_t mine = 0;
+        for (uint32_t n = tid; n < p.N; n += SEL_THREADS) mine += (score[n] <= admit);
+        if (mine) atomicAdd(&s_total, mine);
+    }
+    __syncthreads();
 
     // candidates, one index chunk at a time so that a chunk plus the running best always fit the sorter
     if (tid == 0) s_nbest = 0;
     uint32_t total_cand = 0;
-    const uint32_t chunk = SEL_CAND - p.np;
+    // all candidates at once when they fit the sorter (the usual case), else one index chunk at a time
+    const uint32_t chunk = (s_total + p.np <= SEL_CAND) ? p.N : SEL_CAND - p.np;
     for (uint32_t n0 = 0; n0 < p.N; n0 += chunk) {
         __syncthreads();
         if (tid == 0) s_ncand = s_nbest;  // entries [0, nbest) hold the best so far

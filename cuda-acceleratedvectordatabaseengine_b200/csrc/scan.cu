@@ -97,11 +97,21 @@ __device__ __forceinline__ uint32_t n_ranges(const ListTable& lt, uint32_t l, ui
 
 // ------------------------------------------------------- 1. probe grouping
 
+// SMEM: the four per-list work arrays live in dynamic shared memory (nlist <= 8192) instead of global
+// scratch, which removes most of the kernel's global round trips.
+template <bool SMEM>
 __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const uint32_t* __restrict__ probes,
                                                             uint32_t npairs, uint32_t ppi, WorkList wl) {
     __shared__ uint32_t s_warp[33];
+    extern __shared__ uint32_t s_lists[];
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
     const uint32_t nlist = lt.nlist;
+    if (SMEM) {
+        wl.gcount = s_lists;
+        wl.gfill = s_lists + (nlist + 1);
+        wl.goff = s_lists + 2 * (nlist + 1);
+        wl.ioff = s_lists + 3 * (nlist + 1);
+    }
 
     for (uint32_t l = tid; l < nlist; l += NT) {
         wl.gcount[l] = 0;
@@ -186,23 +196,37 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
     }
     // one item per (list, page range); the scan loops over the list's query tiles inside the item, so the
     // second and later tiles re-read the same rows from L2 right after the first brought them in
-    for (uint32_t l = tid; l < nlist; l += NT) {
-        uint32_t c = wl.gcount[l];
-        if (!c) continue;
-        const uint32_t nr = n_ranges(lt, l, ppi);
-        const uint32_t o = wl.ioff[l], g0 = wl.goff[l];
-        const uint32_t pg_first = lt.page_off[l], npages = lt.page_off[l + 1] - pg_first, rows = lt.rows[l];
-        for (uint32_t r = 0; r < nr; ++r) {
-            ScanItem it;
-            it.gbase = g0;
-            it.gcount = c;
-            it.range = r;
-            it.pg0 = pg_first + r * ppi;
-            it.npg = min(ppi, npages - r * ppi);
-            it.row_base = r * ppi * lt.page_rows;
-            it.rows_left = rows - it.row_base;
-            it.list = l;
-            wl.items[o + r] = it;
+    auto write_item = [&](uint32_t l, uint32_t r, uint32_t slot) {
+        const uint32_t pg_first = lt.page_off[l], npages = lt.page_off[l + 1] - pg_first;
+        uint4 lo, hi;
+        lo.x = wl.goff[l];                      // gbase
+        lo.y = wl.gcount[l];                    // gcount
+        lo.z = r;                               // range
+        lo.w = pg_first + r * ppi;              // pg0
+        hi.x = min(ppi, npages - r * ppi);      // npg
+        hi.y = r * ppi * lt.page_rows;          // row_base
+        hi.z = lt.rows[l] - hi.y;               // rows_left
+        hi.w = l;                               // list
+        uint4* dst = reinterpret_cast<uint4*>(wl.items + slot);
+        dst[0] = lo;
+        dst[1] = hi;
+    };
+    if (SMEM) {
+        // thread per item: the owning list is found by binary search in the (shared-memory) item offsets
+        const uint32_t total = wl.ioff[nlist];
+        for (uint32_t idx = tid; idx < total; idx += NT) {
+            uint32_t lo = 0, hi = nlist;  // last l with ioff[l] <= idx (empty lists share their successor's offset)
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (wl.ioff[mid] <= idx) lo = mid; else hi = mid - 1;
+            }
+            write_item(lo, idx - wl.ioff[lo], idx);
+        }
+    } else {
+        for (uint32_t l = tid; l < nlist; l += NT) {
+            if (!wl.gcount[l]) continue;
+            const uint32_t nr = n_ranges(lt, l, ppi), o = wl.ioff[l];
+            for (uint32_t r = 0; r < nr; ++r) write_item(l, r, o + r);
         }
     }
 }
@@ -809,7 +833,33 @@ __device__ __forceinline__ void pool_compact_block(const MergePool& pl, uint32_t
     }
     __syncthreads();
     bitonic_sort_pairs(pl.d, pl.id, n2, tid, MERGE_THREADS, [] { __syncthreads(); });
-    if (dedup && c > 1) {
+    bool may_dup = dedup && c > 1;
+    if (may_dup && c <= P / 2) {
+        // cheap screen: insert the ids into an open-addressing table (the scratch id array); only if some id
+        // really occurs twice is the quadratic stable de-duplication below needed
+        __shared__ uint32_t s_dup;
+        if (tid == 0) s_dup = 0;
+        for (uint32_t i = tid; i < P; i += MERGE_THREADS) tmp_i[i] = ID_PAD;
+        __syncthreads();
+        for (uint32_t i = tid; i < c; i += MERGE_THREADS) {
+            const uint64_t id = pl.id[i];
+            uint32_t h = (uint32_t)((id * 0x9E3779B97F4A7C15ull) >> 40) & (P - 1);
+            for (uint32_t probe = 0; probe < P; ++probe) {
+                const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&tmp_i[h]),
+                                                         (unsigned long long)ID_PAD, (unsigned long long)id);
+                if (old == ID_PAD) break;
+                if (old == id) {
+                    s_dup = 1;
+                    break;
+                }
+                h = (h + 1) & (P - 1);
+            }
+        }
+        __syncthreads();
+        may_dup = s_dup != 0;
+        __syncthreads();
+    }
+    if (may_dup) {
         // keep[i] = no earlier entry carries the same id; stable compaction through tmp
         const uint32_t per = (c + MERGE_THREADS - 1) / MERGE_THREADS;
         const uint32_t lo = min(tid * per, c), hi = min(lo + per, c);
@@ -946,43 +996,50 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
                 if (tot == 0) continue;
                 const bool direct = (ns == 1) || (tot <= k);
                 if (!direct && tot > MERGE_W) continue;  // left to the block-wide path below
-                // lane per slot: gather the pair's entries, straight into the cross-list pool when they already
-                // are the list's top-k, else into this warp's scratch for the per-list selection
+                // the pair's partial slots are contiguous, so (slot, entry) flattens to one coalesced index range;
+                // valid entries go straight into the cross-list pool when they already are the list's top-k,
+                // else into this warp's scratch for the per-list selection
                 uint32_t wcnt = 0;
-                for (uint32_t s0 = 0; s0 < ns; s0 += 32) {
-                    const uint32_t sidx = s0 + lane;
-                    const uint32_t n = sidx < ns ? (p.part_cnt ? p.part_cnt[slot0 + sidx] : k) : 0;
-                    const float* sd = p.part_d + (size_t)(slot0 + sidx) * k;
-                    const uint64_t* si = p.part_i + (size_t)(slot0 + sidx) * k;
-                    if (direct) {
-                        for (uint32_t e = 0; e < n; ++e) {
-                            const float d = sd[e];
-                            const uint64_t id = si[e];
-                            if (id == ID_PAD && d == FLT_MAX) continue;
-                            if (d <= thr) {
+                const uint32_t span = ns * k;
+                const float* sd = p.part_d + (size_t)slot0 * k;
+                const uint64_t* si = p.part_i + (size_t)slot0 * k;
+                for (uint32_t i0 = 0; i0 < span; i0 += 128) {
+                    float dv[4];
+                    uint64_t iv[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t idx = i0 + u * 32 + lane;
+                        const uint32_t sidx = idx / k, e = idx - sidx * k;
+                        ok[u] = idx < span && e < (p.part_cnt ? p.part_cnt[slot0 + sidx] : k);
+                        dv[u] = ok[u] ? sd[idx] : FLT_MAX;
+                        iv[u] = ok[u] ? si[idx] : ID_PAD;
+                        ok[u] = ok[u] && !(iv[u] == ID_PAD && dv[u] == FLT_MAX);  // padding of a short partial
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (direct) {
+                            if (ok[u] && dv[u] <= thr) {
                                 const uint32_t pos = atomicAdd(&cnt2, 1u);
                                 if (pos < P) {
-                                    d2[pos] = d;
-                                    i2[pos] = id;
+                                    d2[pos] = dv[u];
+                                    i2[pos] = iv[u];
                                 }
                             }
+                        } else {
+                            const uint32_t m = __ballot_sync(0xffffffffu, ok[u]);
+                            if (ok[u]) {
+                                const uint32_t pos = wcnt + __popc(m & ((1u << lane) - 1u));
+                                if (pos < MERGE_W) {
+                                    wd_[pos] = dv[u];
+                                    wi_[pos] = iv[u];
+                                }
+                            }
+                            wcnt += __popc(m);
                         }
-                    } else {
-                        // exclusive prefix of n over the lanes = where this slot's entries go in the scratch
-                        uint32_t x = n;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                            if (lane >= (uint32_t)o) x += y;
-                        }
-                        const uint32_t base = wcnt + x - n;
-                        for (uint32_t e = 0; e < n; ++e) {
-                            wd_[base + e] = sd[e];
-                            wi_[base + e] = si[e];
-                        }
-                        wcnt += __shfl_sync(0xffffffffu, x, 31);
                     }
                 }
+                wcnt = min(wcnt, MERGE_W);
                 if (!direct) {
                     // level 1 by one warp: the list's top-k, duplicates kept (search_list_cpu), then on to the pool
                     const uint32_t n2 = dev_next_pow2(max(wcnt, 1u));
@@ -1178,7 +1235,20 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats,
                 ws.qthr, nq};
     if (ev) cudaEventRecord(ev[0], stream);
-    build_groups_kernel<<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, ppi, wl);
+    if (lt.nlist <= 8192) {
+        const uint32_t gsm = 4 * (lt.nlist + 1) * 4;
+        static bool gconf[8] = {false};
+        int gdev = 0;
+        cudaGetDevice(&gdev);
+        if (gdev < 8 && !gconf[gdev]) {
+            VDB_CUDA_TRY(cudaFuncSetAttribute(build_groups_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              4 * 8193 * 4));
+            gconf[gdev] = true;
+        }
+        build_groups_kernel<true><<<1, 1024, gsm, stream>>>(lt, probes_dev, npairs, ppi, wl);
+    } else {
+        build_groups_kernel<false><<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, ppi, wl);
+    }
     VDB_CUDA_TRY(cudaGetLastError());
 
     ScanParams sp;

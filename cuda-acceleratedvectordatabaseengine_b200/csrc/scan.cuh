@@ -7,7 +7,7 @@ namespace vdb {
 
 // One unit of scan work: page range `range` of list `list`, scanned once per
 // tile of the queries that probe the list.
-struct ScanItem {
+struct alignas(16) ScanItem {
     uint32_t gbase, gcount;  // the (query, probe) pairs that name this list: gpairs[gbase .. gbase+gcount)
     uint32_t range;          // index of the page range inside the list (selects the partial-result slot)
     uint32_t pg0, npg;       // absolute first page in the page tables, pages in this item
