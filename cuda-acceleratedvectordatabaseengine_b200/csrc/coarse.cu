@@ -23,89 +23,18 @@
 // lower bound s_n - E_n exceeds U cannot be among the nprobe best.  Everything
 // else is a candidate and is re-scored in exact fp32, which makes the result
 // independent of the tensor-core rounding.
-#include <cuda.h>
-
-#include <mutex>
-
 #include "coarse.cuh"
+#include "tc_common.cuh"
 #include "topk.cuh"
 
 namespace vdb {
 namespace {
 
-// ------------------------------------------------------------------ PTX glue
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// tcgen05.commit: arrives on the mbarrier when every MMA issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major tile
-// whose rows are 128 bytes apart, 128-byte swizzle, 8-row groups 1024 bytes
-// apart, descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                                  // leading byte offset (unused with swizzle), [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset, [32,46)
-    d |= (uint64_t)1 << 46;                                  // version, [46,48)
-    d |= (uint64_t)2 << 61;                                  // layout type SWIZZLE_128B, [61,64)
-    return d;
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulator,
-// TF32 x TF32, both operands K-major, N and M encoded >>3 and >>4.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
+using namespace tc;
 
 // ------------------------------------------------------------ 1. score GEMM
 
 constexpr int GM = 128;      // rows of A per CTA (UMMA M)
-constexpr int GK = 32;       // fp32 elements per stage row = 128 bytes = one swizzle atom
 constexpr int GSTAGES = 4;
 constexpr int GEMM_THREADS = 192;  // warps 0-3 epilogue (TMEM lane quadrants), 4 TMA producer, 5 MMA issuer + TMEM owner
 
@@ -212,45 +141,6 @@ score_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 5) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
     }
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    return fn;
-}
-
-// [rows][cols] fp32, row stride ld floats -> boxes of [box_rows][32 floats], 128-byte swizzle, zero fill out of bounds
-int32_t make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-    EncodeTiledFn fn = encode_tiled();
-    if (!fn) {
-        set_last_error("cuTensorMapEncodeTiled is not available from this driver");
-        return VDB_CUDA_ERROR;
-    }
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)GK, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-        return VDB_CUDA_ERROR;
-    }
-    return VDB_OK;
 }
 
 constexpr int BN_COARSE = 64;

@@ -115,6 +115,7 @@ struct vdb_index {
     DevBuf<uint64_t> ids_stage;
     ScanLaunchInfo last_scan_info{};
     bool have_search = false;
+    AssignTcScratch tc_assign;
     // profiling: event quintuples (coarse start, then the four scan_search marks) per search
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -130,6 +131,16 @@ struct vdb_index {
 };
 
 namespace {
+
+// assign_to_lists: tensor cores + exact re-check for large centroid tables (bit-identical to the scalar
+// kernel), the scalar order-exact kernel otherwise or when train_mode = EXACT asks for it
+int32_t assign_rows(vdb_index* ix, const float* x, uint64_t n, uint32_t* out, cudaStream_t stream) {
+    if (ix->cfg.train_mode != VDB_TRAIN_EXACT && n >= 256 && assign_tensor_supported(ix->nlist, ix->ld))
+        return kmeans_assign_tensor(x, n, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric, out,
+                                    ix->tc_assign, stream);
+    return kmeans_assign_exact(x, n, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric, out, nullptr,
+                               stream);
+}
 
 ListTable centroid_table(vdb_index* ix) {
     ListTable lt;
@@ -412,6 +423,7 @@ int32_t vdb_index_destroy(vdb_index* ix) {
         ix->coarse_i.release(); ix->out_i.release(); ix->probes.release(); ix->zero_probes.release();
         ix->assign_buf.release(); ix->hist_buf.release(); ix->fill_buf.release(); ix->stage_buf.release();
         ix->ids_stage.release();
+        ix->tc_assign.release();
         ix->ws_coarse.release();
         ix->ws_scan.release();
         for (auto e : ix->prof_events) cudaEventDestroy(e);
@@ -438,8 +450,7 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
         st = kmeanspp_seed_exact(x, (uint32_t)n, ldx, ix->dim, ix->ld, ix->nlist, ix->centroids.p, sc, ix->stream);
     // exactly 10 Lloyd iterations; assignment honours the index metric (:109-142, :275-285)
     for (int iter = 0; iter < 10 && st == VDB_OK; ++iter) {
-        st = kmeans_assign_exact(x, n, ldx, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric, sc.assign,
-                                 nullptr, ix->stream);
+        st = assign_rows(ix, x, n, sc.assign, ix->stream);
         if (st == VDB_OK)
             st = kmeans_update_exact(x, (uint32_t)n, ldx, sc.assign, ix->nlist, ix->ld, ix->centroids.p, sc,
                                      ix->stream);
@@ -479,8 +490,7 @@ int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
         }
         // assign (ivf_flat_index.cpp:151-157)
         VDB_TRY(ix->assign_buf.reserve(m));
-        VDB_TRY(kmeans_assign_exact(x, m, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric,
-                                    ix->assign_buf.p, nullptr, ix->stream));
+        VDB_TRY(assign_rows(ix, x, m, ix->assign_buf.p, ix->stream));
         // per-list counts -> grow the page chains
         VDB_TRY(ix->hist_buf.reserve(ix->nlist));
         VDB_TRY(ix->fill_buf.reserve(ix->nlist));
@@ -591,8 +601,7 @@ int32_t vdb_index_assign(vdb_index* ix, const float* vectors, uint64_t n, uint32
     const float* x = nullptr;
     VDB_TRY(stage_rows(ix, vectors, n, ix->stage_buf, &x, ix->stream));
     VDB_TRY(ix->assign_buf.reserve(n));
-    VDB_TRY(kmeans_assign_exact(x, n, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric,
-                                ix->assign_buf.p, nullptr, ix->stream));
+    VDB_TRY(assign_rows(ix, x, n, ix->assign_buf.p, ix->stream));
     VDB_CUDA_TRY(cudaMemcpyAsync(lists, ix->assign_buf.p, n * 4,
                                  is_device_ptr(lists) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                                  ix->stream));

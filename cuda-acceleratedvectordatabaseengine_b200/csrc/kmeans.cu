@@ -24,7 +24,8 @@ constexpr int TV = 64, TC = 64, DK = 32;
 __global__ void __launch_bounds__(256) assign_exact_kernel(const float* __restrict__ x, uint64_t n, uint32_t ldx,
                                                            const float* __restrict__ c, uint32_t nc, uint32_t ldc,
                                                            uint32_t dim, int metric, uint32_t* __restrict__ assign,
-                                                           float* __restrict__ dist_out) {
+                                                           float* __restrict__ dist_out,
+                                                           const uint32_t* __restrict__ row_index) {
     __shared__ float sv[TV][DK + 1];
     __shared__ float sc[TC][DK + 1];
     __shared__ float sbd[TV][17];
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(256) assign_exact_kernel(const float* __restri
             for (uint32_t e = tid; e < TV * DK; e += 256) {
                 const uint32_t r = e / DK, dd = e % DK;
                 const uint64_t v = v0 + r;
-                sv[r][dd] = (v < n && d0 + dd < dim) ? x[v * ldx + d0 + dd] : 0.f;
+                const uint64_t src = (v < n && row_index) ? row_index[v] : v;  // optional gather of selected rows
+                sv[r][dd] = (v < n && d0 + dd < dim) ? x[src * ldx + d0 + dd] : 0.f;
                 const uint32_t cc = c0 + r;
                 sc[r][dd] = (cc < nc && d0 + dd < dim) ? c[(size_t)cc * ldc + d0 + dd] : 0.f;
             }
@@ -113,8 +115,9 @@ __global__ void __launch_bounds__(256) assign_exact_kernel(const float* __restri
         }
         const uint64_t v = v0 + tid;
         if (v < n) {
-            assign[v] = b;
-            if (dist_out) dist_out[v] = d;
+            const uint64_t dst = row_index ? row_index[v] : v;
+            assign[dst] = b;
+            if (dist_out) dist_out[dst] = d;
         }
     }
 }
@@ -461,11 +464,6 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, uint32_t lds, uin
     dst[i] = d < dim ? src[r * lds + d] : 0.f;
 }
 
-__global__ void gather_ids_kernel(const uint64_t* __restrict__ page_ids_base, uint32_t rows, uint64_t* out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows) out[i] = page_ids_base[i];
-}
-
 }  // namespace
 
 size_t rng_state_bytes() { return sizeof(DevRng); }
@@ -476,7 +474,19 @@ int32_t kmeans_assign_exact(const float* x, uint64_t n, uint32_t ldx, const floa
     VDB_REQUIRE(nc >= 1 && dim >= 1, "assign: empty centroid table");
     const uint64_t blocks = (n + TV - 1) / TV;
     VDB_REQUIRE(blocks < (1ull << 31), "assign: too many rows for one call");
-    assign_exact_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, n, ldx, c, nc, ldc, dim, metric, assign, dist_out);
+    assign_exact_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, n, ldx, c, nc, ldc, dim, metric, assign, dist_out,
+                                                              nullptr);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+// the same for the rows listed in row_index[0..m): results go to assign[row_index[i]]
+int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint64_t m, uint32_t ldx, const float* c,
+                                 uint32_t nc, uint32_t ldc, uint32_t dim, int metric, uint32_t* assign,
+                                 cudaStream_t stream) {
+    if (m == 0) return VDB_OK;
+    assign_exact_kernel<<<(uint32_t)((m + TV - 1) / TV), 256, 0, stream>>>(x, m, ldx, c, nc, ldc, dim, metric, assign,
+                                                                            nullptr, row_index);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
 }

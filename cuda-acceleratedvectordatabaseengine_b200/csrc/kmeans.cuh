@@ -23,6 +23,29 @@ struct KMeansScratch {
 
 int32_t kmeans_assign_exact(const float* x, uint64_t n, uint32_t ldx, const float* c, uint32_t nc, uint32_t ldc,
                             uint32_t dim, int metric, uint32_t* assign, float* dist_out, cudaStream_t stream);
+int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint64_t m, uint32_t ldx, const float* c,
+                                 uint32_t nc, uint32_t ldc, uint32_t dim, int metric, uint32_t* assign,
+                                 cudaStream_t stream);
+
+// tensor-core assignment (assign_tc.cu): bit-identical to kmeans_assign_exact, O(n nlist dim) on tcgen05
+struct AssignTcScratch {
+    float* xnorm = nullptr;
+    float* cnorm2 = nullptr;
+    uint32_t* cand_idx = nullptr;
+    uint32_t* cand_cnt = nullptr;
+    uint32_t* overflow_rows = nullptr;
+    uint32_t* overflow_count = nullptr;
+    uint32_t* h_overflow = nullptr;
+    uint64_t cap_n = 0;
+    uint32_t cap_nc = 0;
+    uint32_t last_overflow = 0;
+    int32_t reserve(uint64_t n, uint32_t nc);
+    void release();
+};
+bool assign_tensor_supported(uint32_t nc, uint32_t ld);
+int32_t kmeans_assign_tensor(const float* x, uint64_t n, uint32_t ldx, const float* c, uint32_t nc, uint32_t ldc,
+                             uint32_t dim, int metric, uint32_t* assign, AssignTcScratch& sc, cudaStream_t stream);
+
 int32_t kmeanspp_seed_exact(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
                             float* centroids, KMeansScratch& sc, cudaStream_t stream);
 int32_t kmeans_update_exact(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,

@@ -248,6 +248,41 @@ def test_search_same_under_both_coarse_modes():
         check_search(out[mode][0], out[mode][1], g["D"], g["I"])
 
 
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+@pytest.mark.parametrize("dim,nlist,n", [(96, 300, 5000), (768, 512, 3000), (50, 1000, 2500)])
+def test_tensor_core_assignment_is_bit_exact(metric, dim, nlist, n):
+    """tcgen05 GEMM + bounds + reference-order re-check == assign_to_lists (nlist >= 256 takes this path)"""
+    x = O.gaussian(500 + dim, n + nlist, dim)
+    v, cent = x[:n], x[n:] * np.linspace(0.3, 1.2, nlist, dtype=np.float32)[:, None]
+    ora = O.OracleIndex(dim, nlist, metric)
+    ora.centroids = cent
+    ref = ora.assign(v)
+    for mode in (pkg.TrainMode.AUTO, pkg.TrainMode.EXACT):  # tensor cores, scalar kernel
+        ix = new_index(dim, nlist, metric, train_mode=mode)
+        ix.centroids = cent
+        assert np.array_equal(ix.assign(v), ref), f"train_mode {mode}"
+    # near-duplicate centroids: many candidates per row, ties resolved by the lowest index
+    cent2 = np.repeat(cent[: nlist // 4], 4, axis=0)
+    cent2[1::4] += 1e-7
+    ora.centroids = cent2
+    ix = new_index(dim, nlist, metric)
+    ix.centroids = cent2
+    assert np.array_equal(ix.assign(v[:600]), ora.assign(v[:600]))
+
+
+def test_train_bit_exact_with_tensor_core_assignment():
+    dim, nlist, n = 32, 256, 4096
+    x = O.gaussian(77, n, dim)
+    ora = O.OracleIndex(dim, nlist)
+    ora.train(x)
+    ix = new_index(dim, nlist)
+    ix.train(x)
+    assert np.array_equal(ix.centroids, ora.centroids)
+    ora.add(x)
+    ix.add(x)
+    assert np.array_equal(ix.list_sizes(), ora.list_sizes())
+
+
 def test_merge_topk_entry_point():
     import torch
     parts, nq, k = 4, 9, 10
