@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(32) seed_sample_kernel(DevRng* g, const float*
                                                          uint32_t ldx, uint32_t ld, const float* __restrict__ mind,
                                                          float* __restrict__ ckpt, float* __restrict__ centroids,
                                                          uint32_t cidx, uint32_t* picked) {
-    __shared__ float buf[SEQ_CHUNK];
+    __shared__ __align__(16) float buf[SEQ_CHUNK];
     __shared__ uint32_t s_pick;
     __shared__ float s_start;
     const uint32_t lane = threadIdx.x;
@@ -246,9 +246,29 @@ __global__ void __launch_bounds__(32) seed_sample_kernel(DevRng* g, const float*
         for (uint32_t i = lane; i < SEQ_CHUNK; i += 32) buf[i] = (base + i < n) ? mind[base + i] : 0.f;
         __syncwarp();
         if (lane == 0) {
+            // the dependent fp32 add chain is the critical path (4 cycles per element): keep the shared-memory
+            // loads off it by fetching the next 32 values while the current 32 are being added
             const uint32_t m = min(SEQ_CHUNK, n - base);
-#pragma unroll 8
-            for (uint32_t i = 0; i < m; ++i) run = __fadd_rn(run, buf[i]);
+            const float4* b4 = reinterpret_cast<const float4*>(buf);
+            float4 cur[8], nxt[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[u] = b4[u];
+            uint32_t i = 0;
+            for (; i + 32 <= m; i += 32) {
+                const uint32_t nb = (i + 32) >> 2;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) nxt[u] = b4[min(nb + u, SEQ_CHUNK / 4 - 1)];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    run = __fadd_rn(run, cur[u].x);
+                    run = __fadd_rn(run, cur[u].y);
+                    run = __fadd_rn(run, cur[u].z);
+                    run = __fadd_rn(run, cur[u].w);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+            }
+            for (; i < m; ++i) run = __fadd_rn(run, buf[i]);
             ckpt[ch] = run;  // running sum after this chunk
         }
         __syncwarp();

@@ -348,3 +348,40 @@ def test_cpp_host_mirror_simple_test():
     I = np.array([int(r[2]) for r in rows], np.uint64).reshape(g["I"].shape)
     D = np.array([float(r[3]) for r in rows], np.float32).reshape(g["D"].shape)
     check_search(D, I, g["D"], g["I"])
+
+
+def test_concurrent_searches_from_host_threads():
+    """the gRPC server calls Search from several poller threads on one index (server/main.cpp:92-94)"""
+    import threading
+    g, db, q, p = load_case("ctest_gpu_vs_cpu")
+    ix = new_index(p["dim"], p["nlist"], p["metric"])
+    ix.centroids = g["centroids"]
+    ix.add(db)
+    errs = []
+
+    def worker(lo):
+        try:
+            for _ in range(5):
+                D, I = ix.search(q[lo:lo + 25], pkg.SearchParams(nprobe=p["nprobe"], k=p["k"]))
+                check_search(D, I, g["D"][lo:lo + 25], g["I"][lo:lo + 25])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(lo,)) for lo in (0, 25, 50, 75)]
+    [t_.start() for t_ in th]
+    [t_.join() for t_ in th]
+    assert not errs, errs
+
+
+def test_single_query_and_k1_and_nlist1():
+    x = O.gaussian(2, 3000, 20)
+    ora = O.OracleIndex(20, 1)
+    ora.train(x[:50])
+    ora.add(x[:2900])
+    ix = new_index(20, 1)
+    ix.train(x[:50])
+    ix.add(x[:2900])
+    for nq, k in [(1, 1), (1, 17), (100, 1)]:
+        Dr, Ir = ora.search(x[2900:2900 + nq], 1, k)
+        D, I = ix.search(x[2900:2900 + nq], 1, k)
+        check_search(D, I, Dr, Ir)
