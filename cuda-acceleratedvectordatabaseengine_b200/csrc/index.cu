@@ -446,8 +446,12 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
     if (st == VDB_OK) st = sc.reserve((uint32_t)n, ix->nlist, ix->ld);
     const uint32_t ldx = ix->ld;
     // k-means++ seeding, always L2 (ivf_flat_index.cpp:63-104)
+    // AUTO: the reference's sequential sampling sums (bit-exact) unless that would take minutes
+    const bool exact_seed = ix->cfg.train_mode == VDB_TRAIN_EXACT ||
+                            (ix->cfg.train_mode == VDB_TRAIN_AUTO && (uint64_t)n * ix->nlist <= (2ull << 30));
     if (st == VDB_OK)
-        st = kmeanspp_seed_exact(x, (uint32_t)n, ldx, ix->dim, ix->ld, ix->nlist, ix->centroids.p, sc, ix->stream);
+        st = kmeanspp_seed(x, (uint32_t)n, ldx, ix->dim, ix->ld, ix->nlist, ix->centroids.p, sc, exact_seed,
+                           ix->stream);
     // exactly 10 Lloyd iterations; assignment honours the index metric (:109-142, :275-285)
     for (int iter = 0; iter < 10 && st == VDB_OK; ++iter) {
         st = assign_rows(ix, x, n, sc.assign, ix->stream);
@@ -792,10 +796,11 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
         lt.ids_flat = dids; lt.nlist = 1; lt.page_rows = page_rows; lt.ld = ld;
         VDB_TRY(zero.reserve(nq));
         VDB_CUDA_TRY(cudaMemsetAsync(zero.p, 0, (size_t)nq * 4, s));
-        // items ~ tiles x ranges: aim at a few per SM, and keep the partial buffer modest
-        const uint64_t tiles = (nq + 7) / 8;
-        uint32_t ppi = (uint32_t)std::max<uint64_t>(1, (uint64_t)npages * tiles / (NUM_SMS_B200 * 6));
-        while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (1ull << 30)) ppi *= 2;
+        // one item per page range, every query tile scanned inside it: single-page items keep the rows of all
+        // concurrently running items within L2 (148 x 768 KB) while the tiles re-read them; widen only when the
+        // partial-result buffer (nq x ranges x k entries) would get out of hand
+        uint32_t ppi = 1;
+        while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (8ull << 30)) ppi *= 2;
         const uint64_t slots = (uint64_t)nq * ((npages + ppi - 1) / ppi);
         float* dd = distances;
         uint64_t* di = indices;

@@ -318,6 +318,54 @@ __global__ void __launch_bounds__(32) seed_sample_kernel(DevRng* g, const float*
     for (uint32_t d = lane; d < ld; d += 32) centroids[(size_t)cidx * ld + d] = x[(size_t)v * ldx + d];
 }
 
+// FAST-mode sampler: the same D^2 sampling (same RNG stream), but the total and the running sums are
+// accumulated in parallel (double precision, 1024 chunks) instead of one sequential fp32 chain, so the row
+// picked can differ from the reference's when the target falls within rounding distance of a boundary.
+__global__ void __launch_bounds__(1024) seed_sample_fast_kernel(DevRng* g, const float* __restrict__ x, uint32_t n,
+                                                                uint32_t ldx, uint32_t ld,
+                                                                const float* __restrict__ mind,
+                                                                float* __restrict__ centroids, uint32_t cidx,
+                                                                uint32_t* picked) {
+    __shared__ double s_part[1024];
+    __shared__ double s_target;
+    __shared__ uint32_t s_pick;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = (n + 1023) / 1024;
+    const uint32_t lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    double s = 0.0;
+    for (uint32_t i = lo; i < hi; ++i) s += (double)mind[i];
+    s_part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double run = 0.0;
+        for (int i = 0; i < 1024; ++i) {
+            const double t = s_part[i];
+            s_part[i] = run;  // exclusive prefix
+            run += t;
+        }
+        s_target = (double)rng_real_0_b(g, (float)run);
+        s_pick = 0xffffffffu;
+    }
+    __syncthreads();
+    const double target = s_target;
+    const double before = s_part[tid];
+    if (before < target || (tid == 0 && target <= 0.0)) {
+        double run = before;
+        for (uint32_t i = lo; i < hi; ++i) {
+            run += (double)mind[i];
+            if (run >= target) {
+                atomicMin(&s_pick, i);  // first row whose running sum reaches the target
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t v = s_pick;
+    if (tid == 0) picked[cidx] = v;
+    if (v == 0xffffffffu) return;
+    for (uint32_t d = tid; d < ld; d += 1024) centroids[(size_t)cidx * ld + d] = x[(size_t)v * ldx + d];
+}
+
 // ------------------------------------------------------------- Lloyd update
 
 // Stable bucketing of row numbers by cluster (members of a cluster in input
@@ -511,15 +559,19 @@ int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint
     return VDB_OK;
 }
 
-int32_t kmeanspp_seed_exact(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
-                            float* centroids, KMeansScratch& sc, cudaStream_t stream) {
+int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
+                      float* centroids, KMeansScratch& sc, bool exact, cudaStream_t stream) {
     seed_init_kernel<<<1, 256, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, centroids, sc.picked);
     fill_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(sc.mind, n, FLT_MAX);
     for (uint32_t c = 1; c < nlist; ++c) {
         seed_dist_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, ldx, dim, centroids + (size_t)(c - 1) * ld,
                                                                sc.mind);
-        seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, sc.ckpt, centroids, c,
-                                                 sc.picked);
+        if (exact)
+            seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, sc.ckpt, centroids, c,
+                                                     sc.picked);
+        else
+            seed_sample_fast_kernel<<<1, 1024, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
+                                                            sc.picked);
     }
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;

@@ -41,10 +41,14 @@ typedef enum {
 /* kernels.cuh:24-28.  L2 is the SQUARED distance, InnerProduct is -dot. */
 typedef enum { VDB_METRIC_L2 = 0, VDB_METRIC_IP = 1, VDB_METRIC_COSINE = 2 } vdb_metric;
 
-/* EXACT reproduces the reference's fp32 summation order in k-means++ seeding,
- * assignment and centroid update bit for bit; FAST uses parallel reductions
- * (and, where enabled, the tensor-core assignment) and agrees statistically.
- * AUTO = EXACT while n * nlist * dim is small. */
+/* Assignment and centroid update are always bit-identical to the reference
+ * (the tensor-core assignment re-checks its survivors in reference order).
+ * EXACT also keeps the scalar assignment kernel and the reference's sequential
+ * fp32 sums in the k-means++ sampling (bit-identical seeds); FAST samples with
+ * parallel double-precision sums (same RNG stream, a pick can differ when the
+ * target lies within rounding distance of a row boundary).  AUTO = exact
+ * sampling while n_train * nlist <= 2^31, tensor-core assignment when
+ * nlist >= 256. */
 typedef enum { VDB_TRAIN_AUTO = 0, VDB_TRAIN_EXACT = 1, VDB_TRAIN_FAST = 2 } vdb_train_mode;
 
 /* How the query x centroid coarse distances are produced:

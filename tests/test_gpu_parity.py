@@ -358,12 +358,13 @@ def test_concurrent_searches_from_host_threads():
     ix.centroids = g["centroids"]
     ix.add(db)
     errs = []
+    Dg, Ig = np.array(g["D"]), np.array(g["I"])  # NpzFile members are not safe to read from several threads
 
     def worker(lo):
         try:
             for _ in range(5):
                 D, I = ix.search(q[lo:lo + 25], pkg.SearchParams(nprobe=p["nprobe"], k=p["k"]))
-                check_search(D, I, g["D"][lo:lo + 25], g["I"][lo:lo + 25])
+                check_search(D, I, Dg[lo:lo + 25], Ig[lo:lo + 25])
         except Exception as e:  # noqa: BLE001
             errs.append(e)
 
@@ -385,3 +386,21 @@ def test_single_query_and_k1_and_nlist1():
         Dr, Ir = ora.search(x[2900:2900 + nq], 1, k)
         D, I = ix.search(x[2900:2900 + nq], 1, k)
         check_search(D, I, Dr, Ir)
+
+
+def test_fast_train_mode_is_statistically_equivalent():
+    """FAST k-means++ sampling (parallel sums): same RNG stream, nearly always the same seeds; the clustering
+    quality (inertia) must match the reference's within 1 %"""
+    dim, nlist, n = 24, 64, 6000
+    x = O.clustered(9, n, dim, n_centers=20, spread=0.5)
+    ora = O.OracleIndex(dim, nlist)
+    ora.train(x)
+    ix = new_index(dim, nlist, train_mode=pkg.TrainMode.FAST)
+    ix.train(x)
+
+    def inertia(c):
+        d = ((x[:, None, :].astype(np.float64) - c[None, :, :]) ** 2).sum(-1)
+        return d.min(1).sum()
+
+    a, b = inertia(ix.centroids), inertia(ora.centroids)
+    assert abs(a - b) <= 0.01 * b, (a, b)
