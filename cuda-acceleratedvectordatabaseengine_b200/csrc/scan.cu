@@ -245,17 +245,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait carries a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~1 ms
+// passes) instead of re-issuing the probe, which keeps memory-bound waiting off the issue slots and the
+// power budget
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(1000000u)
         : "memory");
 }
 // 1-D bulk TMA copy global -> shared, completion counted in bytes on `bar`
@@ -493,8 +496,6 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
             if (lane == 0) mbar_arrive(&s.empty[cur]);  // slot free: this warp's last row now lives in registers
         }
         float2 acc2[QC];
-#pragma unroll
-        for (int t = 0; t < QC; ++t) acc2[t] = make_float2(0.f, 0.f);
         if (p.metric == VDB_METRIC_L2) {
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
@@ -503,7 +504,7 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
                 for (int j = 0; j < QC; ++j) {
                     const float2 dlo = __ffma2_rn(vlo, neg1, make_float2(qv[j][jj].x, qv[j][jj].y));
                     const float2 dhi = __ffma2_rn(vhi, neg1, make_float2(qv[j][jj].z, qv[j][jj].w));
-                    acc2[j] = __ffma2_rn(dlo, dlo, acc2[j]);
+                    acc2[j] = jj == 0 ? __fmul2_rn(dlo, dlo) : __ffma2_rn(dlo, dlo, acc2[j]);
                     acc2[j] = __ffma2_rn(dhi, dhi, acc2[j]);
                 }
             }
@@ -513,7 +514,8 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
                 const float2 vlo = make_float2(v[jj].x, v[jj].y), vhi = make_float2(v[jj].z, v[jj].w);
 #pragma unroll
                 for (int j = 0; j < QC; ++j) {
-                    acc2[j] = __ffma2_rn(make_float2(qv[j][jj].x, qv[j][jj].y), vlo, acc2[j]);
+                    const float2 qlo = make_float2(qv[j][jj].x, qv[j][jj].y);
+                    acc2[j] = jj == 0 ? __fmul2_rn(qlo, vlo) : __ffma2_rn(qlo, vlo, acc2[j]);
                     acc2[j] = __ffma2_rn(make_float2(qv[j][jj].z, qv[j][jj].w), vhi, acc2[j]);
                 }
             }
