@@ -79,6 +79,8 @@ ABI = {
     "vdb_index_assign": (_i32, [_vp, _vp, _u64, _vp]),
     "vdb_index_get_centroids": (_i32, [_vp, _vp]),
     "vdb_index_set_centroids": (_i32, [_vp, _vp]),
+    "vdb_index_get_owners": (_i32, [_vp, _vp]),
+    "vdb_index_set_owners": (_i32, [_vp, _vp]),
     "vdb_index_list_sizes": (_i32, [_vp, _vp]),
     "vdb_index_list_ids": (_i32, [_vp, _u32, _vp]),
     "vdb_index_stats": (_i32, [_vp, C.POINTER(_Stats)]),
@@ -302,6 +304,17 @@ class IVFFlatIndex:
     def set_centroids_device(self, t):
         assert tuple(t.shape) == (self.config.nlist, self.config.dimension) and t.is_contiguous()
         _check(lib().vdb_index_set_centroids(self._h, _ptr(t)))
+
+    def owners(self):
+        """rank that holds each inverted list (all zeros on an unsharded index)"""
+        out = np.empty(self.config.nlist, np.uint8)
+        _check(lib().vdb_index_get_owners(self._h, _ptr(out)))
+        return out
+
+    def set_owners(self, owners):
+        o = np.ascontiguousarray(owners, np.uint8)
+        assert o.shape == (self.config.nlist,)
+        _check(lib().vdb_index_set_owners(self._h, _ptr(o)))
 
     def list_sizes(self):
         out = np.empty(self.config.nlist, np.uint64)

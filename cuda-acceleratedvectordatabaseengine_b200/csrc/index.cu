@@ -106,6 +106,9 @@ struct vdb_index {
     std::vector<uint32_t> npages_desc;  // page counts, descending (search slot bound)
 
     uint64_t total_vectors = 0, local_vectors = 0, slab_bytes_total = 0;
+    // sharding: owner[l] = rank that holds list l (null on an unsharded index)
+    std::vector<uint8_t> h_owner;
+    DevBuf<uint8_t> d_owner;
 
     ScanWorkspace ws_coarse, ws_scan;
     DevBuf<float> q_buf, coarse_d, out_d;
@@ -187,6 +190,32 @@ int32_t build_flat_view(const float* base, uint64_t n, uint32_t ld, uint32_t pag
     VDB_CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors die here
     *npages_out = npages;
     return VDB_OK;
+}
+
+int32_t upload_owners(vdb_index* ix) {
+    if (ix->cfg.shard_count <= 1) return VDB_OK;
+    VDB_TRY(ix->d_owner.reserve(ix->nlist));
+    VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_owner.p, ix->h_owner.data(), ix->nlist, cudaMemcpyHostToDevice, ix->stream));
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+// Greedy (largest first) byte balancing of the lists over the shards from per-list row counts: iid data
+// clusters very unevenly, so `l % world` can leave one GPU with far more to scan than another.
+// Deterministic, so every rank computes the same table from the same counts.
+void balance_owners(vdb_index* ix, const std::vector<uint32_t>& counts) {
+    const uint32_t world = ix->cfg.shard_count;
+    std::vector<uint32_t> order(ix->nlist);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return counts[a] > counts[b]; });
+    std::vector<uint64_t> load(world, 0);
+    for (uint32_t l : order) {
+        uint32_t best = 0;
+        for (uint32_t r = 1; r < world; ++r)
+            if (load[r] < load[best]) best = r;
+        ix->h_owner[l] = (uint8_t)best;
+        load[best] += (uint64_t)counts[l] + 1;  // +1 spreads the empty lists too
+    }
 }
 
 int32_t refresh_centroid_aux(vdb_index* ix) {
@@ -374,7 +403,8 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     VDB_REQUIRE(cfg->dimension <= 2048, "dimension must be <= 2048 (kernels.cuh MAX_DIM)");
     VDB_REQUIRE(cfg->metric == VDB_METRIC_L2 || cfg->metric == VDB_METRIC_IP,
                 "metric must be L2 or InnerProduct (the reference CPU path computes 0 for Cosine)");
-    VDB_REQUIRE(cfg->shard_count >= 1 && cfg->shard_rank < cfg->shard_count, "bad shard rank/count");
+    VDB_REQUIRE(cfg->shard_count >= 1 && cfg->shard_count <= 255 && cfg->shard_rank < cfg->shard_count,
+                "bad shard rank/count");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -404,6 +434,11 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     VDB_CUDA_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     VDB_TRY(ix->centroids.reserve((size_t)ix->nlist * ix->ld));
     VDB_CUDA_TRY(cudaMemsetAsync(ix->centroids.p, 0, ix->centroids.bytes(), ix->stream));  // centroids_ value-init (:22)
+    if (cfg->shard_count > 1) {
+        ix->h_owner.resize(ix->nlist);
+        for (uint32_t l = 0; l < ix->nlist; ++l) ix->h_owner[l] = (uint8_t)(l % cfg->shard_count);
+        VDB_TRY(upload_owners(ix.get()));
+    }
     VDB_TRY(refresh_centroid_view(ix.get()));
     VDB_TRY(refresh_centroid_aux(ix.get()));
     VDB_TRY(upload_list_tables(ix.get()));
@@ -422,7 +457,7 @@ int32_t vdb_index_destroy(vdb_index* ix) {
         ix->d_page_ids.release(); ix->q_buf.release(); ix->coarse_d.release(); ix->out_d.release();
         ix->coarse_i.release(); ix->out_i.release(); ix->probes.release(); ix->zero_probes.release();
         ix->assign_buf.release(); ix->hist_buf.release(); ix->fill_buf.release(); ix->stage_buf.release();
-        ix->ids_stage.release();
+        ix->ids_stage.release(); ix->d_owner.release();
         ix->tc_assign.release();
         ix->ws_coarse.release();
         ix->ws_scan.release();
@@ -460,6 +495,22 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
                                      ix->stream);
     }
     if (st == VDB_OK) st = refresh_centroid_aux(ix);
+    if (st == VDB_OK && ix->cfg.shard_count > 1 && ix->total_vectors == 0) {
+        // list sizes of the training sample under the final centroids -> byte-balanced list ownership
+        std::vector<uint32_t> counts(ix->nlist, 0);
+        st = assign_rows(ix, x, n, sc.assign, ix->stream);
+        if (st == VDB_OK) st = ix->hist_buf.reserve(ix->nlist);
+        if (st == VDB_OK && cudaMemsetAsync(ix->hist_buf.p, 0, ix->nlist * 4, ix->stream) != cudaSuccess) st = VDB_CUDA_ERROR;
+        if (st == VDB_OK) st = launch_hist(sc.assign, n, ix->nlist, 0, nullptr, ix->hist_buf.p, ix->stream);
+        if (st == VDB_OK && cudaMemcpyAsync(counts.data(), ix->hist_buf.p, ix->nlist * 4, cudaMemcpyDeviceToHost,
+                                            ix->stream) != cudaSuccess)
+            st = VDB_CUDA_ERROR;
+        if (st == VDB_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) st = VDB_CUDA_ERROR;
+        if (st == VDB_OK) {
+            balance_owners(ix, counts);
+            st = upload_owners(ix);
+        }
+    }
     if (st == VDB_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) {
         set_last_error(std::string("train: ") + cudaGetErrorString(cudaGetLastError()));
         st = VDB_CUDA_ERROR;
@@ -500,7 +551,7 @@ int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
         VDB_TRY(ix->fill_buf.reserve(ix->nlist));
         VDB_CUDA_TRY(cudaMemsetAsync(ix->hist_buf.p, 0, ix->nlist * 4, ix->stream));
         VDB_CUDA_TRY(cudaMemsetAsync(ix->fill_buf.p, 0, ix->nlist * 4, ix->stream));
-        VDB_TRY(launch_hist(ix->assign_buf.p, m, ix->nlist, ix->cfg.shard_rank, ix->cfg.shard_count, ix->hist_buf.p,
+        VDB_TRY(launch_hist(ix->assign_buf.p, m, ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->hist_buf.p,
                             ix->stream));
         std::vector<uint32_t> hist(ix->nlist);
         VDB_CUDA_TRY(cudaMemcpyAsync(hist.data(), ix->hist_buf.p, ix->nlist * 4, cudaMemcpyDeviceToHost, ix->stream));
@@ -523,7 +574,7 @@ int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
         VDB_TRY(upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
         VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, ix->assign_buf.p, ix->d_rows.p,
                                     ix->fill_buf.p, ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p,
-                                    ix->page_rows, ix->ld, ix->cfg.shard_rank, ix->cfg.shard_count, ix->stream));
+                                    ix->page_rows, ix->ld, ix->cfg.shard_rank, ix->d_owner.p, ix->stream));
         ix->h_rows = new_rows;
         VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), ix->nlist * 4, cudaMemcpyHostToDevice,
                                      ix->stream));
@@ -636,6 +687,28 @@ int32_t vdb_index_set_centroids(vdb_index* ix, const float* in) {
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
     ix->trained = true;
     return VDB_OK;
+}
+
+int32_t vdb_index_get_owners(vdb_index* ix, uint8_t* out) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(out, "get_owners: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    for (uint32_t l = 0; l < ix->nlist; ++l) out[l] = ix->cfg.shard_count > 1 ? ix->h_owner[l] : 0;
+    return VDB_OK;
+}
+
+int32_t vdb_index_set_owners(vdb_index* ix, const uint8_t* in) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(in, "set_owners: null buffer");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    VDB_REQUIRE(ix->total_vectors == 0, "set_owners: list ownership can only change while the index is empty");
+    if (ix->cfg.shard_count <= 1) return VDB_OK;
+    for (uint32_t l = 0; l < ix->nlist; ++l) {
+        VDB_REQUIRE(in[l] < ix->cfg.shard_count, "set_owners: rank out of range");
+        ix->h_owner[l] = in[l];
+    }
+    return upload_owners(ix);
 }
 
 int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out) {

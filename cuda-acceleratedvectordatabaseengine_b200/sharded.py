@@ -7,7 +7,8 @@ partitioning follows from merge_results (ivf_flat_index.cpp:474-518): a query's
 answer is the top-k of the union of per-list top-k's, so lists are independent
 units and the only exchange step is the final merge.
 
-    rank r owns list l  <=>  l % world == r          (owner_of)
+    owner[l] = l % world until train(), which re-balances the lists over the ranks by bytes
+    (greedy, largest first, identical table on every rank; IVFFlatIndex.owners())
     every rank: same centroids, same coarse selection on the full query batch,
                 scan of the probed lists it owns -> local [nq][k] padded FLT_MAX/UINT64_MAX
     all_gather of the local (distances, ids)         (gather_topk)
@@ -21,7 +22,7 @@ import torch.distributed as dist
 
 
 def owner_of(list_id, world):
-    """Rank that owns inverted list `list_id` (must match the `l % shard_count` test in the add kernels)."""
+    """Default owner of inverted list `list_id` (the table an untrained sharded index starts from)."""
     return int(list_id) % int(world)
 
 

@@ -69,8 +69,8 @@ typedef struct {
     int32_t train_mode;      /* vdb_train_mode */
     int32_t coarse_mode;     /* vdb_coarse_mode */
     uint32_t page_rows;      /* rows per inverted-list page, 0 = auto */
-    uint32_t shard_rank;     /* this process owns lists l with l % shard_count == shard_rank */
-    uint32_t shard_count;    /* 1 = unsharded */
+    uint32_t shard_rank;     /* this process holds the lists whose owner is shard_rank (see vdb_index_get_owners) */
+    uint32_t shard_count;    /* 1 = unsharded, at most 255 */
     uint32_t reserved[5];
 } vdb_config;
 
@@ -130,6 +130,11 @@ int32_t vdb_index_assign(vdb_index* ix, const float* vectors, uint64_t n, uint32
 /* Test hooks / persistence seam: centroids_ is [nlist][dimension] fp32 row-major. */
 int32_t vdb_index_get_centroids(vdb_index* ix, float* out);
 int32_t vdb_index_set_centroids(vdb_index* ix, const float* in);
+/* List ownership of a sharded index: owner[l] = rank holding list l.  Starts as l % shard_count;
+ * vdb_index_train() re-balances it by bytes (greedy, largest list first, from the training sample's
+ * list sizes -- deterministic, identical on every rank); may be set explicitly while the index is empty. */
+int32_t vdb_index_get_owners(vdb_index* ix, uint8_t* out /* [nlist] */);
+int32_t vdb_index_set_owners(vdb_index* ix, const uint8_t* in /* [nlist] */);
 int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out /* [nlist] */);
 int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out /* [list size] */);
 int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out);
