@@ -1,0 +1,71 @@
+"""GPU test of the sharded path (needs >= 2 GPUs; skipped otherwise): two NCCL ranks, byte-balanced list
+ownership, local scans + all-gather + merge kernel == the unsharded index == the oracle."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as O
+from parity import check_search
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WORLD = 2
+
+
+def _worker(rank, port, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_DEBUG="WARN")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
+    pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
+    sharded = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200.sharded")
+    dim, nlist, n, nq, nprobe, k = 64, 48, 20000, 40, 12, 10
+    x = O.gaussian(31, n + nq, dim)
+    db, q = x[:n], x[n:]
+    ix = sharded.ShardedIVFFlatIndex(pkg, pkg.Config(dimension=dim, nlist=nlist, device=rank))
+    ix.train(db[:4000])
+    owners = ix.local.owners()
+    ix.add(db)
+    D, I = ix.search(q, nprobe, k)
+    sizes = ix.local.list_sizes()
+    assert (sizes[owners != rank] == 0).all()
+    tot = torch.tensor([int(sizes.sum())], device="cuda")
+    dist.all_reduce(tot)
+    if rank == 0:
+        ora = O.OracleIndex(dim, nlist)
+        ora.train(db[:4000])
+        ora.add(db)
+        Dr, Ir = ora.search(q, nprobe, k)
+        try:
+            assert int(tot.item()) == n
+            check_search(D, I, Dr, Ir)
+            full = ora.list_sizes().astype(np.int64)
+            load = [int(full[owners == r].sum()) for r in range(WORLD)]
+            assert max(load) - min(load) <= max(full.max(), n // 20), load  # byte-balanced ownership
+            ret.put("ok")
+        except AssertionError as e:
+            ret.put(f"FAIL {e}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharded_search_matches_oracle():
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, port, ret)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    msg = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+    assert msg == "ok", msg
