@@ -73,6 +73,7 @@ ABI = {
     "vdb_index_destroy": (_i32, [_vp]),
     "vdb_index_train": (_i32, [_vp, _vp, _u64]),
     "vdb_index_add": (_i32, [_vp, _vp, _vp, _u64]),
+    "vdb_index_add_assigned": (_i32, [_vp, _vp, _vp, _vp, _u64, _u64]),
     "vdb_index_search": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "vdb_index_search_async": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "vdb_index_select_nprobe": (_i32, [_vp, _vp, _u32, _u32, _vp]),
@@ -226,6 +227,21 @@ class IVFFlatIndex:
         if ids is not None and not _is_torch(ids):
             ids = np.ascontiguousarray(ids, np.uint64)
         _check(lib().vdb_index_add(self._h, _ptr(v), _ptr(ids), n))
+
+    def add_assigned(self, vectors, ids, assignments, global_n):
+        """device tensors: rows whose lists are already known (data-parallel add of a sharded index)"""
+        n = vectors.shape[0]
+        _check(lib().vdb_index_add_assigned(self._h, _ptr(vectors) if n else None, _ptr(ids) if n else None,
+                                            _ptr(assignments) if n else None, n, global_n))
+
+    def assign_device(self, vectors):
+        """CUDA tensor [n][dim] -> CUDA int32 tensor [n] of list ids"""
+        import torch
+        v = self._rows(vectors)
+        out = torch.empty(v.shape[0], dtype=torch.int32, device=v.device)
+        if v.shape[0]:
+            _check(lib().vdb_index_assign(self._h, _ptr(v), v.shape[0], _ptr(out)))
+        return out
 
     def search(self, queries, params_or_nprobe=None, k=None, distances=None, indices=None):
         """search(queries, SearchParams) -> (distances [nq][k] f32, indices [nq][k] u64).

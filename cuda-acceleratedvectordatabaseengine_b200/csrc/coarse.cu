@@ -314,21 +314,46 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
         __syncthreads();
         const uint32_t nb = s_nbest, nc = s_ncand;
         total_cand += nc - nb;
-        // exact fp32 distance of every new candidate: one warp per candidate
-        for (uint32_t i = nb + warp; i < nc; i += SEL_THREADS / 32) {
-            const float* cv = p.centroids + (size_t)cid[i] * p.ld;
-            float a = 0.f;
-            if (p.metric == VDB_METRIC_L2) {
-                for (uint32_t d = lane; d < p.ld; d += 32) {
-                    const float diff = qv[d] - cv[d];
-                    a = fmaf(diff, diff, a);
+        // exact fp32 distance of every new candidate: one warp per candidate, 128-bit loads, two candidates
+        // in flight per warp so the L2 round trips overlap
+        {
+            const uint32_t ld4 = p.ld >> 2;
+            const float4* q4 = reinterpret_cast<const float4*>(qv);
+            const float4* c4base = reinterpret_cast<const float4*>(p.centroids);
+            constexpr uint32_t NW = SEL_THREADS / 32;
+            for (uint32_t i = nb + warp; i < nc; i += 2 * NW) {
+                const uint32_t i2 = i + NW;
+                const bool two = i2 < nc;
+                const float4* ca = c4base + (size_t)cid[i] * ld4;
+                const float4* cb = c4base + (size_t)cid[two ? i2 : i] * ld4;
+                float a = 0.f, b = 0.f;
+                for (uint32_t d = lane; d < ld4; d += 32) {
+                    const float4 qq4 = q4[d], va = ca[d], vb = cb[d];
+                    if (p.metric == VDB_METRIC_L2) {
+                        float t;
+                        t = qq4.x - va.x; a = fmaf(t, t, a);
+                        t = qq4.y - va.y; a = fmaf(t, t, a);
+                        t = qq4.z - va.z; a = fmaf(t, t, a);
+                        t = qq4.w - va.w; a = fmaf(t, t, a);
+                        t = qq4.x - vb.x; b = fmaf(t, t, b);
+                        t = qq4.y - vb.y; b = fmaf(t, t, b);
+                        t = qq4.z - vb.z; b = fmaf(t, t, b);
+                        t = qq4.w - vb.w; b = fmaf(t, t, b);
+                    } else {
+                        a = fmaf(qq4.x, va.x, a); a = fmaf(qq4.y, va.y, a); a = fmaf(qq4.z, va.z, a); a = fmaf(qq4.w, va.w, a);
+                        b = fmaf(qq4.x, vb.x, b); b = fmaf(qq4.y, vb.y, b); b = fmaf(qq4.z, vb.z, b); b = fmaf(qq4.w, vb.w, b);
+                    }
                 }
-            } else {
-                for (uint32_t d = lane; d < p.ld; d += 32) a = fmaf(qv[d], cv[d], a);
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) cd[i] = (p.metric == VDB_METRIC_L2) ? a : -a;
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) {
+                    cd[i] = (p.metric == VDB_METRIC_L2) ? a : -a;
+                    if (two) cd[i2] = (p.metric == VDB_METRIC_L2) ? b : -b;
+                }
+            }
         }
         __syncthreads();
         const uint32_t n2 = dev_next_pow2(max(nc, 1u));

@@ -521,12 +521,9 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
     return st;
 }
 
-int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
-    VDB_TRY(check_index(ix));
-    if (n == 0) return VDB_OK;
-    VDB_REQUIRE(vectors, "add: null vectors");
-    std::lock_guard<std::mutex> lock(ix->mu);
-    DeviceGuard g(ix->device);
+// add() and add_assigned() share everything but the assignment step
+static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids, const uint32_t* assigned,
+                        uint64_t n, uint64_t counted) {
     const uint64_t chunk_rows = std::max<uint64_t>(1024, ADD_CHUNK_BYTES / (ix->ld * 4ull));
     const bool ids_dev = is_device_ptr(ids);
     for (uint64_t lo = 0; lo < n; lo += chunk_rows) {
@@ -543,16 +540,19 @@ int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
                 dids = ix->ids_stage.p;
             }
         }
-        // assign (ivf_flat_index.cpp:151-157)
-        VDB_TRY(ix->assign_buf.reserve(m));
-        VDB_TRY(assign_rows(ix, x, m, ix->assign_buf.p, ix->stream));
+        // assign (ivf_flat_index.cpp:151-157), unless the caller already did
+        const uint32_t* asg = assigned ? assigned + lo : nullptr;
+        if (!asg) {
+            VDB_TRY(ix->assign_buf.reserve(m));
+            VDB_TRY(assign_rows(ix, x, m, ix->assign_buf.p, ix->stream));
+            asg = ix->assign_buf.p;
+        }
         // per-list counts -> grow the page chains
         VDB_TRY(ix->hist_buf.reserve(ix->nlist));
         VDB_TRY(ix->fill_buf.reserve(ix->nlist));
         VDB_CUDA_TRY(cudaMemsetAsync(ix->hist_buf.p, 0, ix->nlist * 4, ix->stream));
         VDB_CUDA_TRY(cudaMemsetAsync(ix->fill_buf.p, 0, ix->nlist * 4, ix->stream));
-        VDB_TRY(launch_hist(ix->assign_buf.p, m, ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->hist_buf.p,
-                            ix->stream));
+        VDB_TRY(launch_hist(asg, m, ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->hist_buf.p, ix->stream));
         std::vector<uint32_t> hist(ix->nlist);
         VDB_CUDA_TRY(cudaMemcpyAsync(hist.data(), ix->hist_buf.p, ix->nlist * 4, cudaMemcpyDeviceToHost, ix->stream));
         VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
@@ -572,17 +572,37 @@ int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
         }
         // device tables: page chains now, old row counts as the append base
         VDB_TRY(upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
-        VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, ix->assign_buf.p, ix->d_rows.p,
-                                    ix->fill_buf.p, ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p,
-                                    ix->page_rows, ix->ld, ix->cfg.shard_rank, ix->d_owner.p, ix->stream));
+        VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, asg, ix->d_rows.p, ix->fill_buf.p,
+                                    ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p, ix->page_rows, ix->ld,
+                                    ix->cfg.shard_rank, ix->d_owner.p, ix->stream));
         ix->h_rows = new_rows;
         VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), ix->nlist * 4, cudaMemcpyHostToDevice,
                                      ix->stream));
         VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
         ix->local_vectors += added;
     }
-    ix->total_vectors += n;  // total_vectors_ += n_vectors (:200)
+    ix->total_vectors += counted;  // total_vectors_ += n_vectors (:200)
     return VDB_OK;
+}
+
+int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
+    VDB_TRY(check_index(ix));
+    if (n == 0) return VDB_OK;
+    VDB_REQUIRE(vectors, "add: null vectors");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    return add_impl(ix, vectors, ids, nullptr, n, n);
+}
+
+int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64_t* ids,
+                               const uint32_t* assignments_dev, uint64_t n, uint64_t global_n) {
+    VDB_TRY(check_index(ix));
+    if (n == 0 && global_n == 0) return VDB_OK;
+    VDB_REQUIRE(n == 0 || (vectors && ids && assignments_dev), "add_assigned: null buffer");
+    VDB_REQUIRE(n == 0 || is_device_ptr(assignments_dev), "add_assigned: assignments must be a device array");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    return add_impl(ix, vectors, ids, assignments_dev, n, global_n);
 }
 
 int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe, uint32_t k,

@@ -43,8 +43,9 @@ def gather_topk(D, I, group=None):
 class ShardedIVFFlatIndex:
     """vdb::IVFFlatIndex surface over `world` list shards, one per rank.
 
-    train(): every rank trains on the same rows (deterministic -> identical centroids);
+    train(): every rank trains on the same rows (deterministic -> identical centroids and owner table);
     add():   every rank sees the batch, assigns it, and keeps only the rows of the lists it owns;
+    add_distributed(): each rank assigns its own slice, one all-to-all routes rows to the owning ranks;
     search(): local search + all-gather + merge; every rank returns the full answer."""
 
     def __init__(self, pkg, config, group=None):
@@ -59,6 +60,34 @@ class ShardedIVFFlatIndex:
 
     def add(self, vectors, ids=None):
         self.local.add(vectors, ids)
+
+    def add_distributed(self, vectors, ids):
+        """Data-parallel add: every rank passes ITS OWN slice of the batch (CUDA tensors [n_r][dim] f32 and
+        [n_r] int64 ids).  Each rank assigns only its slice (tensor cores), rows are routed to the ranks that
+        own their lists with one all-to-all over NVLink, and land in the owners' HBM pages."""
+        world = self.world
+        a = self.local.assign_device(vectors)
+        if world == 1:
+            self.local.add_assigned(vectors.contiguous(), ids.contiguous(), a, vectors.shape[0])
+            return
+        if not hasattr(self, "_owners_dev"):
+            self._owners_dev = torch.from_numpy(self.local.owners().astype("int64")).to(vectors.device)
+        dest = self._owners_dev[a.long()]
+        order = torch.argsort(dest, stable=True)
+        send_counts = torch.bincount(dest, minlength=world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        nrecv, dim = int(sum(rc)), vectors.shape[1]
+        rv = torch.empty((nrecv, dim), dtype=torch.float32, device=vectors.device)
+        ri = torch.empty(nrecv, dtype=torch.int64, device=vectors.device)
+        ra = torch.empty(nrecv, dtype=torch.int32, device=vectors.device)
+        dist.all_to_all_single(rv, vectors[order].contiguous(), rc, sc, group=self.group)
+        dist.all_to_all_single(ri, ids[order].contiguous(), rc, sc, group=self.group)
+        dist.all_to_all_single(ra, a[order].contiguous(), rc, sc, group=self.group)
+        total = torch.tensor([vectors.shape[0]], dtype=torch.int64, device=vectors.device)
+        dist.all_reduce(total, group=self.group)
+        self.local.add_assigned(rv, ri, ra, int(total.item()))
 
     def search_device(self, queries, nprobe, k, stream=None):
         """queries: CUDA tensor [nq][dim]; returns CUDA tensors ([nq][k] f32, [nq][k] i64 view of u64 ids)."""

@@ -112,6 +112,12 @@ int32_t vdb_index_destroy(vdb_index* ix);
 int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n);
 /* IVFFlatIndex::add, ivf_flat_index.cpp:148-202: assign + append. */
 int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n);
+/* Data-parallel add for a sharded index: the rows' lists were already computed (vdb_index_assign on
+ * the rank that held them) and the rows routed to this rank; only rows of lists this rank owns are
+ * kept.  ids are required.  global_n = rows added across all ranks by this collective step (what
+ * get_total_vectors() grows by). */
+int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64_t* ids,
+                               const uint32_t* assignments_dev, uint64_t n, uint64_t global_n);
 /* IVFFlatIndex::search, ivf_flat_index.cpp:205-256.  distances/indices are
  * [nq][k]; missing results are padded FLT_MAX / UINT64_MAX (:380-383,:514-517).
  * nprobe is clamped to nlist.  Thread-safe against concurrent searches. */

@@ -31,7 +31,12 @@ def _worker(rank, port, ret):
     ix = sharded.ShardedIVFFlatIndex(pkg, pkg.Config(dimension=dim, nlist=nlist, device=rank))
     ix.train(db[:4000])
     owners = ix.local.owners()
-    ix.add(db)
+    # first half replicated add (every rank sees the rows), second half data-parallel add (each rank a slice)
+    half = n // 2
+    ix.add(db[:half], np.arange(half, dtype=np.uint64))
+    mine = np.arange(half + rank, n, WORLD)
+    ix.add_distributed(torch.from_numpy(db[mine]).cuda(), torch.from_numpy(mine.astype(np.int64)).cuda())
+    assert ix.get_total_vectors() == n
     D, I = ix.search(q, nprobe, k)
     sizes = ix.local.list_sizes()
     assert (sizes[owners != rank] == 0).all()
