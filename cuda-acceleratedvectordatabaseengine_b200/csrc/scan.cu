@@ -790,6 +790,7 @@ struct MergeParams {
     const uint64_t* part_i;
     const uint32_t* pair_slot;  // null: `parts` mode, slot(q, p) = p * nq + q, one slot per pair
     const uint32_t* part_cnt;   // valid entries per slot; null: k, padding skipped
+    const uint32_t* qthr;       // per-query bound on the final k-th distance proved by the scan (ordered keys), or null
     uint32_t nq, np, k, P;
     float* out_d;
     uint64_t* out_i;
@@ -991,7 +992,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
         const bool bulk = (uint64_t)npc * k + k <= P;
         if (bulk) {
             if (cnt2 + npc * k > P) pool_compact_block(L2, P, k, true, d3, i3, s_scan);
-            const float thr = thr2;
+            // nothing beyond the bound the scan ended with can reach the final top-k (k distinct ids are already
+            // at or below it), so most of what the early items left in their partials is dropped right here
+            const float thr = fminf(thr2, p.qthr ? key2f(__ldg(&p.qthr[q])) : INFINITY);
             float* wd_ = wd + warp * MERGE_W;
             uint64_t* wi_ = wi + warp * MERGE_W;
             for (uint32_t pl = warp; pl < npc; pl += MERGE_THREADS / 32) {
@@ -1032,6 +1035,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
                                 }
                             }
                         } else {
+                            ok[u] = ok[u] && dv[u] <= thr;
                             const uint32_t m = __ballot_sync(0xffffffffu, ok[u]);
                             if (ok[u]) {
                                 const uint32_t pos = wcnt + __popc(m & ((1u << lane) - 1u));
@@ -1292,6 +1296,7 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     if (ev) cudaEventRecord(ev[2], stream);
     MergeParams mp;
     mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot; mp.part_cnt = ws.part_cnt;
+    mp.qthr = ws.qthr;
     mp.nq = nq; mp.np = np; mp.k = k; mp.P = merge_pool_size(k);
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = out_u32;
     const uint32_t msmem = mp.P * 36 + (MERGE_THREADS / 32) * MERGE_W * 12;
@@ -1311,7 +1316,7 @@ int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts,
                     float* out_d, uint64_t* out_i, cudaStream_t stream) {
     VDB_REQUIRE(k >= 1 && k <= MAX_K && parts >= 1 && nq >= 1, "merge: bad shape");
     MergeParams mp;
-    mp.part_d = dparts; mp.part_i = iparts; mp.pair_slot = nullptr; mp.part_cnt = nullptr;
+    mp.part_d = dparts; mp.part_i = iparts; mp.pair_slot = nullptr; mp.part_cnt = nullptr; mp.qthr = nullptr;
     mp.nq = nq; mp.np = parts; mp.k = k; mp.P = merge_pool_size(k);
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = nullptr;
     int dev = 0;
