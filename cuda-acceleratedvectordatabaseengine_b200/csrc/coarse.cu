@@ -402,6 +402,8 @@ int32_t score_gemm(const float* A, uint32_t M, uint32_t lda, const float* B, uin
     if (dev < 8 && !conf[dev]) {
         VDB_CUDA_TRY(cudaFuncSetAttribute(score_gemm_kernel<BN_COARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
+        VDB_CUDA_TRY(cudaFuncSetAttribute(score_gemm_kernel<BN_COARSE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
         conf[dev] = true;
     }
     dim3 grid((N + BN_COARSE - 1) / BN_COARSE, (M + GM - 1) / GM);
@@ -423,6 +425,8 @@ int32_t coarse_select(const float* dots, uint32_t ldd, const float* queries, uin
     cudaGetDevice(&dev);
     if (dev < 8 && !conf[dev]) {
         VDB_CUDA_TRY(cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VDB_CUDA_TRY(cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
         conf[dev] = true;
     }
     coarse_select_kernel<<<nq, SEL_THREADS, smem, stream>>>(p);

@@ -1252,6 +1252,8 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
         if (gdev < 8 && !gconf[gdev]) {
             VDB_CUDA_TRY(cudaFuncSetAttribute(build_groups_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               4 * 8193 * 4));
+            VDB_CUDA_TRY(cudaFuncSetAttribute(build_groups_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
             gconf[gdev] = true;
         }
         build_groups_kernel<true><<<1, 1024, gsm, stream>>>(lt, probes_dev, npairs, ppi, wl);
@@ -1303,6 +1305,10 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     static bool mconf[8] = {false};
     if (dev < 8 && !mconf[dev]) {
         VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36 + (MERGE_THREADS / 32) * MERGE_W * 12));
+        // every kernel of the search pipeline asks for the same (maximum) shared-memory carve-out, so the SMs
+        // are not reconfigured between the back-to-back launches
+        VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
         mconf[dev] = true;
     }
     merge_kernel<<<nq, MERGE_THREADS, msmem, stream>>>(mp);

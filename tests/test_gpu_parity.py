@@ -404,3 +404,30 @@ def test_fast_train_mode_is_statistically_equivalent():
 
     a, b = inertia(ix.centroids), inertia(ora.centroids)
     assert abs(a - b) <= 0.01 * b, (a, b)
+
+
+def test_kmeans_accumulate_and_finalize_building_blocks():
+    """the data-parallel Lloyd pieces of the ABI: per-cluster sums in input order, counts, division"""
+    import ctypes as C
+    import torch
+    n, dim, nc = 3000, 20, 17
+    x = O.gaussian(4, n, dim)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, nc - 2, n).astype(np.uint32)  # the last two clusters stay empty
+    xd, ad = torch.from_numpy(x).cuda(), torch.from_numpy(a.astype(np.int32)).cuda()
+    sums = torch.zeros((nc, dim), dtype=torch.float32, device="cuda")
+    counts = torch.zeros(nc, dtype=torch.int32, device="cuda")
+    l = pkg.lib()
+    assert l.vdb_kmeans_accumulate(xd.data_ptr(), ad.data_ptr(), n, nc, dim, sums.data_ptr(), counts.data_ptr(), None) == 0
+    ref_s = np.zeros((nc, dim), np.float32)
+    for v in range(n):  # fp32, input order, like ivf_flat_index.cpp:123-131
+        ref_s[a[v]] += x[v]
+    assert np.array_equal(sums.cpu().numpy(), ref_s)
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(a, minlength=nc))
+    cent = torch.full((nc, dim), 7.0, dtype=torch.float32, device="cuda")
+    assert l.vdb_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), cent.data_ptr(), nc, dim, None) == 0
+    torch.cuda.synchronize()
+    c = cent.cpu().numpy()
+    cnt = np.bincount(a, minlength=nc)
+    assert np.array_equal(c[cnt > 0], ref_s[cnt > 0] / cnt[cnt > 0, None].astype(np.float32))
+    assert (c[cnt == 0] == 7.0).all()  # an empty cluster keeps its centroid (:134-141)
