@@ -315,6 +315,9 @@ struct ScanParams {
     uint64_t* part_i;
     uint32_t* part_cnt;  // [nslots] valid entries of each partial
     uint32_t* qthr;      // [nq] ordered keys, see f2key
+    float* gtop_d;       // [nq][k] each query's running best k over everything scanned so far (bound tightening)
+    uint64_t* gtop_i;    // [nq][k]
+    uint32_t* glock;     // [nq] spin locks guarding gtop
     uint32_t* work_counter;
     uint32_t k, P, S, np, check_interval, has_ids;
     uint32_t qt;  // queries per tile at run time (<= the kernel's register tile)
@@ -439,6 +442,76 @@ __device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams
         }
     }
     __syncwarp();
+}
+
+// One warp folds query j's surviving local best (sorted, nc entries at the front of its pool) into the query's
+// global running top-k, under a per-query spin lock, and publishes the new k-th distance as the bound.  An
+// item-local k-th distance only bounds the answer by "the k-th best of these ~1000 rows"; the running top-k
+// over every row scanned so far by any CTA tightens it to what the final answer will be, so that later items
+// admit, keep and hand to the merge almost nothing.  (The partial results stay the source of truth for the
+// merge -- this list only feeds the bound, which is published only while its k ids are distinct.)
+__device__ __forceinline__ void contribute_global(const ScanSmem& s, const ScanParams& p, uint32_t j, uint32_t nc,
+                                                  uint32_t lane) {
+    float* d = s.pool_d + (size_t)j * p.P;
+    uint64_t* id = s.pool_i + (size_t)j * p.P;
+    const uint32_t q = s.sqidx[j], k = p.k;
+    if (!(d[0] <= key2f(__ldcg(&p.qthr[q])))) return;  // cannot improve the running top-k (warp-uniform)
+    // try-lock: when another CTA is updating this query's list right now, skip -- the bound merely tightens a
+    // little later, and no warp ever waits on another CTA
+    uint32_t got = 0;
+    if (lane == 0) {
+        got = atomicCAS(&p.glock[q], 0u, 1u) == 0u;
+        __threadfence();
+    }
+    if (!__shfl_sync(0xffffffffu, got, 0)) return;
+    for (uint32_t i = lane; i < k; i += 32) {
+        d[nc + i] = __ldcg(&p.gtop_d[(size_t)q * k + i]);
+        id[nc + i] = __ldcg(&p.gtop_i[(size_t)q * k + i]);
+    }
+    const uint32_t m = nc + k, n2 = dev_next_pow2(m);  // m <= 2k <= P
+    for (uint32_t i = m + lane; i < n2; i += 32) {
+        d[i] = FLT_MAX;
+        id[i] = ID_PAD;
+    }
+    __syncwarp();
+    bitonic_sort_pairs(d, id, n2, lane, 32, [] { __syncwarp(); });
+    for (uint32_t i = lane; i < k; i += 32) {
+        p.gtop_d[(size_t)q * k + i] = d[i];
+        p.gtop_i[(size_t)q * k + i] = id[i];
+    }
+    if (id[k - 1] != ID_PAD) {  // k real entries: their k-th distance is a bound if the ids are distinct
+        bool dup = false;
+        if (k <= 64) {
+            for (uint32_t i = lane; i < k; i += 32) {
+                const uint64_t me = id[i];
+                for (uint32_t t = 0; t < i; ++t) dup |= (id[t] == me);
+            }
+        } else {
+            uint64_t* sc = id + (p.P >> 1);  // the merged tail beyond k is no longer needed
+            const uint32_t m2 = dev_next_pow2(k);
+            const float kth_keep = d[k - 1];
+            for (uint32_t i = lane; i < m2; i += 32) sc[i] = i < k ? id[i] : ID_PAD;
+            __syncwarp();
+            for (uint32_t size = 2; size <= m2; size <<= 1)
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t t = lane; t < (m2 >> 1); t += 32) {
+                        const uint32_t a = ((t / stride) * (stride << 1)) + (t % stride), b = a + stride;
+                        const uint64_t x = sc[a], y = sc[b];
+                        if (((a & size) == 0) ? (y < x) : (x < y)) {
+                            sc[a] = y;
+                            sc[b] = x;
+                        }
+                    }
+                    __syncwarp();
+                }
+            for (uint32_t i = lane; i + 1 < k; i += 32) dup |= (sc[i] == sc[i + 1]);
+            d[k - 1] = kth_keep;  // (P/2 >= k, so d[k-1] was not touched; kept explicit for clarity)
+        }
+        if (!__any_sync(0xffffffffu, dup) && lane == 0) atomicMin(&p.qthr[q], f2key(d[k - 1]));
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(&p.glock[q], 0u);
 }
 
 // Sum V per-lane partials across the warp: log2(V) "halving" exchanges leave
@@ -678,6 +751,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                 p.part_i[slot * p.k + i] = s.pool_i[(size_t)j * p.P + i];
             }
             if (lane == 0) p.part_cnt[slot] = nc;
+            if (nc > 0) contribute_global(s, p, j, nc, lane);
         }
         consumer_bar();
     }
@@ -1157,7 +1231,18 @@ int32_t launch_scan(const ScanParams& sp, uint32_t grid, uint32_t smem, cudaStre
 
 int32_t scan_max_k() { return (int32_t)MAX_K; }
 
-int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k) {
+int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k, uint32_t nq) {
+    if ((uint64_t)nq * k > cap_gtop) {
+        cudaFree(gtop_d); cudaFree(gtop_i);
+        cap_gtop = (uint64_t)nq * k;
+        VDB_CUDA_TRY(cudaMalloc(&gtop_d, cap_gtop * 4));
+        VDB_CUDA_TRY(cudaMalloc(&gtop_i, cap_gtop * 8));
+    }
+    if (nq > cap_glock) {
+        cudaFree(glock);
+        cap_glock = nq;
+        VDB_CUDA_TRY(cudaMalloc(&glock, (size_t)cap_glock * 4));
+    }
     cudaGetDevice(&device);
     if (nlists + 1 > cap_lists) {
         cudaFree(gcount); cudaFree(gfill); cudaFree(goff); cudaFree(ioff);
@@ -1203,6 +1288,7 @@ int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots
 void ScanWorkspace::release() {
     cudaFree(gcount); cudaFree(gfill); cudaFree(goff); cudaFree(ioff);
     cudaFree(gpairs); cudaFree(pair_slot); cudaFree(items); cudaFree(part_cnt); cudaFree(qthr);
+    cudaFree(gtop_d); cudaFree(gtop_i); cudaFree(glock);
     cudaFree(part_d); cudaFree(part_i); cudaFree(totals); cudaFree(stats);
     *this = ScanWorkspace();
 }
@@ -1239,11 +1325,15 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
     const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P);
 
-    VDB_TRY(ws.reserve(lt.nlist, npairs, std::max<uint64_t>(max_slots, 1), k));
+    VDB_TRY(ws.reserve(lt.nlist, npairs, std::max<uint64_t>(max_slots, 1), k, nq));
 
     WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats,
                 ws.qthr, nq};
     if (ev) cudaEventRecord(ev[0], stream);
+    // running top-k of every query: "empty" = (3.39e38, UINT64_MAX), i.e. bytes 0x7f / 0xff; locks open
+    VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_d, 0x7f, (size_t)nq * k * 4, stream));
+    VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_i, 0xff, (size_t)nq * k * 8, stream));
+    VDB_CUDA_TRY(cudaMemsetAsync(ws.glock, 0, (size_t)nq * 4, stream));
     if (lt.nlist <= 8192) {
         const uint32_t gsm = 4 * (lt.nlist + 1) * 4;
         static bool gconf[8] = {false};
@@ -1273,6 +1363,9 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     sp.part_i = ws.part_i;
     sp.part_cnt = ws.part_cnt;
     sp.qthr = ws.qthr;
+    sp.gtop_d = ws.gtop_d;
+    sp.gtop_i = ws.gtop_i;
+    sp.glock = ws.glock;
     sp.k = k; sp.P = P; sp.S = S; sp.np = np;
     sp.has_ids = has_ids ? 1u : 0u;
     sp.qt = QT;

@@ -30,6 +30,11 @@ struct ScanWorkspace {
     uint32_t* part_cnt = nullptr;  // [cap_slots]
     uint32_t* qthr = nullptr;      // [cap_q]
     uint32_t cap_q = 0;
+    float* gtop_d = nullptr;       // [nq][k] running top-k of every query (bound tightening)
+    uint64_t* gtop_i = nullptr;
+    uint32_t* glock = nullptr;     // [nq]
+    uint64_t cap_gtop = 0;
+    uint32_t cap_glock = 0;
     float* part_d = nullptr;
     uint64_t* part_i = nullptr;
     uint64_t cap_slots = 0, cap_part = 0;
@@ -37,7 +42,7 @@ struct ScanWorkspace {
     unsigned long long* stats = nullptr;    // [0] algorithmic rows, [1] unique rows
     uint64_t bytes = 0;
 
-    int32_t reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k);
+    int32_t reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k, uint32_t nq);
     void release();
 };
 
