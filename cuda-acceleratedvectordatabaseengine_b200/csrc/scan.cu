@@ -539,7 +539,9 @@ __device__ __forceinline__ float transposed_reduce(float (&x)[V], uint32_t lane)
 // group, then ONE transposed reduction for the RB x QC per-lane partials and the pushes of the survivors.
 // Packed fp32x2 FMAs (sm_100): a (row, query) pair costs 2 instructions per float2 of the row --
 // d = v * (-1) + q (exactly q - v), acc += d * d -- instead of 4.
-template <int NJ, int QT, int QC, int RB>
+// FULLW: the row is exactly 32 * NJ float4 wide (768-D, 128-D, ...), so no column needs masking and rows past
+// the end of a short stage are simply read from the last valid row (their results are discarded)
+template <int NJ, int QT, int QC, int RB, bool FULLW>
 __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem& s, const float4* __restrict__ st4,
                                             uint32_t ld4, uint32_t cur, uint32_t r_first, uint32_t r_stride,
                                             uint32_t nr, uint32_t row0, const float4 (&qv)[QT][NJ], uint32_t myq,
@@ -554,10 +556,16 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
     for (int b = 0; b < RB; ++b) {
         const uint32_t r = r_first + r_stride * b;
         float4 v[NJ];
+        if (FULLW) {
+            const float4* row4 = st4 + min(r, nr - 1) * ld4 + lane;
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-            const uint32_t c4 = lane + 32 * jj;
-            v[jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jj = 0; jj < NJ; ++jj) v[jj] = row4[32 * jj];
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const uint32_t c4 = lane + 32 * jj;
+                v[jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         const uint32_t lr = row0 + r;  // list-relative row
         rid[b] = lr;
@@ -620,21 +628,21 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
 }
 
 // QC = register-tile width actually needed (next power of two of the group's query count)
-template <int NJ, int QT, int RB>
+template <int NJ, int QT, int RB, bool FULLW>
 __device__ __forceinline__ void score_dispatch(const ScanParams& p, const ScanSmem& s, const float4* st4, uint32_t ld4,
                                                uint32_t cur, uint32_t r_first, uint32_t r_stride, uint32_t nr,
                                                uint32_t row0, const float4 (&qv)[QT][NJ], uint32_t myq, uint32_t g,
                                                uint32_t ng, uint32_t lane, uint32_t limit, bool& over, bool release) {
     if (QT >= 8 && myq > 4)
-        score_batch<NJ, QT, (QT >= 8 ? 8 : QT), (RB > 4 ? 4 : RB)>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 8 ? 8 : QT), (RB > 4 ? 4 : RB), FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
     else if (QT >= 4 && myq > 3)
-        score_batch<NJ, QT, (QT >= 4 ? 4 : QT), RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 4 ? 4 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
     else if (QT >= 4 && myq > 2)  // 3 queries: a quarter less math than the padded 4-wide tile
-        score_batch<NJ, QT, (QT >= 4 ? 3 : QT), RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 4 ? 3 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
     else if (QT >= 2 && myq > 1)
-        score_batch<NJ, QT, (QT >= 2 ? 2 : QT), RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 2 ? 2 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
     else
-        score_batch<NJ, QT, 1, RB>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, 1, RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
 }
 
 template <int NJ>
@@ -643,6 +651,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
     const uint32_t ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
     const uint32_t ld = p.lt.ld, ld4 = ld >> 2;
     const uint32_t limit = p.P - p.check_interval * STAGE_ROWS;
+    const bool fullw = (ld4 == 32u * NJ);
     uint32_t stage = 0, phase = 0, qbuf = 0, qphase = 0;
     constexpr uint32_t END = 0xffffffffu;
 
@@ -705,14 +714,24 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                     phase ^= 1;
                 }
                 // this warp's rows of the stage (wg, wg + nwg, ...), RB at a time
-                if (ng == 1) {
-                    score_dispatch<NJ, QT, 2>(p, s, st4, ld4, cur, wg, nwg, nr, row_base + r0, qv, myq, g, ng, lane,
-                                              limit, over, true);
+                if (fullw) {
+                    if (ng == 1) {
+                        score_dispatch<NJ, QT, 2, true>(p, s, st4, ld4, cur, wg, nwg, nr, row_base + r0, qv, myq, g, ng,
+                                                        lane, limit, over, true);
+                    } else {
+#pragma unroll 1
+                        for (uint32_t i0 = 0; i0 < rows_per_warp; i0 += 4)
+                            score_dispatch<NJ, QT, 4, true>(p, s, st4, ld4, cur, wg + nwg * i0, nwg, nr, row_base + r0,
+                                                            qv, myq, g, ng, lane, limit, over, i0 + 4 >= rows_per_warp);
+                    }
+                } else if (ng == 1) {
+                    score_dispatch<NJ, QT, 2, false>(p, s, st4, ld4, cur, wg, nwg, nr, row_base + r0, qv, myq, g, ng, lane,
+                                                     limit, over, true);
                 } else {
 #pragma unroll 1
                     for (uint32_t i0 = 0; i0 < rows_per_warp; i0 += 4)
-                        score_dispatch<NJ, QT, 4>(p, s, st4, ld4, cur, wg + nwg * i0, nwg, nr, row_base + r0, qv, myq,
-                                                  g, ng, lane, limit, over, i0 + 4 >= rows_per_warp);
+                        score_dispatch<NJ, QT, 4, false>(p, s, st4, ld4, cur, wg + nwg * i0, nwg, nr, row_base + r0, qv,
+                                                         myq, g, ng, lane, limit, over, i0 + 4 >= rows_per_warp);
                 }
 
                 if (++since_check == p.check_interval) {
