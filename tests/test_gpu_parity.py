@@ -431,3 +431,23 @@ def test_kmeans_accumulate_and_finalize_building_blocks():
     cnt = np.bincount(a, minlength=nc)
     assert np.array_equal(c[cnt > 0], ref_s[cnt > 0] / cnt[cnt > 0, None].astype(np.float32))
     assert (c[cnt == 0] == 7.0).all()  # an empty cluster keeps its centroid (:134-141)
+
+
+@pytest.mark.parametrize("dim", [200, 256, 512, 1000, 1024, 1536, 2048])
+def test_every_row_width_instantiation(dim):
+    """one case per register-tile instantiation of the scan kernel (NJ = 2, 4, 8, 12, 16; full and masked widths)"""
+    n, nq, k, nlist = 1500, 11, 7, 5
+    x = O.gaussian(900 + dim, n + nq, dim)
+    db, q = x[:n], x[n:]
+    Dr, Ir = O.flat_search(db, q, k)
+    D, I = pkg.bruteforce_search(db, q, k)
+    check_search(D, I, Dr, Ir)
+    ora = O.OracleIndex(dim, nlist)
+    ora.train(db[:300])
+    ora.add(db)
+    ix = new_index(dim, nlist)
+    ix.centroids = ora.centroids
+    ix.add(db)
+    Dr, Ir = ora.search(q, 3, k)
+    D, I = ix.search(q, 3, k)
+    check_search(D, I, Dr, Ir)
