@@ -320,6 +320,7 @@ struct ScanParams {
     uint32_t* glock;     // [nq] spin locks guarding gtop
     uint32_t* work_counter;
     uint32_t k, P, S, np, check_interval, has_ids;
+    uint32_t stage_rows;  // rows per ring stage: 16, or 8 for rows wider than 4 KB
     uint32_t qt;  // queries per tile at run time (<= the kernel's register tile)
     int metric;
 };
@@ -346,7 +347,7 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     ScanSmem s;
     uint8_t* q = base;
     s.stages = (float*)q;
-    q += (size_t)p.S * STAGE_ROWS * p.lt.ld * 4;
+    q += (size_t)p.S * p.stage_rows * p.lt.ld * 4;
     s.stage_ids = (uint64_t*)q;
     q += (size_t)p.S * STAGE_ROWS * 8;
     s.sq = (float*)q;
@@ -375,8 +376,8 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     return s;
 }
 
-static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P) {
-    return S * STAGE_ROWS * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64;
+static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P, uint32_t stage_rows) {
+    return S * stage_rows * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64;
 }
 
 // queries held in registers per tile, by the number of float4 columns a lane owns
@@ -702,12 +703,12 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
             const uint32_t row_base = it.row_base + pgi * p.lt.page_rows;  // list-relative row of the page start
             const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
-            for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
-                const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
+            for (uint32_t r0 = 0; r0 < rows_in_page; r0 += p.stage_rows) {
+                const uint32_t nr = min(p.stage_rows, rows_in_page - r0);
                 mbar_wait(&s.full[stage], phase);
                 // this warp's rows of the stage, one at a time: row slice -> registers (lane owns float4 columns
                 // lane, lane+32, ...), score against the tile; the slot is handed back once the last row is read
-                const float4* st4 = reinterpret_cast<const float4*>(s.stages + (size_t)stage * STAGE_ROWS * ld);
+                const float4* st4 = reinterpret_cast<const float4*>(s.stages + (size_t)stage * p.stage_rows * ld);
                 const uint32_t cur = stage;
                 if (++stage == p.S) {
                     stage = 0;
@@ -823,14 +824,14 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
                 const float* src = reinterpret_cast<const float*>(pgi ? p.lt.page_vec[pg] : src0);
                 const uint64_t* ids =
                     p.has_ids ? reinterpret_cast<const uint64_t*>(pgi ? p.lt.page_ids[pg] : ids0) : nullptr;
-                for (uint32_t r0 = 0; r0 < rows_in_page; r0 += STAGE_ROWS) {
-                    const uint32_t nr = min((uint32_t)STAGE_ROWS, rows_in_page - r0);
+                for (uint32_t r0 = 0; r0 < rows_in_page; r0 += p.stage_rows) {
+                    const uint32_t nr = min(p.stage_rows, rows_in_page - r0);
                     const uint32_t bytes = nr * ld * 4;
                     // bulk copies move multiples of 16 bytes: an odd tail reads one id slot further, inside the page
                     const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
                     mbar_wait(&s.empty[stage], phase ^ 1);
                     mbar_expect_tx(&s.full[stage], bytes + id_bytes);
-                    tma_bulk_g2s_hint(s.stages + (size_t)stage * STAGE_ROWS * ld, src + (size_t)r0 * ld, bytes,
+                    tma_bulk_g2s_hint(s.stages + (size_t)stage * p.stage_rows * ld, src + (size_t)r0 * ld, bytes,
                                       &s.full[stage], policy);
                     if (ids) tma_bulk_g2s(s.stage_ids + stage * STAGE_ROWS, ids + r0, id_bytes, &s.full[stage]);
                     if (++stage == p.S) {
@@ -1333,7 +1334,8 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     // ring; shrunk below the register tile when the pools of a large k need the room
     const uint32_t QTreg = (uint32_t)tile_queries((int)NJ);
     uint32_t P = next_pow2(std::max(k + 64, 2 * k));
-    auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P) <= SMEM_BUDGET; };
+    const uint32_t stage_rows = lt.ld > 1024 ? STAGE_ROWS / 2 : STAGE_ROWS;
+    auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P, stage_rows) <= SMEM_BUDGET; };
     uint32_t ngroups = CONSUMER_WARPS;
     while (ngroups > 1 && (QTreg * ngroups > MAX_QT || !fits(3, QTreg * ngroups))) ngroups >>= 1;
     uint32_t QT = QTreg * ngroups;
@@ -1342,7 +1344,7 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     while (S > 2 && !fits(S, QT)) --S;
     VDB_REQUIRE(fits(S, QT), "dimension * k too large for the scan kernel's shared memory");
     const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
-    const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P);
+    const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P, stage_rows);
 
     VDB_TRY(ws.reserve(lt.nlist, npairs, std::max<uint64_t>(max_slots, 1), k, nq));
 
@@ -1388,6 +1390,7 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     sp.k = k; sp.P = P; sp.S = S; sp.np = np;
     sp.has_ids = has_ids ? 1u : 0u;
     sp.qt = QT;
+    sp.stage_rows = stage_rows;
     sp.work_counter = ws.totals + 2;
     sp.check_interval = check_interval;
     sp.metric = metric;
