@@ -347,6 +347,12 @@ def run_b200(a):
     uniq_bytes = uniq_rows * bpr / a.steps
     achieved = alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
 
+    rank_scan_ms = None
+    if world > 1:  # per-rank scan time and distinct bytes: shows how well the list ownership balances
+        mine = torch.tensor([scan_ms, uniq_bytes / 1e9], device=dev, dtype=torch.float64)
+        allr = torch.empty((world, 2), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        rank_scan_ms = [[round(float(a), 3), round(float(b_), 2)] for a, b_ in allr.cpu().tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -363,7 +369,8 @@ def run_b200(a):
                    "cache": f"inputs larger than L2: each batch streams {uniq_bytes / 1e9:.2f} GB of distinct list data",
                    "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
-                   "index_gb": round(st.gpu_memory_bytes / 1e9, 2)},
+                   "index_gb": round(st.gpu_memory_bytes / 1e9, 2),
+                   **({"rank_scan_ms_and_unique_gb": rank_scan_ms} if rank_scan_ms else {})},
         "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "unique_bytes_per_launch": uniq_bytes,

@@ -347,9 +347,10 @@ int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t
         ++ev;
     }
     VDB_TRY(coarse_select(ix, q_dev, nq, np, stream));
-    // pages per scan item: large indexes hand out longer runs of a list, so the per-item costs (tile
-    // announcement, barriers, final selection, partial write-out) are paid once per ~3 MB instead of per page
-    uint32_t ppi = ix->pages_used > NUM_SMS_B200 * 256u ? 4 : ix->pages_used > NUM_SMS_B200 * 64u ? 2 : 1;
+    // pages per scan item: longer runs of a list amortise the per-item costs (tile announcement, barriers,
+    // final selection, partial write-out) over up to ~3 MB, as long as every SM still gets >= ~16 items
+    uint32_t ppi = std::max<uint32_t>(1, std::min<uint32_t>(4, ix->pages_used / (NUM_SMS_B200 * 16u)));
+    if (ppi == 3) ppi = 2;
     while (slot_bound(ix, nq, np, ppi) * k * 12 > (1ull << 30)) ppi *= 2;
     const uint64_t slots = slot_bound(ix, nq, np, ppi);
     VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,

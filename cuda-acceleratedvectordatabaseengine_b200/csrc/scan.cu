@@ -340,6 +340,8 @@ struct ScanSmem {
     uint64_t* qfull;   // [2]
     uint64_t* qempty;  // [2]
     uint32_t* tile;    // [2][8] {item | END, first pair, queries, range, pages, row_base, rows_left, -}: producer -> consumers
+    uint32_t* tq;      // [2][MAX_QT] query index of each tile slot            (written by the producer with the tile)
+    uint32_t* tslot;   // [2][MAX_QT] partial-result slot of each (pair, range)
 };
 
 __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
@@ -373,11 +375,15 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     s.qempty = (uint64_t*)q;
     q += 2 * 8;
     s.tile = (uint32_t*)q;
+    q += 2 * 8 * 4;
+    s.tq = (uint32_t*)q;
+    q += 2 * MAX_QT * 4;
+    s.tslot = (uint32_t*)q;
     return s;
 }
 
 static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P, uint32_t stage_rows) {
-    return S * stage_rows * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64;
+    return S * stage_rows * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64 + 4 * MAX_QT * 4;
 }
 
 // queries held in registers per tile, by the number of float4 columns a lane owns
@@ -661,8 +667,17 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         mbar_wait(&s.qfull[qbuf], qphase);
         const uint32_t* tw = s.tile + qbuf * 8;
         if (tw[0] == END) break;
-        const uint32_t gbase = tw[1], qcount = tw[2];
+        const uint32_t qcount = tw[2];
         struct { uint32_t range, npg, row_base, rows_left; } it = {tw[3], tw[4], tw[5], tw[6]};
+        // per-query tile state; the bound is the only global read of the set-up and is issued first so that it
+        // overlaps the query loads below
+        uint32_t my_q = 0, my_slot = 0;
+        float my_thr = INFINITY;
+        if (ctid < qcount) {
+            my_q = s.tq[qbuf * MAX_QT + ctid];
+            my_slot = s.tslot[qbuf * MAX_QT + ctid];
+            my_thr = key2f(__ldcg(&p.qthr[my_q]));  // start from what earlier items already proved
+        }
         // a tile wider than the register tile is split over warp groups: group g keeps queries g, g+ng, ...
         // and every group reads every staged row, so the rows are still brought in from HBM once
         uint32_t ng = 1;
@@ -689,12 +704,10 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
             qphase ^= 1;
         }
         if (ctid < qcount) {
-            const uint32_t pair = p.gpairs[gbase + ctid];
-            const uint32_t q = pair / p.np;
             s.cnt[ctid] = 0;
-            s.spair[ctid] = p.pair_slot[pair] + it.range;  // the partial-result slot of (pair, range)
-            s.sqidx[ctid] = q;
-            s.thr[ctid] = key2f(__ldcg(&p.qthr[q]));  // start from what earlier items already proved
+            s.spair[ctid] = my_slot;
+            s.sqidx[ctid] = my_q;
+            s.thr[ctid] = my_thr;
         }
         consumer_bar();
 
@@ -757,7 +770,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
             compact_pool(s, p, j, lane);
             // entries beyond the bound the whole grid has proved by now cannot reach the final top-k: drop them
             // here, so that most partials leave the kernel (nearly) empty and the merge has little to do
-            const float bound = key2f(__ldcg(&p.qthr[s.sqidx[j]]));
+            const float bound = s.thr[j];  // min(the grid-wide bound as last refreshed, this pool's own k-th)
             const uint32_t kept = s.cnt[j];
             uint32_t nc = 0;
             for (uint32_t i0 = 0; i0 < kept; i0 += 32) {
@@ -807,12 +820,18 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
             tw[4] = it.npg;
             tw[5] = it.row_base;
             tw[6] = it.rows_left;
-            mbar_expect_tx(&s.qfull[qbuf], qcount * ld * 4);  // release: publishes s.tile too
+            // per query of the tile: its index and the partial-result slot of (pair, range), so that the
+            // consumers' tile set-up touches no global memory except the bound
+#pragma unroll 4
             for (uint32_t j = 0; j < qcount; ++j) {
-                const uint32_t q = p.gpairs[it.gbase + g0 + j] / p.np;
-                tma_bulk_g2s(s.sq + ((size_t)qbuf * p.qt + j) * ld, p.queries + (size_t)q * ld, ld * 4,
-                             &s.qfull[qbuf]);
+                const uint32_t pair = p.gpairs[it.gbase + g0 + j];
+                s.tq[qbuf * MAX_QT + j] = pair / p.np;
+                s.tslot[qbuf * MAX_QT + j] = p.pair_slot[pair] + it.range;
             }
+            mbar_expect_tx(&s.qfull[qbuf], qcount * ld * 4);  // release: publishes the tile words too
+            for (uint32_t j = 0; j < qcount; ++j)
+                tma_bulk_g2s(s.sq + ((size_t)qbuf * p.qt + j) * ld, p.queries + (size_t)s.tq[qbuf * MAX_QT + j] * ld,
+                             ld * 4, &s.qfull[qbuf]);
             if (++qbuf == 2) {
                 qbuf = 0;
                 qphase ^= 1;
