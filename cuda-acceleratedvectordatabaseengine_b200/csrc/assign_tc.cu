@@ -4,7 +4,7 @@
 // (ivf_flat_index.cpp:259-295) / kmeans_assign_kernel (kernels.cuh:315-354) for
 // large centroid tables, in three steps:
 //   1. row_norms_kernel      |x_v| of every row
-//   2. assign_gemm_kernel    persistent tcgen05 GEMM: a CTA owns 128 rows and
+//   2. rowtile_gemm_kernel<AssignEpi, ASSIGN_AN> (rowtile_gemm.cuh)  persistent tcgen05 GEMM: a CTA owns 128 rows and
 //      walks ALL centroid tiles (128 columns each); operands arrive by 2-D TMA
 //      through a 4-stage ring, the TF32 MMAs accumulate into one of two TMEM
 //      buffers while the four epilogue warps drain the other (thread = row).
@@ -19,17 +19,13 @@
 // Bound: as in coarse.cu, |true - tf32 score| <= E = 2^-8 |x||c| (+5 % and a
 // relative 1e-6 for the fp32 rounding of the bound arithmetic itself).
 #include "kmeans.cuh"
-#include "tc_common.cuh"
+#include "rowtile_gemm.cuh"
 
 namespace vdb {
 namespace {
 
 using namespace tc;
 
-constexpr int AM = 128;        // rows per CTA tile (UMMA M)
-constexpr int AN = 128;        // centroid columns per tile (UMMA N)
-constexpr int ASTAGES = 4;
-constexpr int ATHREADS = 192;  // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM owner
 constexpr int NCAND = 4;
 
 __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32_t ld, float* __restrict__ out,
@@ -47,183 +43,88 @@ __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32
     if (lane == 0) out[w] = take_sqrt ? sqrtf(s) : s;
 }
 
-struct AssignGemmParams {
+// Epilogue of the assignment: per row, the smallest UPPER bound of a true score seen so far and the (at most
+// NCAND) centroids whose LOWER bound does not exceed it.
+constexpr int ASSIGN_AN = 256;  // centroid columns per accumulator tile
+
+struct AssignEpi {
     const float* xnorm;   // [M] |x_v|
     const float* cnorm2;  // [N] |c|^2
-    uint32_t M, N, num_kb;
+    uint32_t M, N, num_kb, n_split;
     int metric;
     uint32_t* cand_idx;   // [M][NCAND]
     uint32_t* cand_cnt;   // [M]  (NCAND + 1 = overflow: fall back to the exact kernel for this row)
-};
 
-__global__ void __launch_bounds__(ATHREADS, 1)
-assign_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
-                   const AssignGemmParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr uint32_t A_BYTES = AM * GK * 4, B_BYTES = AN * GK * 4;
-    uint8_t* sa = smem;
-    uint8_t* sb = smem + ASTAGES * A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sb + ASTAGES * B_BYTES);
-    uint64_t* empty = full + ASTAGES;
-    uint64_t* acc_full = empty + ASTAGES;  // [2]
-    uint64_t* acc_empty = acc_full + 2;    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t m_tiles = (p.M + AM - 1) / AM, n_tiles = (p.N + AN - 1) / AN;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < ASTAGES; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+    struct State {
+        float xe, U;
+        float clb[NCAND];
+        uint32_t cix[NCAND];
+        uint32_t cnt;
+        bool overflow;
+    };
+    static constexpr uint32_t WARP_SMEM = 0;
+    __device__ __forceinline__ void chunk_end(State&, uint8_t*) const {}
+    __device__ __forceinline__ void begin(State& s, uint32_t row, uint8_t*) const {
+        s.xe = 1.05f * 0.00390625f * xnorm[row];
+        s.U = INFINITY;
+        s.cnt = 0;
+        s.overflow = false;
+#pragma unroll
+        for (int i = 0; i < NCAND; ++i) {
+            s.clb[i] = INFINITY;
+            s.cix[i] = 0;
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 5) {  // two accumulator buffers of AN fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(2 * AN)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    __device__ __forceinline__ void consume_chunk(State& s, uint32_t row, uint32_t n0, const uint32_t (&acc)[32]) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (n0 + i < N) consume(s, row, n0 + i, __uint_as_float(acc[i]));
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 4 && lane == 0) {
-        uint32_t s = 0, ph = 0;
-        for (uint32_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
-            for (uint32_t nt = 0; nt < n_tiles; ++nt)
-                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-                    tma_load_2d(sa + s * A_BYTES, &map_x, (int32_t)(kb * GK), (int32_t)(mt * AM), &full[s]);
-                    tma_load_2d(sb + s * B_BYTES, &map_c, (int32_t)(kb * GK), (int32_t)(nt * AN), &full[s]);
-                    if (++s == ASTAGES) {
-                        s = 0;
-                        ph ^= 1;
-                    }
-                }
-    } else if (warp == 5 && lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(AM, AN);
-        uint32_t s = 0, ph = 0, buf = 0, bph = 0;
-        for (uint32_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
-            for (uint32_t nt = 0; nt < n_tiles; ++nt) {
-                mbar_wait(&acc_empty[buf], bph ^ 1);  // the epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * AN;
-                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sa + s * A_BYTES), db = umma_desc_sw128(sb + s * B_BYTES);
+    __device__ __forceinline__ void consume(State& s, uint32_t, uint32_t n, float dot) const {
+        const float cn2 = __ldg(cnorm2 + n);
+        const float sc = (metric == VDB_METRIC_L2) ? fmaf(-2.f, dot, cn2) : -dot;
+        const float e = s.xe * sqrtf(cn2) + 1e-6f * fabsf(sc) + 1e-30f;
+        const float ub = sc + e, lb = sc - e;
+        s.U = fminf(s.U, ub);
+        if (lb <= s.U) {
+            // keep it; first drop survivors the tighter bound has ruled out meanwhile
+            uint32_t w = 0;
 #pragma unroll
-                    for (uint32_t k = 0; k < GK / 8; ++k)
-                        umma_tf32(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(&empty[s]);
-                    if (++s == ASTAGES) {
-                        s = 0;
-                        ph ^= 1;
-                    }
-                }
-                umma_commit(&acc_full[buf]);
-                if (++buf == 2) {
-                    buf = 0;
-                    bph ^= 1;
-                }
-            }
-    } else if (warp < 4) {
-        uint32_t buf = 0, bph = 0;
-        for (uint32_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-            const uint32_t row = mt * AM + warp * 32 + lane;
-            const float xe = row < p.M ? 1.05f * 0.00390625f * p.xnorm[row] : 0.f;
-            float U = INFINITY;  // smallest upper bound of a true score so far
-            float clb[NCAND];
-            uint32_t cix[NCAND];
-            uint32_t cnt = 0;
-            bool overflow = false;
+            for (int j = 0; j < NCAND; ++j)
+                if ((uint32_t)j < s.cnt && s.clb[j] <= s.U) {
+                    const float tl = s.clb[j];
+                    const uint32_t ti = s.cix[j];
 #pragma unroll
-            for (int i = 0; i < NCAND; ++i) {
-                clb[i] = INFINITY;
-                cix[i] = 0;
-            }
-            for (uint32_t nt = 0; nt < n_tiles; ++nt) {
-                mbar_wait(&acc_full[buf], bph);
-                tc_fence_after();
-#pragma unroll 1
-                for (uint32_t c0 = 0; c0 < (uint32_t)AN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((warp * 32u) << 16) + buf * AN + c0, r);
-                    const uint32_t nb = nt * AN + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint32_t n = nb + i;
-                        if (n >= p.N) continue;  // warp-uniform
-                        const float dot = __uint_as_float(r[i]);
-                        const float cn2 = __ldg(p.cnorm2 + n);
-                        const float sc = (p.metric == VDB_METRIC_L2) ? fmaf(-2.f, dot, cn2) : -dot;
-                        const float e = xe * sqrtf(cn2) + 1e-6f * fabsf(sc) + 1e-30f;
-                        const float ub = sc + e, lb = sc - e;
-                        U = fminf(U, ub);
-                        if (lb <= U) {
-                            // keep it; first drop survivors the tighter bound has ruled out meanwhile
-                            uint32_t w = 0;
-#pragma unroll
-                            for (int j = 0; j < NCAND; ++j)
-                                if ((uint32_t)j < cnt && clb[j] <= U) {
-                                    const float tl = clb[j];
-                                    const uint32_t ti = cix[j];
-#pragma unroll
-                                    for (int t = 0; t < NCAND; ++t)
-                                        if ((uint32_t)t == w) {
-                                            clb[t] = tl;
-                                            cix[t] = ti;
-                                        }
-                                    ++w;
-                                }
-                            cnt = w;
-                            if (cnt < NCAND) {
-#pragma unroll
-                                for (int t = 0; t < NCAND; ++t)
-                                    if ((uint32_t)t == cnt) {
-                                        clb[t] = lb;
-                                        cix[t] = n;
-                                    }
-                                ++cnt;
-                            } else {
-                                overflow = true;
-                            }
+                    for (int t = 0; t < NCAND; ++t)
+                        if ((uint32_t)t == w) {
+                            s.clb[t] = tl;
+                            s.cix[t] = ti;
                         }
-                    }
+                    ++w;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                if (++buf == 2) {
-                    buf = 0;
-                    bph ^= 1;
-                }
-            }
-            if (row < p.M) {
-                uint32_t w = 0;
+            s.cnt = w;
+            if (s.cnt < NCAND) {
 #pragma unroll
-                for (int j = 0; j < NCAND; ++j)
-                    if ((uint32_t)j < cnt && clb[j] <= U) p.cand_idx[(size_t)row * NCAND + w++] = cix[j];
-                p.cand_cnt[row] = overflow ? NCAND + 1 : w;
+                for (int t = 0; t < NCAND; ++t)
+                    if ((uint32_t)t == s.cnt) {
+                        s.clb[t] = lb;
+                        s.cix[t] = n;
+                    }
+                ++s.cnt;
+            } else {
+                s.overflow = true;
             }
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * AN) : "memory");
+    __device__ __forceinline__ void end(State& s, uint32_t row, bool valid, uint8_t*) const {
+        if (!valid) return;
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < NCAND; ++j)
+            if ((uint32_t)j < s.cnt && s.clb[j] <= s.U) cand_idx[(size_t)row * NCAND + w++] = s.cix[j];
+        cand_cnt[row] = s.overflow ? NCAND + 1 : w;
     }
-}
+};
 
 // exact fp32 re-scoring of the surviving centroids, in the reference's order (one thread per row; tiles are
 // transposed through shared memory so the row reads stay coalesced)
@@ -347,22 +248,22 @@ int32_t kmeans_assign_tensor(const float* x, uint64_t n, uint32_t ldx, const flo
     row_norms_kernel<<<(uint32_t)(((uint64_t)nc * 32 + 255) / 256), 256, 0, stream>>>(c, nc, ldc, sc.cnorm2, false);
     CUtensorMap mx, mc;
     VDB_TRY(tc::make_map(&mx, x, n, ldx, ldx, AM));
-    VDB_TRY(tc::make_map(&mc, c, nc, ldc, ldc, AN));
-    AssignGemmParams p;
+    VDB_TRY(tc::make_map(&mc, c, nc, ldc, ldc, ASSIGN_AN));
+    AssignEpi p;
     p.xnorm = sc.xnorm; p.cnorm2 = sc.cnorm2;
-    p.M = (uint32_t)n; p.N = nc; p.num_kb = (ldx + GK - 1) / GK; p.metric = metric;
+    p.M = (uint32_t)n; p.N = nc; p.num_kb = (ldx + GK - 1) / GK; p.n_split = 1; p.metric = metric;
     p.cand_idx = sc.cand_idx; p.cand_cnt = sc.cand_cnt;
-    constexpr uint32_t smem = ASTAGES * (AM * GK * 4 + AN * GK * 4) + (2 * ASTAGES + 4) * 8 + 16 + 1024;
+    constexpr uint32_t smem = rowtile_smem<AssignEpi, ASSIGN_AN>();
     static bool conf[8] = {false};
     int dev = 0, sms = NUM_SMS_B200;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (dev < 8 && !conf[dev]) {
-        VDB_CUDA_TRY(cudaFuncSetAttribute(assign_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VDB_CUDA_TRY(cudaFuncSetAttribute(rowtile_gemm_kernel<AssignEpi, ASSIGN_AN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf[dev] = true;
     }
     const uint32_t m_tiles = (uint32_t)((n + AM - 1) / AM);
-    assign_gemm_kernel<<<std::min<uint32_t>(m_tiles, (uint32_t)sms), ATHREADS, smem, stream>>>(mx, mc, p);
+    rowtile_gemm_kernel<AssignEpi, ASSIGN_AN><<<std::min<uint32_t>(m_tiles, (uint32_t)sms), ATHREADS, smem, stream>>>(mx, mc, p);
     VDB_CUDA_TRY(cudaGetLastError());
     VDB_CUDA_TRY(cudaMemsetAsync(sc.overflow_count, 0, 4, stream));
     assign_recheck_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, stream>>>(x, n, ldx, c, ldc, dim, metric, sc.cand_idx,

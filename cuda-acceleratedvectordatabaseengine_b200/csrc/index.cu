@@ -14,6 +14,7 @@
 #include <numeric>
 #include <vector>
 
+#include "bruteforce_tc.cuh"
 #include "coarse.cuh"
 #include "common.cuh"
 #include "kmeans.cuh"
@@ -847,7 +848,9 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
     DevBuf<uint64_t> oi, idb, pv, pi;
     DevBuf<uint32_t> rows, poff, zero;
     ScanWorkspace ws;
+    BruteTcScratch btc;
     auto cleanup = [&] {
+        btc.release();
         dbb.release(); qb.release(); od.release(); oi.release(); idb.release(); pv.release(); pi.release();
         rows.release(); poff.release(); zero.release(); ws.release();
     };
@@ -882,6 +885,28 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
             VDB_CUDA_TRY(cudaMemcpyAsync(idb.p, ids, n * 8, cudaMemcpyHostToDevice, s));
             dids = idb.p;
         }
+        float* dd = distances;
+        uint64_t* di = indices;
+        if (!o_dev) {
+            VDB_TRY(od.reserve((size_t)nq * k));
+            VDB_TRY(oi.reserve((size_t)nq * k));
+            dd = od.p;
+            di = oi.p;
+        }
+        auto deliver = [&]() -> int32_t {
+            if (!o_dev) {
+                VDB_CUDA_TRY(cudaMemcpyAsync(distances, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+                VDB_CUDA_TRY(cudaMemcpyAsync(indices, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+            }
+            VDB_CUDA_TRY(cudaStreamSynchronize(s));  // temporaries are freed on return
+            return VDB_OK;
+        };
+        if (bruteforce_tensor_supported(n, nq, ld, k)) {
+            // large inputs: contraction on the tensor cores, exact fp32 re-scoring of the few survivors
+            int overflowed = 0;
+            VDB_TRY(bruteforce_tensor(db, n, ld, dids, q, nq, k, metric, dd, di, btc, &overflowed, s));
+            if (!overflowed) return deliver();
+        }
         const uint32_t page_rows = 256;
         uint32_t npages = 0;
         VDB_TRY(build_flat_view(db, n, ld, page_rows, rows, poff, pv, pi, &npages, s));
@@ -896,21 +921,8 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
         uint32_t ppi = 1;
         while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (8ull << 30)) ppi *= 2;
         const uint64_t slots = (uint64_t)nq * ((npages + ppi - 1) / ppi);
-        float* dd = distances;
-        uint64_t* di = indices;
-        if (!o_dev) {
-            VDB_TRY(od.reserve((size_t)nq * k));
-            VDB_TRY(oi.reserve((size_t)nq * k));
-            dd = od.p;
-            di = oi.p;
-        }
         VDB_TRY(scan_search(lt, q, nq, zero.p, 1, k, metric, ppi, slots, ws, false, dd, di, nullptr, s));
-        if (!o_dev) {
-            VDB_CUDA_TRY(cudaMemcpyAsync(distances, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
-            VDB_CUDA_TRY(cudaMemcpyAsync(indices, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
-        }
-        VDB_CUDA_TRY(cudaStreamSynchronize(s));  // temporaries are freed on return
-        return VDB_OK;
+        return deliver();
     };
     const int32_t st = run();
     cleanup();

@@ -184,6 +184,52 @@ def test_bruteforce_768d_many_queries():
     assert (np.diff(D, axis=1) >= 0).all()
 
 
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+@pytest.mark.parametrize("n,dim,nq,k", [(70001, 96, 37, 100), (131072, 100, 130, 10), (90000, 768, 64, 33)])
+def test_bruteforce_tensor_path_matches_flat_oracle(metric, n, dim, nq, k):
+    """n >= 65536 and >= 16 queries: TF32 contraction over nested samples + exact fp32 re-scoring (bruteforce_tc.cu)
+    must return what the exact scan returns -- ids bit-exact up to ties, distances to 1e-5"""
+    x = O.gaussian(77 + dim, n + nq, dim)
+    db, q = x[:n], x[n:]
+    ids = (np.arange(n, dtype=np.uint64) * 5 + 11) if dim == 96 else None
+    nchk = min(nq, 24)
+    Dr, Ir = O.flat_search(db, q[:nchk], k, metric, ids)
+    D, I = pkg.bruteforce_search(db, q, k, pkg.Metric(metric), ids)
+    check_search(D[:nchk], I[:nchk], Dr, Ir, scale=scale_for(metric, q[:nchk], db))
+    assert (np.diff(D, axis=1) >= 0).all()
+    # the small-batch route (< 16 queries) is the exact scan: both routes must agree on every query they share
+    D2, I2 = pkg.bruteforce_search(db, q[:8], k, pkg.Metric(metric), ids)
+    check_search(D[:8], I[:8], D2, I2, scale=scale_for(metric, q[:8], db))
+
+
+def test_bruteforce_tensor_path_heavy_ties_falls_back():
+    """every row identical: the candidate lists overflow and the call must still answer exactly (scan fallback)"""
+    import torch
+    n, dim, nq, k = 70000, 64, 32, 10
+    db = torch.ones(n, dim, device="cuda")
+    db[12345] = 0.5
+    q = torch.full((nq, dim), 0.5, device="cuda")
+    D, I = pkg.bruteforce_search(db, q, k)
+    assert (I[:, 0] == 12345).all() and (D[:, 0] == 0).all()
+    assert torch.equal(I[:, 1:].cpu(), torch.arange(0, k - 1).expand(nq, k - 1))
+    assert torch.allclose(D[:, 1:], torch.full((nq, k - 1), 16.0, device="cuda"))
+
+
+def test_bruteforce_tensor_path_sorted_database():
+    """database ordered by cluster: the strided samples still see every cluster"""
+    import torch
+    n, dim, nq, k = 100000, 128, 48, 20
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    centers = torch.randn(50, dim, generator=gen, device="cuda") * 4
+    lab = torch.arange(n, device="cuda") // (n // 50)
+    db = centers[lab] + torch.randn(n, dim, generator=gen, device="cuda")
+    q = centers[torch.arange(nq, device="cuda") % 50] + torch.randn(nq, dim, generator=gen, device="cuda")
+    D, I = pkg.bruteforce_search(db, q, k)
+    ref = torch.cdist(q.double(), db.double()).pow(2).topk(k, largest=False)
+    assert torch.equal(ref.indices, I.long())
+    assert torch.allclose(ref.values.float(), D, rtol=1e-5)
+
+
 def test_kmeans_assign_entry_point():
     n, dim, nc = 5000, 40, 50
     x = O.gaussian(8, n + nc, dim)

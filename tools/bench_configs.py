@@ -100,6 +100,18 @@ def c5(ntrain):
                       "list_min_med_max": [int(sizes.min()), int(np.median(sizes)), int(sizes.max())]}), flush=True)
 
 
+def assign():
+    """nearest-centroid assignment alone (the contraction inside add() and every Lloyd iteration)"""
+    n, dim, nlist = 1_000_000, 768, 16384
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, dim, generator=g, device="cuda")
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist))
+    ix.centroids = torch.randn(nlist, dim, generator=g, device="cuda").cpu().numpy()
+    ms = ev_time(lambda: ix.assign_device(x), 3, warm=1)
+    print(json.dumps({"config": "assign 1Mx768 vs 16384 centroids", "ms": ms,
+                      "tflops_equiv": 2.0 * n * nlist * dim / ms / 1e9}), flush=True)
+
+
 if __name__ == "__main__":
     args = sys.argv[1:] or ["c1", "c2"]
     ntrain = 262144
@@ -109,5 +121,7 @@ if __name__ == "__main__":
         c1()
     if "c2" in args:
         c2()
+    if "assign" in args:
+        assign()
     if "c5" in args:
         c5(ntrain)
