@@ -10,7 +10,7 @@
 //      buffers while the four epilogue warps drain the other (thread = row).
 //      The epilogue never materialises the n x nlist score matrix: per row it
 //      keeps the smallest UPPER bound of the true score seen so far and the
-//      (at most 4) centroids whose LOWER bound does not exceed it.
+//      (at most 8) centroids whose LOWER bound does not exceed it.
 //   3. assign_recheck_kernel the survivors (1-2 per row in practice) are scored
 //      exactly like the reference -- fp32, ascending dimension, unfused multiply
 //      and add, strict '<' in ascending centroid order -- so the result is
@@ -26,7 +26,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int NCAND = 4;
+constexpr int NCAND = 8;
 
 __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32_t ld, float* __restrict__ out,
                                  bool take_sqrt) {
@@ -44,85 +44,164 @@ __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32
 }
 
 // Epilogue of the assignment: per row, the smallest UPPER bound of a true score seen so far and the (at most
-// NCAND) centroids whose LOWER bound does not exceed it.
+// NCAND) centroids whose LOWER bound does not exceed it.  With score = |c|^2 - 2 x.c (L2, the common |x|^2 left
+// out) or -x.c (IP), and eps = (dim + 16) 2^-24 covering the fp32 rounding of this arithmetic and of the exact
+// kernel's own summation:
+//     t  = fma(dot, alpha, A_c)            A_c = |c|^2 (L2) / 0 (IP), alpha = -2 / -1
+//     e  = fma(|x| c', |c|, E_c)           c' = 1.05 * 2^-8 + 2 eps,  E_c = eps |c|^2 (L2) / 0 (IP)
+//     ub = t + e,  lb = t - e              a centroid survives while lb <= min ub + 2 eps |x|^2
+// A_c, |c| and E_c come from column tables padded to the tile width (A = +inf there: never a survivor).
 constexpr int ASSIGN_AN = 256;  // centroid columns per accumulator tile
 
+__global__ void assign_columns_kernel(const float* __restrict__ c, uint32_t nc, uint32_t npad, uint32_t ld, int metric,
+                                      float eps, float* __restrict__ colA, float* __restrict__ colB,
+                                      float* __restrict__ colE) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= npad) return;
+    if (w >= nc) {
+        if (lane == 0) {
+            colA[w] = INFINITY;
+            colB[w] = 0.f;
+            colE[w] = 0.f;
+        }
+        return;
+    }
+    float s = 0.f;
+    for (uint32_t d = lane; d < ld; d += 32) {
+        const float v = c[(size_t)w * ld + d];
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const bool l2 = metric == VDB_METRIC_L2;
+        colA[w] = l2 ? s : 0.f;
+        colB[w] = sqrtf(s) * (1.f + 1e-6f);
+        colE[w] = l2 ? eps * s : 0.f;
+    }
+}
+
 struct AssignEpi {
-    const float* xnorm;   // [M] |x_v|
-    const float* cnorm2;  // [N] |c|^2
+    const float* xnorm;  // [M] |x_v|
+    const float* colA;   // [N padded to ASSIGN_AN]
+    const float* colB;
+    const float* colE;
     uint32_t M, N, num_kb, n_split;
     int metric;
-    uint32_t* cand_idx;   // [M][NCAND]
-    uint32_t* cand_cnt;   // [M]  (NCAND + 1 = overflow: fall back to the exact kernel for this row)
+    float eps;
+    uint32_t* cand_idx;  // [M][NCAND]
+    uint32_t* cand_cnt;  // [M]  (NCAND + 1 = overflow: fall back to the exact kernel for this row)
 
+    static constexpr uint32_t WARP_SMEM = 0;
     struct State {
-        float xe, U;
+        float xe, U, slack, alpha;  // U = smallest ub so far; survivors need lb <= U + slack
         float clb[NCAND];
         uint32_t cix[NCAND];
         uint32_t cnt;
-        bool overflow;
+        float dropped;  // smallest lower bound among survivors that did not fit; harmless if it ends above the limit
     };
-    static constexpr uint32_t WARP_SMEM = 0;
-    __device__ __forceinline__ void chunk_end(State&, uint8_t*) const {}
     __device__ __forceinline__ void begin(State& s, uint32_t row, uint8_t*) const {
-        s.xe = 1.05f * 0.00390625f * xnorm[row];
+        const float xn = xnorm[row];
+        const bool l2 = metric == VDB_METRIC_L2;
+        s.xe = xn * (1.05f * 0.00390625f + (l2 ? 2.f * eps : eps));
+        s.slack = l2 ? 2.f * eps * xn * xn : 0.f;
+        s.alpha = l2 ? -2.f : -1.f;
         s.U = INFINITY;
         s.cnt = 0;
-        s.overflow = false;
+        s.dropped = INFINITY;
 #pragma unroll
         for (int i = 0; i < NCAND; ++i) {
             s.clb[i] = INFINITY;
             s.cix[i] = 0;
         }
     }
-    __device__ __forceinline__ void consume_chunk(State& s, uint32_t row, uint32_t n0, const uint32_t (&acc)[32]) const {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (n0 + i < N) consume(s, row, n0 + i, __uint_as_float(acc[i]));
-    }
-    __device__ __forceinline__ void consume(State& s, uint32_t, uint32_t n, float dot) const {
-        const float cn2 = __ldg(cnorm2 + n);
-        const float sc = (metric == VDB_METRIC_L2) ? fmaf(-2.f, dot, cn2) : -dot;
-        const float e = s.xe * sqrtf(cn2) + 1e-6f * fabsf(sc) + 1e-30f;
-        const float ub = sc + e, lb = sc - e;
-        s.U = fminf(s.U, ub);
-        if (lb <= s.U) {
-            // keep it; first drop survivors the tighter bound has ruled out meanwhile
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < NCAND; ++j)
-                if ((uint32_t)j < s.cnt && s.clb[j] <= s.U) {
-                    const float tl = s.clb[j];
-                    const uint32_t ti = s.cix[j];
-#pragma unroll
-                    for (int t = 0; t < NCAND; ++t)
-                        if ((uint32_t)t == w) {
-                            s.clb[t] = tl;
-                            s.cix[t] = ti;
-                        }
-                    ++w;
-                }
-            s.cnt = w;
-            if (s.cnt < NCAND) {
-#pragma unroll
-                for (int t = 0; t < NCAND; ++t)
-                    if ((uint32_t)t == s.cnt) {
-                        s.clb[t] = lb;
-                        s.cix[t] = n;
-                    }
-                ++s.cnt;
-            } else {
-                s.overflow = true;
-            }
-        }
-    }
-    __device__ __forceinline__ void end(State& s, uint32_t row, bool valid, uint8_t*) const {
-        if (!valid) return;
+    // keep centroid n (lower bound lb); first drop survivors the tighter bound has ruled out meanwhile
+    __device__ __forceinline__ void keep(State& s, uint32_t n, float lb) const {
+        const float lim = s.U + s.slack;
         uint32_t w = 0;
 #pragma unroll
         for (int j = 0; j < NCAND; ++j)
-            if ((uint32_t)j < s.cnt && s.clb[j] <= s.U) cand_idx[(size_t)row * NCAND + w++] = s.cix[j];
-        cand_cnt[row] = s.overflow ? NCAND + 1 : w;
+            if ((uint32_t)j < s.cnt && s.clb[j] <= lim) {
+                const float tl = s.clb[j];
+                const uint32_t ti = s.cix[j];
+#pragma unroll
+                for (int t = 0; t < NCAND; ++t)
+                    if ((uint32_t)t == w) {
+                        s.clb[t] = tl;
+                        s.cix[t] = ti;
+                    }
+                ++w;
+            }
+        s.cnt = w;
+        if (s.cnt < NCAND) {
+#pragma unroll
+            for (int t = 0; t < NCAND; ++t)
+                if ((uint32_t)t == s.cnt) {
+                    s.clb[t] = lb;
+                    s.cix[t] = n;
+                }
+            ++s.cnt;
+        } else {
+            // full: the entry with the largest lower bound (the new one included) makes room
+            float worst = lb;
+            int wi = -1;
+#pragma unroll
+            for (int t = 0; t < NCAND; ++t)
+                if (s.clb[t] > worst) {
+                    worst = s.clb[t];
+                    wi = t;
+                }
+            s.dropped = fminf(s.dropped, worst);
+#pragma unroll
+            for (int t = 0; t < NCAND; ++t)
+                if (t == wi) {
+                    s.clb[t] = lb;
+                    s.cix[t] = n;
+                }
+        }
+    }
+    __device__ __forceinline__ void consume_chunk(State& s, uint32_t, uint32_t n0, const uint32_t (&acc)[32]) const {
+        const float4* A4 = reinterpret_cast<const float4*>(colA + n0);
+        const float4* B4 = reinterpret_cast<const float4*>(colB + n0);
+        const float4* E4 = reinterpret_cast<const float4*>(colE + n0);
+        float lb[32];
+        float U = s.U;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(A4 + j), b = __ldg(B4 + j), ee = __ldg(E4 + j);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, ev[4] = {ee.x, ee.y, ee.z, ee.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float t = fmaf(__uint_as_float(acc[4 * j + i]), s.alpha, av[i]);
+                const float e = fmaf(s.xe, bv[i], ev[i]);
+                U = fminf(U, t + e);
+                lb[4 * j + i] = t - e;
+            }
+        }
+        s.U = U;
+        const float lim = U + s.slack;
+        uint32_t hit = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hit |= (lb[i] <= lim ? 1u : 0u) << i;
+        while (hit) {  // rare: a new running minimum, or a near tie with it
+            const uint32_t i = __ffs(hit) - 1;
+            hit &= hit - 1;
+            float l = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if ((uint32_t)j == i) l = lb[j];
+            if (n0 + i < N) keep(s, n0 + i, l);
+        }
+    }
+    __device__ __forceinline__ void chunk_end(State&, uint8_t*) const {}
+    __device__ __forceinline__ void end(State& s, uint32_t row, bool valid, uint8_t*) const {
+        if (!valid) return;
+        const float lim = s.U + s.slack;
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < NCAND; ++j)
+            if ((uint32_t)j < s.cnt && s.clb[j] <= lim) cand_idx[(size_t)row * NCAND + w++] = s.cix[j];
+        cand_cnt[row] = s.dropped <= lim ? NCAND + 1 : w;
     }
 };
 
@@ -220,11 +299,12 @@ int32_t AssignTcScratch::reserve(uint64_t n, uint32_t nc) {
     }
     if (nc > cap_nc) {
         cudaFree(cnorm2);
-        cap_nc = nc;
-        VDB_CUDA_TRY(cudaMalloc(&cnorm2, (size_t)cap_nc * 4));
+        cap_nc = round_up(nc, (uint32_t)ASSIGN_AN);
+        VDB_CUDA_TRY(cudaMalloc(&cnorm2, (size_t)cap_nc * 3 * 4));  // three column tables (assign_columns_kernel)
     }
     if (!overflow_count) {
         VDB_CUDA_TRY(cudaMalloc(&overflow_count, 4));
+        VDB_CUDA_TRY(cudaMalloc(&fewrow_keys, FEWROWS_MAX * 8));
         VDB_CUDA_TRY(cudaMallocHost(&h_overflow, 4));
     }
     return VDB_OK;
@@ -232,7 +312,7 @@ int32_t AssignTcScratch::reserve(uint64_t n, uint32_t nc) {
 
 void AssignTcScratch::release() {
     cudaFree(xnorm); cudaFree(cand_idx); cudaFree(cand_cnt); cudaFree(overflow_rows); cudaFree(cnorm2);
-    cudaFree(overflow_count);
+    cudaFree(overflow_count); cudaFree(fewrow_keys);
     if (h_overflow) cudaFreeHost(h_overflow);
     *this = AssignTcScratch();
 }
@@ -245,12 +325,16 @@ int32_t kmeans_assign_tensor(const float* x, uint64_t n, uint32_t ldx, const flo
     VDB_REQUIRE(n < (1ull << 31), "assign: too many rows for one call");
     VDB_TRY(sc.reserve(n, nc));
     row_norms_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, ldx, sc.xnorm, true);
-    row_norms_kernel<<<(uint32_t)(((uint64_t)nc * 32 + 255) / 256), 256, 0, stream>>>(c, nc, ldc, sc.cnorm2, false);
+    const uint32_t npad = round_up(nc, (uint32_t)ASSIGN_AN);
+    const float eps = std::max(1e-6f, (float)(ldx + 16) * 5.9604645e-8f);
+    float *colA = sc.cnorm2, *colB = sc.cnorm2 + npad, *colE = sc.cnorm2 + 2 * (size_t)npad;
+    assign_columns_kernel<<<(uint32_t)(((uint64_t)npad * 32 + 255) / 256), 256, 0, stream>>>(c, nc, npad, ldc, metric, eps,
+                                                                                          colA, colB, colE);
     CUtensorMap mx, mc;
     VDB_TRY(tc::make_map(&mx, x, n, ldx, ldx, AM));
     VDB_TRY(tc::make_map(&mc, c, nc, ldc, ldc, ASSIGN_AN));
     AssignEpi p;
-    p.xnorm = sc.xnorm; p.cnorm2 = sc.cnorm2;
+    p.xnorm = sc.xnorm; p.colA = colA; p.colB = colB; p.colE = colE; p.eps = eps;
     p.M = (uint32_t)n; p.N = nc; p.num_kb = (ldx + GK - 1) / GK; p.n_split = 1; p.metric = metric;
     p.cand_idx = sc.cand_idx; p.cand_cnt = sc.cand_cnt;
     constexpr uint32_t smem = rowtile_smem<AssignEpi, ASSIGN_AN>();
@@ -275,7 +359,7 @@ int32_t kmeans_assign_tensor(const float* x, uint64_t n, uint32_t ldx, const flo
     sc.last_overflow = *sc.h_overflow;
     if (sc.last_overflow)  // rows with more than NCAND survivors: the scalar kernel, on just those rows
         VDB_TRY(kmeans_assign_exact_rows(x, sc.overflow_rows, sc.last_overflow, ldx, c, nc, ldc, dim, metric, assign,
-                                         stream));
+                                         sc.fewrow_keys, stream));
     return VDB_OK;
 }
 

@@ -550,11 +550,78 @@ int32_t kmeans_assign_exact(const float* x, uint64_t n, uint32_t ldx, const floa
     return VDB_OK;
 }
 
+// A handful of rows (the tensor path's overflow list): the tiled kernel above would leave the GPU idle, so one row
+// is spread over FEW_SPLIT blocks, one thread per centroid with the reference's sequential sum, and the block
+// results meet in an atomicMin on (distance, centroid) keys -- strict '<' with the lowest index winning ties.
+constexpr uint32_t FEW_SPLIT = 16;
+
+__device__ __forceinline__ uint32_t ordered_bits(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) assign_fewrows_kernel(const float* __restrict__ x, uint32_t ldx,
+                                                             const uint32_t* __restrict__ row_index,
+                                                             const float* __restrict__ c, uint32_t nc, uint32_t ldc,
+                                                             uint32_t dim, int metric,
+                                                             unsigned long long* __restrict__ keys) {
+    extern __shared__ float srow[];
+    const uint32_t r = blockIdx.x, tid = threadIdx.x;
+    const float* xr = x + (size_t)row_index[r] * ldx;
+    for (uint32_t d = tid; d < dim; d += 256) srow[d] = xr[d];
+    __syncthreads();
+    const uint32_t per = (nc + FEW_SPLIT - 1) / FEW_SPLIT;
+    const uint32_t lo = blockIdx.y * per, hi = min(nc, lo + per);
+    unsigned long long best = ~0ull;
+    for (uint32_t cc = lo + tid; cc < hi; cc += 256) {
+        const float* cv = c + (size_t)cc * ldc;
+        float a = 0.f;
+        if (metric == VDB_METRIC_L2) {
+            for (uint32_t d = 0; d < dim; ++d) {
+                const float diff = __fsub_rn(srow[d], __ldg(cv + d));
+                a = __fadd_rn(a, __fmul_rn(diff, diff));
+            }
+        } else {
+            for (uint32_t d = 0; d < dim; ++d) a = __fadd_rn(a, __fmul_rn(srow[d], __ldg(cv + d)));
+            a = -a;
+        }
+        if (a == 0.f) a = 0.f;  // -0 and +0 compare equal in the reference; keep one encoding
+        if (a < FLT_MAX) {
+            const unsigned long long key = ((unsigned long long)ordered_bits(a) << 32) | cc;
+            best = key < best ? key : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((tid & 31) == 0 && best != ~0ull) atomicMin(&keys[r], best);
+}
+
+__global__ void assign_fewrows_finish_kernel(const unsigned long long* __restrict__ keys,
+                                             const uint32_t* __restrict__ row_index, uint32_t m,
+                                             uint32_t* __restrict__ assign) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    // nothing below FLT_MAX: min_dist stays at its initial value and best_list at 0 (:266-267)
+    assign[row_index[r]] = keys[r] == ~0ull ? 0u : (uint32_t)(keys[r] & 0xffffffffu);
+}
+
 // the same for the rows listed in row_index[0..m): results go to assign[row_index[i]]
 int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint64_t m, uint32_t ldx, const float* c,
                                  uint32_t nc, uint32_t ldc, uint32_t dim, int metric, uint32_t* assign,
-                                 cudaStream_t stream) {
+                                 unsigned long long* keys, cudaStream_t stream) {
     if (m == 0) return VDB_OK;
+    if (keys && m <= FEWROWS_MAX && nc >= 4096) {  // keys: FEWROWS_MAX words of scratch
+        VDB_CUDA_TRY(cudaMemsetAsync(keys, 0xff, m * 8, stream));
+        assign_fewrows_kernel<<<dim3((uint32_t)m, FEW_SPLIT), 256, dim * 4, stream>>>(x, ldx, row_index, c, nc, ldc, dim,
+                                                                                      metric, keys);
+        assign_fewrows_finish_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, stream>>>(keys, row_index, (uint32_t)m,
+                                                                                      assign);
+        VDB_CUDA_TRY(cudaGetLastError());
+        return VDB_OK;
+    }
     assign_exact_kernel<<<(uint32_t)((m + TV - 1) / TV), 256, 0, stream>>>(x, m, ldx, c, nc, ldc, dim, metric, assign,
                                                                             nullptr, row_index);
     VDB_CUDA_TRY(cudaGetLastError());

@@ -23,9 +23,10 @@ struct KMeansScratch {
 
 int32_t kmeans_assign_exact(const float* x, uint64_t n, uint32_t ldx, const float* c, uint32_t nc, uint32_t ldc,
                             uint32_t dim, int metric, uint32_t* assign, float* dist_out, cudaStream_t stream);
+constexpr uint64_t FEWROWS_MAX = 2048;  // up to this many listed rows take the row-parallel kernel
 int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint64_t m, uint32_t ldx, const float* c,
                                  uint32_t nc, uint32_t ldc, uint32_t dim, int metric, uint32_t* assign,
-                                 cudaStream_t stream);
+                                 unsigned long long* keys, cudaStream_t stream);
 
 // tensor-core assignment (assign_tc.cu): bit-identical to kmeans_assign_exact, O(n nlist dim) on tcgen05
 struct AssignTcScratch {
@@ -35,6 +36,7 @@ struct AssignTcScratch {
     uint32_t* cand_cnt = nullptr;
     uint32_t* overflow_rows = nullptr;
     uint32_t* overflow_count = nullptr;
+    unsigned long long* fewrow_keys = nullptr;  // [FEWROWS_MAX]
     uint32_t* h_overflow = nullptr;
     uint64_t cap_n = 0;
     uint32_t cap_nc = 0;
