@@ -94,7 +94,13 @@ def c5(ntrain):
         torch.cuda.synchronize()
         t = time.perf_counter(); ix.add(x); t_add += time.perf_counter() - t
     sizes = ix.list_sizes()
+    # exactness spot check of the tensor-core assignment against a float64 torch argmin
+    cent = torch.from_numpy(ix.centroids).cuda().double()
+    xs = x[:20000]
+    d2 = (cent * cent).sum(1)[None, :] - 2.0 * xs.double() @ cent.T
+    agree = float((d2.argmin(1).int() == ix.assign_device(xs)).float().mean())
     print(json.dumps({"config": f"c5 train({ntrain}) + add(10M) 768D nlist=16384", "train_s": t_train,
+                      "assign_agreement_vs_torch_f64": agree,
                       "add_s": t_add, "add_rows_per_s": n / t_add,
                       "add_assign_tflops": 2.0 * n * nlist * dim / t_add / 1e12,
                       "list_min_med_max": [int(sizes.min()), int(np.median(sizes)), int(sizes.max())]}), flush=True)
