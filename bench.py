@@ -40,8 +40,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--metric", default="l2", choices=["l2", "ip"])
     ap.add_argument("--nlist", type=int, default=4096)
     ap.add_argument("--nprobe", type=int, default=32)
     ap.add_argument("--k", type=int, default=10)
@@ -54,8 +55,11 @@ def parse():
 
 
 def workload_name(a):
-    return (f"IVF-Flat {a.n / 1e6:g}M x {a.dim}D L2 nlist={a.nlist} nprobe={a.nprobe} k={a.k} batch={a.batch} "
-            f"(BASELINE.json configs[2])")
+    shape = (a.n, a.dim, a.metric, a.nlist, a.nprobe, a.k, a.batch)
+    tag = {(10_000_000, 768, "l2", 4096, 32, 10, 64): " (BASELINE.json configs[2])",
+           (100_000_000, 768, "ip", 16384, 64, 10, 64): " (BASELINE.json configs[3])"}.get(shape, "")
+    return (f"IVF-Flat {a.n / 1e6:g}M x {a.dim}D {'L2' if a.metric == 'l2' else 'inner product'} nlist={a.nlist} "
+            f"nprobe={a.nprobe} k={a.k} batch={a.batch}{tag}")
 
 
 # ---------------------------------------------------------------- clocks
@@ -226,7 +230,7 @@ def run_b200(a):
 
     # ---- build: synthetic N(0,1) rows generated on the device, trained + added by the CUDA path
     t_build = time.perf_counter()
-    ix = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, metric=pkg.Metric.L2, device=local,
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, metric=pkg.Metric.L2 if a.metric == "l2" else pkg.Metric.InnerProduct, device=local,
                                      shard_rank=rank, shard_count=world))
     gen = torch.Generator(device=dev).manual_seed(12345)
     chunk = 1_000_000
