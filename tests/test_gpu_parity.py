@@ -185,7 +185,8 @@ def test_bruteforce_768d_many_queries():
 
 
 @pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
-@pytest.mark.parametrize("n,dim,nq,k", [(70001, 96, 37, 100), (131072, 100, 130, 10), (90000, 768, 64, 33)])
+@pytest.mark.parametrize("n,dim,nq,k", [(70001, 96, 37, 100), (131072, 100, 130, 10), (90000, 768, 64, 33),
+                                        (65536, 64, 16, 1000), (300000, 32, 257, 1)])
 def test_bruteforce_tensor_path_matches_flat_oracle(metric, n, dim, nq, k):
     """n >= 65536 and >= 16 queries: TF32 contraction over nested samples + exact fp32 re-scoring (bruteforce_tc.cu)
     must return what the exact scan returns -- ids bit-exact up to ties, distances to 1e-5"""
