@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ntrain", type=int, default=262144)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: peer-memory exchange+merge kernel, or NCCL all-gathers + merge kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
     ap.add_argument("--dump-groups", action="store_true", help="stderr: probed-row work by queries-per-list")
@@ -269,14 +271,23 @@ def run_b200(a):
     if world > 1:
         Dg = torch.empty((world, a.batch, a.k), dtype=torch.float32, device=dev)
         Ig = torch.empty((world, a.batch, a.k), dtype=torch.int64, device=dev)
+        Dm = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
+        Im = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
+        sharded = importlib.import_module(PKG + ".sharded")
+        exch = sharded.PeerExchange(pkg, local, None, a.batch, a.k) if a.exchange == "p2p" else None
+
+    def exchange_merge():
+        # every rank's local top-k -> all ranks, merged by (distance, id)
+        if exch is not None:  # one kernel per rank: peer-memory publish + wait + merge (csrc/exchange.cu)
+            exch.merge_topk_into(D, I, Dm, Im, stream)
+            return Dm, Im
+        dist.all_gather_into_tensor(Dg, D)
+        dist.all_gather_into_tensor(Ig, I)
+        return pkg.merge_topk(Dg, Ig, stream)
 
     def step_device(s):
         ix.search_async(q_all[s], a.nprobe, a.k, D, I, stream)
-        if world > 1:  # every rank's local top-k -> all ranks, then merge by (distance, id)
-            dist.all_gather_into_tensor(Dg, D)
-            dist.all_gather_into_tensor(Ig, I)
-            return pkg.merge_topk(Dg, Ig, stream)
-        return D, I
+        return exchange_merge() if world > 1 else (D, I)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -316,11 +327,9 @@ def run_b200(a):
         else:
             qd = q_host[s].to(dev, non_blocking=True)
             ix.search_async(qd, a.nprobe, a.k, D, I, stream)
-            dist.all_gather_into_tensor(Dg, D)
-            dist.all_gather_into_tensor(Ig, I)
-            Dm, Im = pkg.merge_topk(Dg, Ig, stream)
-            Dh.copy_(Dm, non_blocking=True)
-            Ih.copy_(Im, non_blocking=True)
+            Do, Io = exchange_merge()
+            Dh.copy_(Do, non_blocking=True)
+            Ih.copy_(Io, non_blocking=True)
             torch.cuda.synchronize()
 
     for s in range(min(a.warmup, 5)):
@@ -369,7 +378,9 @@ def run_b200(a):
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, NCCL all-gather merge",
+        "config": {"workload": workload_name(a), "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, " +
+                   ("single GPU: no exchange" if world == 1 else
+                    "NVLink peer-memory exchange+merge kernel" if a.exchange == "p2p" else "NCCL all-gather + merge kernel"),
                    "cache": f"inputs larger than L2: each batch streams {uniq_bytes / 1e9:.2f} GB of distinct list data",
                    "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),

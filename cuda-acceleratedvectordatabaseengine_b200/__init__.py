@@ -94,6 +94,11 @@ ABI = {
     "vdb_kmeans_accumulate": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp]),
     "vdb_kmeans_finalize": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "vdb_merge_topk": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "vdb_exchange_create": (_i32, [_i32, _u32, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "vdb_exchange_handle": (_i32, [_vp, _vp]),
+    "vdb_exchange_connect": (_i32, [_vp, _vp]),
+    "vdb_exchange_merge_topk": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "vdb_exchange_destroy": (_i32, [_vp]),
     "vdb_arena_create": (_i32, [_i32, _u64, _u64, _i32, C.POINTER(_vp)]),
     "vdb_arena_destroy": (_i32, [_vp]),
     "vdb_arena_allocate_device": (_vp, [_vp, _u64]),

@@ -11,8 +11,10 @@ units and the only exchange step is the final merge.
     (greedy, largest first, identical table on every rank; IVFFlatIndex.owners())
     every rank: same centroids, same coarse selection on the full query batch,
                 scan of the probed lists it owns -> local [nq][k] padded FLT_MAX/UINT64_MAX
-    all_gather of the local (distances, ids)         (gather_topk)
-    merge by (distance, id), duplicates dropped      (vdb_merge_topk kernel)
+    exchange + merge by (distance, id), duplicates dropped:
+      exchange="p2p"   one kernel per rank over NVLink peer memory (PeerExchange / csrc/exchange.cu) -- the default
+                       on a CUDA group with peer access
+      exchange="nccl"  all_gather of the local (distances, ids) (gather_topk) + vdb_merge_topk kernel
 
 The result is independent of the number of ranks by construction (same
 tie-break everywhere); tests/test_sharded_gloo.py checks exactly that.
@@ -40,6 +42,51 @@ def gather_topk(D, I, group=None):
     return Dg, Ig
 
 
+class PeerExchange:
+    """vdb_exchange_*: the per-rank mailboxes are mapped into every peer with CUDA IPC handles gathered over the
+    process group; merge_topk() is then a single kernel launch per rank (publish -> wait -> merge)."""
+
+    def __init__(self, pkg, device, group=None, max_nq=1024, max_k=64):
+        import ctypes as C
+        self.pkg, self.group = pkg, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.max_nq, self.max_k = max_nq, max_k
+        h = C.c_void_p()
+        pkg._check(pkg.lib().vdb_exchange_create(device, self.rank, self.world, max_nq, max_k, C.byref(h)))
+        self._h = h
+        mine = (C.c_uint8 * 64)()
+        pkg._check(pkg.lib().vdb_exchange_handle(self._h, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        buf = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        pkg._check(pkg.lib().vdb_exchange_connect(self._h, buf))
+        dist.barrier(group=group)  # every peer has mapped every mailbox before the first publish
+
+    def merge_topk(self, D, I, stream=0):
+        """local [nq][k] CUDA tensors -> merged ([nq][k] f32, [nq][k] i64); collective, same order on all ranks"""
+        nq, k = D.shape
+        Do = torch.empty((nq, k), dtype=torch.float32, device=D.device)
+        Io = torch.empty((nq, k), dtype=torch.int64, device=D.device)
+        self.merge_topk_into(D, I, Do, Io, stream)
+        return Do, Io
+
+    def merge_topk_into(self, D, I, Do, Io, stream=0):
+        nq, k = D.shape
+        self.pkg._check(self.pkg.lib().vdb_exchange_merge_topk(self._h, D.data_ptr(), I.data_ptr(), nq, k,
+                                                               Do.data_ptr(), Io.data_ptr(), stream))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.pkg.lib().vdb_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedIVFFlatIndex:
     """vdb::IVFFlatIndex surface over `world` list shards, one per rank.
 
@@ -48,12 +95,18 @@ class ShardedIVFFlatIndex:
     add_distributed(): each rank assigns its own slice, one all-to-all routes rows to the owning ranks;
     search(): local search + all-gather + merge; every rank returns the full answer."""
 
-    def __init__(self, pkg, config, group=None):
+    def __init__(self, pkg, config, group=None, exchange="auto", max_nq=1024, max_k=64):
         self.pkg, self.group = pkg, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         config.shard_rank, config.shard_count = self.rank, self.world
         self.local = pkg.IVFFlatIndex(config)
         self.config = config
+        # exchange: "p2p" (peer-memory kernel), "nccl" (all-gather + merge kernel), "auto" = p2p on an NCCL group
+        # of more than one rank whose (world * max_k) fits the mailbox merge
+        if exchange == "auto":
+            exchange = "p2p" if (self.world > 1 and torch.cuda.is_available() and
+                                 dist.get_backend(group) == "nccl" and self.world * max_k <= 4096) else "nccl"
+        self.exchange = PeerExchange(pkg, config.device, group, max_nq, max_k) if exchange == "p2p" else None
 
     def train(self, vectors):
         self.local.train(vectors)
@@ -98,6 +151,9 @@ class ShardedIVFFlatIndex:
         self.local.search_async(queries, nprobe, k, D, I, s)
         if self.world == 1:
             return D, I
+        ex = self.exchange
+        if ex is not None and nq <= ex.max_nq and k <= ex.max_k:
+            return ex.merge_topk(D, I, s)
         Dg, Ig = gather_topk(D, I, self.group)
         return self.pkg.merge_topk(Dg, Ig, s)
 

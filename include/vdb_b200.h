@@ -95,6 +95,7 @@ typedef struct {
 
 typedef struct vdb_index vdb_index;
 typedef struct vdb_arena vdb_arena;
+typedef struct vdb_exchange vdb_exchange;
 
 const char* vdb_last_error_string(void);
 const char* vdb_status_string(int32_t status);
@@ -179,6 +180,20 @@ int32_t vdb_kmeans_finalize(const float* sums_dev, const uint32_t* counts_dev, f
  * by (distance, id), duplicates removed, padded.  Device pointers. */
 int32_t vdb_merge_topk(const float* dist_parts_dev, const uint64_t* id_parts_dev, uint32_t parts, uint32_t nq,
                        uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
+
+/* The same merge fused with the exchange, over NVLink peer memory (csrc/exchange.cu): one kernel per rank stores
+ * the rank's local [nq][k] block into every peer's mailbox, waits for the peers' blocks and merges -- instead of
+ * two all-gathers plus vdb_merge_topk.  One process per GPU: create on every rank, pass the 64-byte handle of
+ * every rank (rank order; e.g. from an all_gather of vdb_exchange_handle) to connect, then call merge_topk
+ * collectively (same order and shapes on every rank).  world * max_k <= 4096.  A peer that never arrives makes
+ * the call's results padded and the NEXT call return VDB_NCCL_ERROR (5 s timeout). */
+int32_t vdb_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint32_t max_nq, uint32_t max_k,
+                            vdb_exchange** out);
+int32_t vdb_exchange_handle(vdb_exchange* ex, uint8_t* out64);
+int32_t vdb_exchange_connect(vdb_exchange* ex, const uint8_t* handles);
+int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev,
+                                uint32_t nq, uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
+int32_t vdb_exchange_destroy(vdb_exchange* ex);
 
 /* TransferManager rewrite (transfer_manager.h:42-88): one HBM slab and one
  * pinned slab carved by a best-fit allocator, a stream pool, async copies. */

@@ -37,7 +37,23 @@ def _worker(rank, port, ret):
     mine = np.arange(half + rank, n, WORLD)
     ix.add_distributed(torch.from_numpy(db[mine]).cuda(), torch.from_numpy(mine.astype(np.int64)).cuda())
     assert ix.get_total_vectors() == n
+    assert ix.exchange is not None, "an NCCL group of 2 ranks must take the peer-memory exchange"
     D, I = ix.search(q, nprobe, k)
+    # the portable exchange (two all-gathers + merge kernel) must give the same bits, call after call
+    qd = torch.from_numpy(q).cuda()
+    for rep in range(5):
+        Dp, Ip = ix.search_device(qd, nprobe, k)
+        ex, ix.exchange = ix.exchange, None
+        Dn, In = ix.search_device(qd, nprobe, k)
+        ix.exchange = ex
+        assert torch.equal(Dp, Dn) and torch.equal(Ip, In), f"p2p and nccl exchange differ (rep {rep})"
+    assert np.array_equal(Dp.cpu().numpy(), D) and np.array_equal(Ip.cpu().numpy().view(np.uint64), I)
+    # ragged shapes through the mailbox: fewer queries, larger k (padding travels too)
+    D2, I2 = ix.search_device(qd[:7], nlist, 64)
+    ex, ix.exchange = ix.exchange, None
+    D3, I3 = ix.search_device(qd[:7], nlist, 64)
+    ix.exchange = ex
+    assert torch.equal(D2, D3) and torch.equal(I2, I3)
     sizes = ix.local.list_sizes()
     assert (sizes[owners != rank] == 0).all()
     tot = torch.tensor([int(sizes.sum())], device="cuda")
