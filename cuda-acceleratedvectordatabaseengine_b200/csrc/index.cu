@@ -483,12 +483,13 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
     if (st == VDB_OK) st = sc.reserve((uint32_t)n, ix->nlist, ix->ld);
     const uint32_t ldx = ix->ld;
     // k-means++ seeding, always L2 (ivf_flat_index.cpp:63-104)
-    // AUTO: the reference's sequential sampling sums (bit-exact) unless that would take minutes
-    const bool exact_seed = ix->cfg.train_mode == VDB_TRAIN_EXACT ||
-                            (ix->cfg.train_mode == VDB_TRAIN_AUTO && (uint64_t)n * ix->nlist <= (2ull << 30));
+    // AUTO: the reference's sequential fp32 sampling sums, evaluated in parallel (bit-exact at any size);
+    // EXACT: the literal one-lane chain (and the scalar assignment kernel) -- the checker for AUTO; FAST: fp64 sums
+    const SeedSampler sampler = ix->cfg.train_mode == VDB_TRAIN_EXACT  ? SeedSampler::Sequential
+                                : ix->cfg.train_mode == VDB_TRAIN_FAST ? SeedSampler::Fast
+                                                                       : SeedSampler::ExactParallel;
     if (st == VDB_OK)
-        st = kmeanspp_seed(x, (uint32_t)n, ldx, ix->dim, ix->ld, ix->nlist, ix->centroids.p, sc, exact_seed,
-                           ix->stream);
+        st = kmeanspp_seed(x, (uint32_t)n, ldx, ix->dim, ix->ld, ix->nlist, ix->centroids.p, sc, sampler, ix->stream);
     // exactly 10 Lloyd iterations; assignment honours the index metric (:109-142, :275-285)
     for (int iter = 0; iter < 10 && st == VDB_OK; ++iter) {
         st = assign_rows(ix, x, n, sc.assign, ix->stream);

@@ -318,6 +318,242 @@ __global__ void __launch_bounds__(32) seed_sample_kernel(DevRng* g, const float*
     for (uint32_t d = lane; d < ld; d += 32) centroids[(size_t)cidx * ld + d] = x[(size_t)v * ldx + d];
 }
 
+// ---- the same sequential fp32 sums, evaluated in parallel, bit for bit ----------------------------------------
+// s_{i+1} = fl(s_i + x_i) with x_i >= 0 looks inherently serial, but while the running sum stays inside one binade
+// (s = S * 2^eu, S an integer below 2^24) round-to-nearest-even is integer arithmetic on S:
+//     S' = S + y + c,   x / 2^eu = y + f,   c = [f > 1/2], or for a tie f = 1/2 the parity of S + y.
+// An element is therefore a map S -> S + (increment that depends only on the parity of S), such maps compose into
+// maps of the same kind (a pair of increments, one per parity of the start value), and composition is associative:
+// a block-wide scan gives every thread the exact sum in front of its elements.  Leaving the binade (S' >= 2^24,
+// about log2(sum / first term) ~ 20-40 times per pass) is detected at the first element where it happens; that one
+// addition is done with a real __fadd_rn, a few dozen more follow sequentially (the sum grows fast at the start),
+// and the scan resumes behind them with the new unit.  Results equal seed_sample_kernel's
+// (tests/test_gpu_parity.py::test_parallel_exact_sampler_matches_sequential) at ~1/10 of its time.
+constexpr uint32_t PS_THREADS = 1024, PS_E = 16;  // up to 16384 terms per round
+constexpr uint32_t PS_SAT = 1u << 26;  // increments at or above 2^24 only ever mean "left the binade"
+constexpr uint32_t PS_NONE = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ps_sat(uint32_t v) { return v < PS_SAT ? v : PS_SAT; }
+
+// x (>= 0) in units of 2^eu: integer part y and rounding class ct (0 down, 1 up, 2 tie)
+__device__ __forceinline__ void ps_step(float x, int eu, uint32_t& y, uint32_t& ct) {
+    const uint32_t b = __float_as_uint(x) & 0x7fffffffu;
+    const uint32_t ef = b >> 23;
+    const uint32_t m = ef ? ((b & 0x7fffffu) | 0x800000u) : b;
+    y = 0;
+    ct = 0;
+    if (m == 0) return;
+    const int d = eu - ((ef ? (int)ef : 1) - 150);  // x = m * 2^(ef - 150): shift that aligns it to the unit
+    if (d <= 0) {
+        y = (d < -2) ? PS_SAT : ps_sat(m << (-d));
+    } else if (d <= 24) {
+        const uint32_t half = 1u << (d - 1);
+        const uint32_t r = m & ((half << 1) - 1u);
+        y = (d == 24) ? 0u : (m >> d);
+        ct = r > half ? 1u : (r == half ? 2u : 0u);
+    }
+}
+
+__device__ __forceinline__ uint32_t ps_apply(uint32_t S, uint32_t y, uint32_t ct) {
+    return ps_sat(S + y + (ct == 2u ? ((S + y) & 1u) : ct));
+}
+
+struct PsMap {
+    uint32_t e, o;  // total increment for an even / odd start value
+};
+__device__ __forceinline__ PsMap ps_then(PsMap f, PsMap g) {  // g after f
+    PsMap h;
+    h.e = ps_sat(f.e + ((f.e & 1u) ? g.o : g.e));
+    h.o = ps_sat(f.o + (((1u + f.o) & 1u) ? g.o : g.e));
+    return h;
+}
+
+// Walks mind[from..n) with the sequential fp32 running sum (`from_sum` = the sum in front of `from`); returns the
+// first index whose running sum is >= target (PS_NONE if none) and leaves the final sum in *total.  Whole block,
+// 1024 threads.  With `ck`, the (position, sum) at the start of every round is recorded so that a second walk can
+// start next to its target instead of at 0.
+constexpr uint32_t PS_CKPTS = 512;
+struct PsCkpt {
+    uint32_t pos[PS_CKPTS];
+    float sum[PS_CKPTS];
+    uint32_t count;
+};
+
+__device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float target, float* total, uint32_t from,
+                            float from_sum, PsCkpt* ck) {
+    __shared__ float s_sum;
+    __shared__ uint32_t s_pos, s_found, s_cross, s_crossS, s_endS;
+    __shared__ PsMap s_warp[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) {
+        s_sum = from_sum;
+        s_pos = from;
+        if (ck) ck->count = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        const uint32_t pos = s_pos;
+        if (pos >= n) break;
+        const float sum = s_sum;
+        if (ck && tid == 0 && ck->count < PS_CKPTS) {
+            ck->pos[ck->count] = pos;
+            ck->sum[ck->count] = sum;
+            ++ck->count;
+        }
+        // elements per thread this round: right after leaving a binade the next exit is about `pos` elements away
+        // (the sum has to double), so early rounds do not need -- and would mostly waste -- the full span
+        const uint32_t E = min(PS_E, max(2u, (pos + PS_THREADS - 1) / PS_THREADS));
+        const uint32_t sb = __float_as_uint(sum), sef = (sb >> 23) & 0xffu;
+        const int eu = (sef ? (int)sef : 1) - 150;
+        const uint32_t S0 = sef ? ((sb & 0x7fffffu) | 0x800000u) : (sb & 0x7fffffu);
+        if (tid == 0) {
+            s_found = PS_NONE;
+            s_cross = PS_NONE;
+        }
+        uint32_t y[PS_E], ct[PS_E];
+        PsMap f{0u, 0u};
+        const uint32_t base = pos + tid * E;  // pos + 16384 cannot wrap: n < 2^31
+#pragma unroll
+        for (uint32_t j = 0; j < PS_E; ++j) {
+            if (j >= E) break;
+            const float x = (base + j < n) ? mind[base + j] : 0.f;
+            ps_step(x, eu, y[j], ct[j]);
+            const uint32_t ie = y[j] + (ct[j] == 2u ? ((f.e + y[j]) & 1u) : ct[j]);
+            const uint32_t io = y[j] + (ct[j] == 2u ? ((1u + f.o + y[j]) & 1u) : ct[j]);
+            f.e = ps_sat(f.e + ie);
+            f.o = ps_sat(f.o + io);
+        }
+        // block-wide exclusive scan of the maps
+        PsMap inc = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            PsMap other;
+            other.e = __shfl_up_sync(0xffffffffu, inc.e, o);
+            other.o = __shfl_up_sync(0xffffffffu, inc.o, o);
+            if ((int)lane >= o) inc = ps_then(other, inc);
+        }
+        if (lane == 31) s_warp[w] = inc;
+        PsMap ex;
+        ex.e = __shfl_up_sync(0xffffffffu, inc.e, 1);
+        ex.o = __shfl_up_sync(0xffffffffu, inc.o, 1);
+        if (lane == 0) ex = PsMap{0u, 0u};
+        __syncthreads();
+        if (w == 0) {
+            PsMap v = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                PsMap other;
+                other.e = __shfl_up_sync(0xffffffffu, v.e, o);
+                other.o = __shfl_up_sync(0xffffffffu, v.o, o);
+                if ((int)lane >= o) v = ps_then(other, v);
+            }
+            PsMap pv;
+            pv.e = __shfl_up_sync(0xffffffffu, v.e, 1);
+            pv.o = __shfl_up_sync(0xffffffffu, v.o, 1);
+            if (lane == 0) pv = PsMap{0u, 0u};
+            s_warp[lane] = pv;  // exclusive prefix over the warps
+        }
+        __syncthreads();
+        const PsMap pre = ps_then(s_warp[w], ex);
+        uint32_t S = ps_sat(S0 + ((S0 & 1u) ? pre.o : pre.e));
+        // walk my elements with the real start value: first target hit, first binade exit
+        uint32_t found = PS_NONE, cross = PS_NONE, crossS = 0;
+        if (S < (1u << 24)) {
+#pragma unroll
+            for (uint32_t j = 0; j < PS_E; ++j) {
+                if (j >= E) break;
+                if (found == PS_NONE && cross == PS_NONE && base + j < n) {
+                    const uint32_t Sn = ps_apply(S, y[j], ct[j]);
+                    if (Sn >= (1u << 24)) {
+                        cross = base + j;
+                        crossS = S;
+                    } else {
+                        S = Sn;
+                        if (ldexpf((float)Sn, eu) >= target) found = base + j;
+                    }
+                }
+            }
+        } else {
+            cross = base;  // an earlier thread has left the binade already: never the minimum
+        }
+        if (found != PS_NONE) atomicMin(&s_found, found);
+        if (cross != PS_NONE && base < n) atomicMin(&s_cross, cross);
+        __syncthreads();
+        if (cross != PS_NONE && cross == s_cross && S < (1u << 24)) s_crossS = crossS;
+        if (tid == PS_THREADS - 1) s_endS = S;
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t fnd = s_found, crs = s_cross;
+            if (fnd < crs) {  // reached the target before leaving the binade (fnd != NONE)
+                s_pos = 0xfffffffeu;
+                s_endS = fnd;
+            } else if (crs != PS_NONE) {
+                // the addition that leaves the binade, then a short sequential stretch, both with real fp32 adds
+                float sacc = __fadd_rn(ldexpf((float)s_crossS, eu), mind[crs]);
+                uint32_t at = crs, hit = PS_NONE;
+                if (sacc >= target) hit = at;
+                float nx[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) nx[t] = (crs + 1 + t < n) ? mind[crs + 1 + t] : 0.f;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    if (hit == PS_NONE && crs + 1 + t < n) {
+                        sacc = __fadd_rn(sacc, nx[t]);
+                        at = crs + 1 + t;
+                        if (sacc >= target) hit = at;
+                    }
+                }
+                if (hit != PS_NONE) {
+                    s_pos = 0xfffffffeu;
+                    s_endS = hit;
+                } else {
+                    s_sum = sacc;
+                    s_pos = at + 1;
+                }
+            } else {
+                s_sum = ldexpf((float)s_endS, eu);
+                s_pos = pos + PS_THREADS * E;
+            }
+        }
+        __syncthreads();
+        if (s_pos == 0xfffffffeu) {
+            const uint32_t r = s_endS;
+            __syncthreads();
+            return r;
+        }
+    }
+    if (tid == 0) *total = s_sum;
+    __syncthreads();
+    return PS_NONE;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) seed_sample_par_kernel(DevRng* g, const float* __restrict__ x, uint32_t n,
+                                                                     uint32_t ldx, uint32_t ld,
+                                                                     const float* __restrict__ mind,
+                                                                     float* __restrict__ centroids, uint32_t cidx,
+                                                                     uint32_t* picked) {
+    __shared__ float s_total, s_target, s_from_sum;
+    __shared__ uint32_t s_from;
+    __shared__ PsCkpt ck;
+    ps_walk(mind, n, INFINITY, &s_total, 0, 0.f, &ck);  // total_dist (ivf_flat_index.cpp:87)
+    if (threadIdx.x == 0) {
+        s_target = rng_real_0_b(g, s_total);
+        // running sums never decrease: the first row reaching the target lies at or behind the last recorded
+        // round start whose sum is still below it
+        uint32_t lo = 0;
+        for (uint32_t i = 1; i < ck.count; ++i)
+            if (ck.sum[i] < s_target) lo = i;
+        s_from = ck.pos[lo];
+        s_from_sum = ck.sum[lo];
+    }
+    __syncthreads();
+    float unused;
+    const uint32_t v = ps_walk(mind, n, s_target, &unused, s_from, s_from_sum, nullptr);
+    if (threadIdx.x == 0) picked[cidx] = v;
+    if (v == PS_NONE) return;  // no row reaches the target: the reference leaves the slot as it was
+    for (uint32_t d = threadIdx.x; d < ld; d += PS_THREADS) centroids[(size_t)cidx * ld + d] = x[(size_t)v * ldx + d];
+}
+
 // FAST-mode sampler: the same D^2 sampling (same RNG stream), but the total and the running sums are
 // accumulated in parallel (double precision, 1024 chunks) instead of one sequential fp32 chain, so the row
 // picked can differ from the reference's when the target falls within rounding distance of a boundary.
@@ -629,15 +865,18 @@ int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint
 }
 
 int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
-                      float* centroids, KMeansScratch& sc, bool exact, cudaStream_t stream) {
+                      float* centroids, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream) {
     seed_init_kernel<<<1, 256, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, centroids, sc.picked);
     fill_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(sc.mind, n, FLT_MAX);
     for (uint32_t c = 1; c < nlist; ++c) {
         seed_dist_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, ldx, dim, centroids + (size_t)(c - 1) * ld,
                                                                sc.mind);
-        if (exact)
+        if (sampler == SeedSampler::Sequential)
             seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, sc.ckpt, centroids, c,
                                                      sc.picked);
+        else if (sampler == SeedSampler::ExactParallel)
+            seed_sample_par_kernel<<<1, PS_THREADS, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
+                                                                 sc.picked);
         else
             seed_sample_fast_kernel<<<1, 1024, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
                                                             sc.picked);

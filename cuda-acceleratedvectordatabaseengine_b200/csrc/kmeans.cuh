@@ -48,9 +48,12 @@ bool assign_tensor_supported(uint32_t nc, uint32_t ld);
 int32_t kmeans_assign_tensor(const float* x, uint64_t n, uint32_t ldx, const float* c, uint32_t nc, uint32_t ldc,
                              uint32_t dim, int metric, uint32_t* assign, AssignTcScratch& sc, cudaStream_t stream);
 
-// exact = sequential fp32 sampling sums, bit-identical to the reference; otherwise parallel (FAST mode)
+// D^2 sampling sums: Sequential = the reference's fp32 chain on one lane (the literal restatement);
+// ExactParallel = the same sums bit for bit from a block-wide scan of parity-dependent integer maps (default);
+// Fast = double-precision partial sums (same RNG stream, a pick can differ within rounding distance)
+enum class SeedSampler { Fast = 0, ExactParallel = 1, Sequential = 2 };
 int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
-                      float* centroids, KMeansScratch& sc, bool exact, cudaStream_t stream);
+                      float* centroids, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream);
 int32_t kmeans_update_exact(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
                             uint32_t ld, float* centroids, KMeansScratch& sc, cudaStream_t stream);
 int32_t kmeans_cluster_sums(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,

@@ -435,6 +435,35 @@ def test_single_query_and_k1_and_nlist1():
         check_search(D, I, Dr, Ir)
 
 
+@pytest.mark.parametrize("case", ["gaussian768", "integer_ties", "subnormal", "duplicates", "tiny_n"])
+def test_parallel_exact_sampler_matches_sequential(case):
+    """AUTO evaluates the reference's sequential fp32 D^2-sampling sums with a block-wide scan of parity-dependent
+    integer maps (seed_sample_par_kernel); EXACT runs the literal one-lane chain.  One differing pick would change
+    every later centroid, so equal centroids == equal sums and picks, bit for bit."""
+    rng = np.random.default_rng(17)
+    if case == "gaussian768":
+        n, dim, nlist = 100_000, 768, 40
+        x = O.gaussian(91, n, dim)
+    elif case == "integer_ties":  # integer distances in the thousands: running sums beyond 2^24 round with exact ties
+        n, dim, nlist = 120_000, 64, 48
+        x = rng.integers(0, 16, (n, dim)).astype(np.float32)
+    elif case == "subnormal":  # squared distances around 1e-41: subnormal terms and sums
+        n, dim, nlist = 50_000, 16, 32
+        x = (rng.standard_normal((n, dim)) * 1e-21).astype(np.float32)
+    elif case == "duplicates":  # many zero terms, a few huge ones (binade jumps of many bits at once)
+        n, dim, nlist = 70_000, 8, 24
+        x = np.repeat(rng.standard_normal((700, dim)).astype(np.float32), 100, axis=0)
+        x[::997] *= 1e6
+    else:
+        n, dim, nlist = 37, 5, 9
+        x = O.gaussian(3, n, dim)
+    a = new_index(dim, nlist)  # AUTO
+    a.train(x)
+    b = new_index(dim, nlist, train_mode=pkg.TrainMode.EXACT)
+    b.train(x)
+    assert np.array_equal(a.centroids, b.centroids), f"max |diff| {np.abs(a.centroids - b.centroids).max()}"
+
+
 def test_fast_train_mode_is_statistically_equivalent():
     """FAST k-means++ sampling (parallel sums): same RNG stream, nearly always the same seeds; the clustering
     quality (inertia) must match the reference's within 1 %"""
