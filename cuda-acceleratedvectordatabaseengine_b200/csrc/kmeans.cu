@@ -12,6 +12,10 @@
 // libstdc++'s uniform distributions are restated on the device).
 #include "kmeans.cuh"
 
+#include <cooperative_groups.h>
+
+#include "tc_common.cuh"
+
 namespace vdb {
 namespace {
 
@@ -225,6 +229,80 @@ __global__ void __launch_bounds__(128) seed_dist_kernel(const float* __restrict_
     }
 }
 
+// The same update with the rows arriving by TMA: a block owns 128 rows, one producer thread streams their 128-byte
+// column blocks (2-D tensor map, 128-byte swizzle) through a 4-stage mbarrier ring, thread t adds up row t -- eight
+// LDS.128 per stage, conflict-free under the swizzle -- in the same ascending order.  The thread-per-row kernel
+// above stalls on its own load -> transpose -> add sequence (3.3 TB/s); this one keeps 64 KB per block in flight.
+constexpr int SD_ROWS = 128, SD_STAGES = 4;
+constexpr uint32_t SD_STAGE_BYTES = SD_ROWS * 128;
+constexpr uint32_t SD_SMEM = SD_STAGES * SD_STAGE_BYTES + 2048 * 4 + 2 * SD_STAGES * 8 + 1024;
+
+__global__ void __launch_bounds__(SD_ROWS + 32) seed_dist_tma_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                      uint32_t n, uint32_t ld,
+                                                                      const float* __restrict__ cnew,
+                                                                      float* __restrict__ mind) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t sd_raw[];
+    uint8_t* smem = sd_raw + ((1024u - (smem_u32(sd_raw) & 1023u)) & 1023u);
+    float* sc = reinterpret_cast<float*>(smem + SD_STAGES * SD_STAGE_BYTES);  // the new centroid, zero padded
+    uint64_t* full = reinterpret_cast<uint64_t*>(sc + 2048);
+    uint64_t* empty = full + SD_STAGES;
+    const uint32_t tid = threadIdx.x, num_kb = (ld + 31) / 32;
+    const uint32_t row0 = blockIdx.x * SD_ROWS;
+    for (uint32_t d = tid; d < num_kb * 32; d += SD_ROWS + 32) sc[d] = d < ld ? cnew[d] : 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < SD_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], SD_ROWS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == SD_ROWS) {  // producer
+        uint32_t s = 0, ph = 0;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], SD_STAGE_BYTES);
+            tma_load_2d(smem + s * SD_STAGE_BYTES, &map_x, (int32_t)(kb * 32), (int32_t)row0, &full[s]);
+            if (++s == SD_STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    } else if (tid < SD_ROWS) {
+        uint32_t s = 0, ph = 0;
+        float acc = 0.f;
+        const uint32_t swz = tid & 7u;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[s], ph);
+            const uint8_t* rowp = smem + s * SD_STAGE_BYTES + tid * 128;
+            const float4* c4 = reinterpret_cast<const float4*>(sc + kb * 32);
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ swz) << 4));
+                const float4 q = c4[c];
+                float diff;
+                diff = __fsub_rn(v.x, q.x); acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+                diff = __fsub_rn(v.y, q.y); acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+                diff = __fsub_rn(v.z, q.z); acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+                diff = __fsub_rn(v.w, q.w); acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+            if (++s == SD_STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+        const uint32_t v = row0 + tid;
+        if (v < n) {
+            const float m = mind[v];
+            mind[v] = acc < m ? acc : m;  // std::min(min_dist, dist)
+        }
+    }
+}
+
 constexpr uint32_t SEQ_CHUNK = 1024;
 
 // One warp: total = sequential fp32 sum of mind[] (ivf_flat_index.cpp:87),
@@ -369,40 +447,95 @@ __device__ __forceinline__ PsMap ps_then(PsMap f, PsMap g) {  // g after f
 }
 
 // Walks mind[from..n) with the sequential fp32 running sum (`from_sum` = the sum in front of `from`); returns the
-// first index whose running sum is >= target (PS_NONE if none) and leaves the final sum in *total.  Whole block,
-// 1024 threads.  With `ck`, the (position, sum) at the start of every round is recorded so that a second walk can
-// start next to its target instead of at 0.
+// first index whose running sum is >= target (PS_NONE if none) and leaves the final sum in *total.  Runs on a
+// cluster of PS_CTAS thread blocks (one round = up to PS_CTAS x 16384 terms): every block scans its slice, the block
+// maps and the per-block outcomes are exchanged through distributed shared memory (two cluster barriers per round,
+// buffers alternate by round parity), and every block then takes the same decision redundantly, so position and sum
+// stay identical in all of them without a broadcast.  With `ck`, the (position, sum) at the start of every round is
+// recorded so that a second walk can start next to its target instead of at 0.
+constexpr uint32_t PS_CTAS = 8;
+constexpr uint32_t PS_HEAD = 4096;
 constexpr uint32_t PS_CKPTS = 512;
 struct PsCkpt {
     uint32_t pos[PS_CKPTS];
     float sum[PS_CKPTS];
     uint32_t count;
 };
+struct PsShare {  // what a block shows to its cluster peers, per round parity
+    PsMap map;    // composition of all the block's terms
+    uint32_t found, cross, crossS, endS;
+};
 
 __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float target, float* total, uint32_t from,
                             float from_sum, PsCkpt* ck) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t crank = cluster.block_rank();
     __shared__ float s_sum;
-    __shared__ uint32_t s_pos, s_found, s_cross, s_crossS, s_endS;
+    __shared__ uint32_t s_pos, s_found, s_cross, s_crossS, s_endS, s_round;
     __shared__ PsMap s_warp[32];
+    __shared__ PsMap s_ctapre;
+    __shared__ PsShare s_share[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) {
         s_sum = from_sum;
         s_pos = from;
-        if (ck) ck->count = 0;
+        s_round = 0;
+        if (ck) {  // the walk's own start is the first checkpoint
+            ck->count = 1;
+            ck->pos[0] = from;
+            ck->sum[0] = from_sum;
+        }
+    }
+    if (from == 0) {
+        // The sum leaves a binade every few terms while it is small: the first PS_HEAD terms go through the plain
+        // one-lane chain (staged in shared memory, 4 cycles per add), every block redundantly.
+        __shared__ __align__(16) float s_head[PS_HEAD];
+        const uint32_t m = min(n, PS_HEAD);
+        for (uint32_t i = tid; i < PS_HEAD; i += PS_THREADS) s_head[i] = i < m ? mind[i] : 0.f;
+        __syncthreads();
+        if (tid == 0) {
+            float run = from_sum;
+            uint32_t hit = PS_NONE;
+            const float4* h4 = reinterpret_cast<const float4*>(s_head);
+            for (uint32_t i = 0; i < PS_HEAD / 4 && hit == PS_NONE; ++i) {
+                const float4 v = h4[i];
+                const float r0 = __fadd_rn(run, v.x), r1 = __fadd_rn(r0, v.y), r2 = __fadd_rn(r1, v.z),
+                            r3 = __fadd_rn(r2, v.w);
+                run = r3;
+                if (r3 >= target) {  // padding terms are zeros: a hit can only be at a real row or repeat one
+                    hit = 4 * i + (r0 >= target ? 0u : r1 >= target ? 1u : r2 >= target ? 2u : 3u);
+                }
+            }
+            if (hit != PS_NONE && hit < m) {
+                s_pos = 0xfffffffeu;
+                s_endS = hit;
+            } else {
+                s_sum = run;
+                s_pos = m;
+            }
+        }
+        __syncthreads();
+        if (s_pos == 0xfffffffeu) {
+            const uint32_t r = s_endS;
+            cluster.sync();
+            return r;
+        }
     }
     __syncthreads();
     for (;;) {
         const uint32_t pos = s_pos;
         if (pos >= n) break;
         const float sum = s_sum;
+        const uint32_t par = s_round & 1u;
         if (ck && tid == 0 && ck->count < PS_CKPTS) {
             ck->pos[ck->count] = pos;
             ck->sum[ck->count] = sum;
             ++ck->count;
         }
-        // elements per thread this round: right after leaving a binade the next exit is about `pos` elements away
-        // (the sum has to double), so early rounds do not need -- and would mostly waste -- the full span
-        const uint32_t E = min(PS_E, max(2u, (pos + PS_THREADS - 1) / PS_THREADS));
+        // terms per thread this round: right after leaving a binade the next exit is about `pos` terms away (the
+        // sum has to double), so early rounds do not need -- and would mostly waste -- the full span
+        const uint32_t E = min(PS_E, max(1u, (pos + PS_CTAS * PS_THREADS - 1) / (PS_CTAS * PS_THREADS)));
         const uint32_t sb = __float_as_uint(sum), sef = (sb >> 23) & 0xffu;
         const int eu = (sef ? (int)sef : 1) - 150;
         const uint32_t S0 = sef ? ((sb & 0x7fffffu) | 0x800000u) : (sb & 0x7fffffu);
@@ -412,7 +545,8 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
         }
         uint32_t y[PS_E], ct[PS_E];
         PsMap f{0u, 0u};
-        const uint32_t base = pos + tid * E;  // pos + 16384 cannot wrap: n < 2^31
+        // pos + 8 * 16384 cannot wrap: n < 2^31
+        const uint32_t cta_base = pos + crank * PS_THREADS * E, base = cta_base + tid * E;
 #pragma unroll
         for (uint32_t j = 0; j < PS_E; ++j) {
             if (j >= E) break;
@@ -423,7 +557,7 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
             f.e = ps_sat(f.e + ie);
             f.o = ps_sat(f.o + io);
         }
-        // block-wide exclusive scan of the maps
+        // block-wide scan of the maps
         PsMap inc = f;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -447,16 +581,23 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
                 other.o = __shfl_up_sync(0xffffffffu, v.o, o);
                 if ((int)lane >= o) v = ps_then(other, v);
             }
+            if (lane == 31) s_share[par].map = v;  // the whole block
             PsMap pv;
             pv.e = __shfl_up_sync(0xffffffffu, v.e, 1);
             pv.o = __shfl_up_sync(0xffffffffu, v.o, 1);
             if (lane == 0) pv = PsMap{0u, 0u};
             s_warp[lane] = pv;  // exclusive prefix over the warps
         }
+        cluster.sync();  // every block's map is visible
+        if (tid == 0) {
+            PsMap pre{0u, 0u};
+            for (uint32_t r = 0; r < crank; ++r) pre = ps_then(pre, cluster.map_shared_rank(&s_share[par], r)->map);
+            s_ctapre = pre;
+        }
         __syncthreads();
-        const PsMap pre = ps_then(s_warp[w], ex);
+        const PsMap pre = ps_then(s_ctapre, ps_then(s_warp[w], ex));
         uint32_t S = ps_sat(S0 + ((S0 & 1u) ? pre.o : pre.e));
-        // walk my elements with the real start value: first target hit, first binade exit
+        // walk my terms with the real start value: first target hit, first binade exit
         uint32_t found = PS_NONE, cross = PS_NONE, crossS = 0;
         if (S < (1u << 24)) {
 #pragma unroll
@@ -483,13 +624,29 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
         if (tid == PS_THREADS - 1) s_endS = S;
         __syncthreads();
         if (tid == 0) {
-            const uint32_t fnd = s_found, crs = s_cross;
+            s_share[par].found = s_found;
+            s_share[par].cross = s_cross;
+            s_share[par].crossS = s_crossS;
+            s_share[par].endS = s_endS;
+        }
+        cluster.sync();  // every block's outcome is visible
+        if (tid == 0) {
+            uint32_t fnd = PS_NONE, crs = PS_NONE, crsS = 0, endS = 0;
+            for (uint32_t r = 0; r < PS_CTAS; ++r) {
+                const PsShare* o = cluster.map_shared_rank(&s_share[par], r);
+                fnd = min(fnd, o->found);
+                if (o->cross < crs) {
+                    crs = o->cross;
+                    crsS = o->crossS;
+                }
+                if (r == PS_CTAS - 1) endS = o->endS;
+            }
             if (fnd < crs) {  // reached the target before leaving the binade (fnd != NONE)
                 s_pos = 0xfffffffeu;
                 s_endS = fnd;
             } else if (crs != PS_NONE) {
                 // the addition that leaves the binade, then a short sequential stretch, both with real fp32 adds
-                float sacc = __fadd_rn(ldexpf((float)s_crossS, eu), mind[crs]);
+                float sacc = __fadd_rn(ldexpf((float)crsS, eu), mind[crs]);
                 uint32_t at = crs, hit = PS_NONE;
                 if (sacc >= target) hit = at;
                 float nx[32];
@@ -511,44 +668,50 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
                     s_pos = at + 1;
                 }
             } else {
-                s_sum = ldexpf((float)s_endS, eu);
-                s_pos = pos + PS_THREADS * E;
+                s_sum = ldexpf((float)endS, eu);
+                s_pos = pos + PS_CTAS * PS_THREADS * E;
             }
+            ++s_round;
         }
         __syncthreads();
         if (s_pos == 0xfffffffeu) {
             const uint32_t r = s_endS;
-            __syncthreads();
+            cluster.sync();  // no block leaves (or starts another walk) while a peer may still read its outcome
             return r;
         }
     }
     if (tid == 0) *total = s_sum;
-    __syncthreads();
+    cluster.sync();
     return PS_NONE;
 }
 
-__global__ void __launch_bounds__(PS_THREADS) seed_sample_par_kernel(DevRng* g, const float* __restrict__ x, uint32_t n,
-                                                                     uint32_t ldx, uint32_t ld,
-                                                                     const float* __restrict__ mind,
-                                                                     float* __restrict__ centroids, uint32_t cidx,
-                                                                     uint32_t* picked) {
+__global__ void __cluster_dims__(PS_CTAS, 1, 1) __launch_bounds__(PS_THREADS)
+seed_sample_par_kernel(DevRng* g, const float* __restrict__ x, uint32_t n, uint32_t ldx, uint32_t ld,
+                       const float* __restrict__ mind, float* __restrict__ centroids, uint32_t cidx, uint32_t* picked) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ float s_total, s_target, s_from_sum;
     __shared__ uint32_t s_from;
     __shared__ PsCkpt ck;
     ps_walk(mind, n, INFINITY, &s_total, 0, 0.f, &ck);  // total_dist (ivf_flat_index.cpp:87)
+    // one draw from the generator (block 0), shown to the other blocks through distributed shared memory
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) s_target = rng_real_0_b(g, s_total);
+    cluster.sync();
     if (threadIdx.x == 0) {
-        s_target = rng_real_0_b(g, s_total);
+        const float target = *cluster.map_shared_rank(&s_target, 0);
         // running sums never decrease: the first row reaching the target lies at or behind the last recorded
         // round start whose sum is still below it
         uint32_t lo = 0;
         for (uint32_t i = 1; i < ck.count; ++i)
-            if (ck.sum[i] < s_target) lo = i;
+            if (ck.sum[i] < target) lo = i;
         s_from = ck.pos[lo];
         s_from_sum = ck.sum[lo];
+        s_total = target;  // (reused as this block's copy of the target)
     }
-    __syncthreads();
+    cluster.sync();  // block 0's s_target has been read by everyone before anything can overwrite it
     float unused;
-    const uint32_t v = ps_walk(mind, n, s_target, &unused, s_from, s_from_sum, nullptr);
+    const uint32_t v = ps_walk(mind, n, s_total, &unused, s_from, s_from_sum, nullptr);
+    if (cluster.block_rank() != 0) return;
     if (threadIdx.x == 0) picked[cidx] = v;
     if (v == PS_NONE) return;  // no row reaches the target: the reference leaves the slot as it was
     for (uint32_t d = threadIdx.x; d < ld; d += PS_THREADS) centroids[(size_t)cidx * ld + d] = x[(size_t)v * ldx + d];
@@ -868,14 +1031,31 @@ int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, ui
                       float* centroids, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream) {
     seed_init_kernel<<<1, 256, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, centroids, sc.picked);
     fill_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(sc.mind, n, FLT_MAX);
+    // rows by TMA when the driver offers tensor maps and the rows are 16-byte aligned (always, for staged rows)
+    CUtensorMap mx;
+    const bool tma = tc::encode_tiled() != nullptr && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ldx <= 2048 && ld == ldx;
+    if (tma) {
+        VDB_TRY(tc::make_map(&mx, x, n, ldx, ldx, SD_ROWS));
+        static bool conf[16] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 16 && !conf[dev]) {
+            VDB_CUDA_TRY(cudaFuncSetAttribute(seed_dist_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM));
+            conf[dev] = true;
+        }
+    }
     for (uint32_t c = 1; c < nlist; ++c) {
-        seed_dist_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, ldx, dim, centroids + (size_t)(c - 1) * ld,
-                                                               sc.mind);
+        if (tma)
+            seed_dist_tma_kernel<<<(n + SD_ROWS - 1) / SD_ROWS, SD_ROWS + 32, SD_SMEM, stream>>>(
+                mx, n, ldx, centroids + (size_t)(c - 1) * ld, sc.mind);
+        else
+            seed_dist_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, ldx, dim, centroids + (size_t)(c - 1) * ld,
+                                                                   sc.mind);
         if (sampler == SeedSampler::Sequential)
             seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, sc.ckpt, centroids, c,
                                                      sc.picked);
         else if (sampler == SeedSampler::ExactParallel)
-            seed_sample_par_kernel<<<1, PS_THREADS, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
+            seed_sample_par_kernel<<<PS_CTAS, PS_THREADS, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
                                                                  sc.picked);
         else
             seed_sample_fast_kernel<<<1, 1024, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
