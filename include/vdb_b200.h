@@ -43,12 +43,13 @@ typedef enum { VDB_METRIC_L2 = 0, VDB_METRIC_IP = 1, VDB_METRIC_COSINE = 2 } vdb
 
 /* Assignment and centroid update are always bit-identical to the reference
  * (the tensor-core assignment re-checks its survivors in reference order).
- * EXACT also keeps the scalar assignment kernel and the reference's sequential
- * fp32 sums in the k-means++ sampling (bit-identical seeds); FAST samples with
+ * AUTO (default) is bit-identical throughout: the reference's sequential fp32
+ * sums of the k-means++ sampling are evaluated exactly by a parallel scan
+ * (seed_sample_par_kernel), tensor-core assignment when nlist >= 256.
+ * EXACT = the literal restatement -- one-lane sequential sums, scalar
+ * assignment kernel -- kept as the checker for AUTO.  FAST samples with
  * parallel double-precision sums (same RNG stream, a pick can differ when the
- * target lies within rounding distance of a row boundary).  AUTO = exact
- * sampling while n_train * nlist <= 2^31, tensor-core assignment when
- * nlist >= 256. */
+ * target lies within rounding distance of a row boundary). */
 typedef enum { VDB_TRAIN_AUTO = 0, VDB_TRAIN_EXACT = 1, VDB_TRAIN_FAST = 2 } vdb_train_mode;
 
 /* How the query x centroid coarse distances are produced:

@@ -64,13 +64,23 @@ __global__ void __launch_bounds__(288, 1) tma_kernel(const char* __restrict__ x,
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
     const size_t bytes = 24ull << 30;
     char* x; float* out;
     cudaMalloc(&x, bytes); cudaMalloc(&out, 4);
     cudaMemset(x, 1, bytes);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms;
+    if (argc > 1) {  // "soak": stream for a few seconds so that nvidia-smi can sample clocks and power beside it
+        cudaFuncSetAttribute(tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const uint32_t stage = 49152, S = 4, chunk = 786432;
+        const int reps = 800;
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; ++r) tma_kernel<<<148, 288, (size_t)S * stage + 256>>>(x, bytes, stage, S, chunk, out);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+        printf("soak: TMA ring 48 KB x 4, %d x 24 GiB in %.1f ms: %.0f GB/s\n", reps, ms, (double)reps * (bytes / chunk * chunk) / ms / 1e6);
+        return 0;
+    }
     for (int blocks : {148 * 4, 148 * 8, 148 * 16}) {
         ldg_kernel<<<blocks, 512>>>((const float4*)x, bytes / 16, out);
         cudaEventRecord(e0);
