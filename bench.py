@@ -274,7 +274,15 @@ def run_b200(a):
         Dm = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
         Im = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
         sharded = importlib.import_module(PKG + ".sharded")
-        exch = sharded.PeerExchange(pkg, local, None, a.batch, a.k) if a.exchange == "p2p" else None
+        exch = None
+        if a.exchange == "p2p":
+            # peer mailboxes need CUDA IPC + peer access between all GPUs of the box; if any rank cannot map them,
+            # every rank takes the NCCL all-gather path (still all on the GPUs) and the config line says so
+            try:
+                exch = sharded.PeerExchange(pkg, local, None, a.batch, a.k)  # raises on every rank or on none
+            except RuntimeError as e:
+                print(f"rank {rank}: {e}; using NCCL all-gather", file=sys.stderr)
+                exch, a.exchange = None, "nccl"
 
     def exchange_merge():
         # every rank's local top-k -> all ranks, merged by (distance, id)

@@ -51,16 +51,33 @@ class PeerExchange:
         self.pkg, self.group = pkg, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.max_nq, self.max_k = max_nq, max_k
-        h = C.c_void_p()
-        pkg._check(pkg.lib().vdb_exchange_create(device, self.rank, self.world, max_nq, max_k, C.byref(h)))
-        self._h = h
-        mine = (C.c_uint8 * 64)()
-        pkg._check(pkg.lib().vdb_exchange_handle(self._h, mine))
+        # every rank runs every collective below whatever happens locally, so that a rank that cannot create or map
+        # a mailbox makes ALL ranks raise instead of leaving the others stuck in a collective
+        self._h, err, mine = None, None, None
+        try:
+            h = C.c_void_p()
+            pkg._check(pkg.lib().vdb_exchange_create(device, self.rank, self.world, max_nq, max_k, C.byref(h)))
+            self._h = h
+            blob = (C.c_uint8 * 64)()
+            pkg._check(pkg.lib().vdb_exchange_handle(self._h, blob))
+            mine = bytes(blob)
+        except Exception as e:  # noqa: BLE001
+            err = str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(mine), group=group)
-        buf = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
-        pkg._check(pkg.lib().vdb_exchange_connect(self._h, buf))
-        dist.barrier(group=group)  # every peer has mapped every mailbox before the first publish
+        dist.all_gather_object(handles, mine, group=group)
+        if err is None and all(x is not None for x in handles):
+            try:
+                buf = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+                pkg._check(pkg.lib().vdb_exchange_connect(self._h, buf))
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+        elif err is None:
+            err = "a peer could not create its mailbox"
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)  # also: every peer has mapped every mailbox
+        if not all(oks):
+            self.close()
+            raise RuntimeError("peer exchange unavailable: " + (err or "a peer could not map the mailboxes"))
 
     def merge_topk(self, D, I, stream=0):
         """local [nq][k] CUDA tensors -> merged ([nq][k] f32, [nq][k] i64); collective, same order on all ranks"""
@@ -103,10 +120,17 @@ class ShardedIVFFlatIndex:
         self.config = config
         # exchange: "p2p" (peer-memory kernel), "nccl" (all-gather + merge kernel), "auto" = p2p on an NCCL group
         # of more than one rank whose (world * max_k) fits the mailbox merge
-        if exchange == "auto":
+        auto = exchange == "auto"
+        if auto:
             exchange = "p2p" if (self.world > 1 and torch.cuda.is_available() and
                                  dist.get_backend(group) == "nccl" and self.world * max_k <= 4096) else "nccl"
-        self.exchange = PeerExchange(pkg, config.device, group, max_nq, max_k) if exchange == "p2p" else None
+        self.exchange = None
+        if exchange == "p2p":
+            try:
+                self.exchange = PeerExchange(pkg, config.device, group, max_nq, max_k)  # raises on all ranks or none
+            except RuntimeError:
+                if not auto:
+                    raise  # asked for explicitly: report it; "auto" falls back to the all-gather path
 
     def train(self, vectors):
         self.local.train(vectors)
