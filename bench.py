@@ -303,6 +303,16 @@ def run_b200(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if world > 1 and exch is not None:
+        # untimed self-check: the peer-memory exchange must reproduce the all-gather + merge-kernel result bit for bit
+        ix.search_async(q_all[0], a.nprobe, a.k, D, I, stream)
+        exch.merge_topk_into(D, I, Dm, Im, stream)
+        dist.all_gather_into_tensor(Dg, D)
+        dist.all_gather_into_tensor(Ig, I)
+        Dn, In = pkg.merge_topk(Dg, Ig, stream)
+        torch.cuda.synchronize()
+        if not (torch.equal(Dm, Dn) and torch.equal(Im, In)):
+            raise SystemExit(f"rank {rank}: peer-memory exchange and NCCL all-gather merge disagree")
     sampler = ClockSampler(local) if rank == 0 else None
     for s in range(a.warmup):
         step_device(s)
