@@ -48,6 +48,37 @@ inline void check(int32_t st, const char* what) {
 }
 }  // namespace detail
 
+namespace kernels {
+// The two launchers the reference's host object links against (engine/kernels.cu:13-43 and :80-92; the kernel seam of
+// SURVEY.md 8b), same names and argument order.  Host or device pointers; the reference's launchers return void and
+// leave errors to cudaGetLastError(), here a failure throws like every other call of this header.
+template <typename T>
+void launch_bruteforce_search(const T* database, const T* queries, const uint64_t* ids, uint64_t n_vectors,
+                              uint32_t n_queries, uint32_t dim, uint32_t k, float* out_distances,
+                              uint64_t* out_indices, Metric metric, cudaStream_t stream);
+template <>
+inline void launch_bruteforce_search<float>(const float* database, const float* queries, const uint64_t* ids,
+                                            uint64_t n_vectors, uint32_t n_queries, uint32_t dim, uint32_t k,
+                                            float* out_distances, uint64_t* out_indices, Metric metric,
+                                            cudaStream_t stream) {
+    detail::check(vdb_bruteforce_search(database, queries, ids, n_vectors, n_queries, dim, k, out_distances,
+                                        out_indices, static_cast<int32_t>(metric), stream),
+                  "launch_bruteforce_search");
+}
+// kernels.cuh:315-354 is L2-only; so is this launcher (IVFFlatIndex::add/train honour the index metric)
+template <typename T>
+void launch_kmeans_assign(const T* vectors, const T* centroids, uint32_t* assignments, float* distances,
+                          uint64_t n_vectors, uint32_t n_centroids, uint32_t dim, cudaStream_t stream);
+template <>
+inline void launch_kmeans_assign<float>(const float* vectors, const float* centroids, uint32_t* assignments,
+                                        float* distances, uint64_t n_vectors, uint32_t n_centroids, uint32_t dim,
+                                        cudaStream_t stream) {
+    detail::check(vdb_kmeans_assign(vectors, centroids, assignments, distances, n_vectors, n_centroids, dim,
+                                    VDB_METRIC_L2, stream),
+                  "launch_kmeans_assign");
+}
+}  // namespace kernels
+
 class TransferManager {
 public:
     struct Config {

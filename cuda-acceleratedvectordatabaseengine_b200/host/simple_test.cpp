@@ -55,6 +55,21 @@ int main() {
             threw = true;
         }
         ok = ok && threw;
+        // the kernel seam (engine/kernels.cu launchers): nprobe = nlist makes IVF exact, so it must agree with the
+        // brute-force launcher; every row's nearest centroid by the assign launcher must be a valid list
+        std::vector<float> Db((size_t)nq * k), De((size_t)nq * k);
+        std::vector<uint64_t> Ib((size_t)nq * k), Ie((size_t)nq * k);
+        kernels::launch_bruteforce_search<float>(db.data(), q.data(), ids.data(), n, nq, dim, k, Db.data(), Ib.data(),
+                                                 kernels::Metric::L2, nullptr);
+        sp.nprobe = nlist;
+        index.search(q.data(), nq, sp, De.data(), Ie.data());
+        for (uint32_t i = 0; i < nq * k; ++i) ok = ok && Ib[i] == Ie[i] && std::fabs(Db[i] - De[i]) <= 1e-5f * De[i];
+        std::vector<uint32_t> assign(n);
+        std::vector<float> cent((size_t)nlist * dim);
+        for (uint32_t c = 0; c < nlist; ++c)
+            for (uint32_t d = 0; d < dim; ++d) cent[(size_t)c * dim + d] = db[(size_t)(c * 7) * dim + d];
+        kernels::launch_kmeans_assign<float>(db.data(), cent.data(), assign.data(), nullptr, n, nlist, dim, nullptr);
+        for (uint32_t c = 0; c < nlist; ++c) ok = ok && assign[c * 7] == c;  // a row that IS a centroid picks it
         std::printf(ok ? "PASSED\n" : "FAILED\n");
         return ok ? 0 : 1;
     } catch (const std::exception& e) {
