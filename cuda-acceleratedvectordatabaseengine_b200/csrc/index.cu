@@ -119,6 +119,11 @@ struct vdb_index {
     DevBuf<uint64_t> ids_stage;
     ScanLaunchInfo last_scan_info{};
     bool have_search = false;
+    // the search workspace above is one per index: a search enqueued on another stream than the previous one first
+    // waits (on the device) for that one to finish
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
     AssignTcScratch tc_assign;
     // profiling: event quintuples (coarse start, then the four scan_search marks) per search
     bool profiling = false;
@@ -307,6 +312,19 @@ uint64_t slot_bound(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t ppi)
     return s * nq;
 }
 
+int32_t ws_acquire(vdb_index* ix, cudaStream_t stream) {
+    if (!ix->ws_event) VDB_CUDA_TRY(cudaEventCreateWithFlags(&ix->ws_event, cudaEventDisableTiming));
+    if (ix->ws_used && ix->ws_stream != stream) VDB_CUDA_TRY(cudaStreamWaitEvent(stream, ix->ws_event, 0));
+    return VDB_OK;
+}
+
+int32_t ws_release(vdb_index* ix, cudaStream_t stream) {
+    VDB_CUDA_TRY(cudaEventRecord(ix->ws_event, stream));
+    ix->ws_stream = stream;
+    ix->ws_used = true;
+    return VDB_OK;
+}
+
 // coarse: top-np centroids of every query = select_nprobe_lists (ivf_flat_index.cpp:298-336)
 int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t np, cudaStream_t stream) {
     const bool tensor = ix->cfg.coarse_mode == VDB_COARSE_TENSOR ||
@@ -340,6 +358,7 @@ int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t n
 int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t nq, uint32_t nprobe, uint32_t k,
                       float* out_d, uint64_t* out_i, cudaStream_t stream) {
     const uint32_t np = std::min(nprobe, ix->nlist);  // the reference reads past probe_lists instead (:221-222)
+    VDB_TRY(ws_acquire(ix, stream));
     cudaEvent_t* ev = nullptr;
     if (ix->profiling && (ix->prof_used + 1) * 5 <= ix->prof_events.size()) {
         ev = ix->prof_events.data() + (size_t)ix->prof_used * 5;
@@ -357,7 +376,7 @@ int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t
     VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,
                         true, out_d, out_i, nullptr, stream, &ix->last_scan_info, ev));
     ix->have_search = true;
-    return VDB_OK;
+    return ws_release(ix, stream);
 }
 
 int32_t check_index(vdb_index* ix) {
@@ -464,6 +483,7 @@ int32_t vdb_index_destroy(vdb_index* ix) {
         ix->ws_coarse.release();
         ix->ws_scan.release();
         for (auto e : ix->prof_events) cudaEventDestroy(e);
+        if (ix->ws_event) cudaEventDestroy(ix->ws_event);
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
     delete ix;
@@ -616,6 +636,7 @@ int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t s = (cudaStream_t)stream;
+    VDB_TRY(ws_acquire(ix, s));
     const float* q = queries_dev;
     if (ix->dim != ix->ld || ((uintptr_t)queries_dev & 15)) {
         VDB_TRY(ix->q_buf.reserve((size_t)nq * ix->ld));
@@ -634,6 +655,7 @@ int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint3
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     const float* q = nullptr;
+    VDB_TRY(ws_acquire(ix, ix->stream));
     VDB_TRY(stage_rows(ix, queries, nq, ix->q_buf, &q, ix->stream));
     const bool out_dev = is_device_ptr(distances);
     VDB_REQUIRE(out_dev == is_device_ptr(indices), "search: distances and indices must live on the same side");
@@ -661,6 +683,7 @@ int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq
     DeviceGuard g(ix->device);
     const uint32_t np = std::min(nprobe, ix->nlist);
     const float* q = nullptr;
+    VDB_TRY(ws_acquire(ix, ix->stream));
     VDB_TRY(stage_rows(ix, queries, nq, ix->q_buf, &q, ix->stream));
     VDB_TRY(coarse_select(ix, q, nq, np, ix->stream));
     VDB_CUDA_TRY(cudaMemcpyAsync(lists, ix->probes.p, (size_t)nq * np * 4,

@@ -126,7 +126,10 @@ int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64
 int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
                          float* distances, uint64_t* indices);
 /* Same, device pointers only, enqueued on `stream` (a cudaStream_t) without a
- * host synchronisation: the form the sharded path and the benchmark use. */
+ * host synchronisation: the form the sharded path and the benchmark use.  The
+ * index owns one search workspace: a search enqueued on a different stream than
+ * the previous one waits on the device for that one to finish (correct from any
+ * stream, but searches of one index do not overlap each other). */
 int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe,
                                uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
 /* select_nprobe_lists, ivf_flat_index.cpp:298-336: [nq][min(nprobe,nlist)] list ids. */

@@ -421,6 +421,32 @@ def test_concurrent_searches_from_host_threads():
     assert not errs, errs
 
 
+def test_async_searches_on_different_streams_do_not_share_a_workspace_in_time():
+    """search_async from alternating streams without any host synchronisation: the index orders the searches on
+    the device (one workspace), so every result must equal the single-stream answer"""
+    import torch
+    g, db, q, p = load_case("config1")
+    ix = new_index(p["dim"], p["nlist"], p["metric"])
+    ix.centroids = g["centroids"]
+    ix.add(db)
+    qd = torch.from_numpy(q).cuda()
+    nq, k = qd.shape[0], p["k"]
+    Dref, Iref = ix.search(qd, p["nprobe"], k)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    torch.cuda.synchronize()
+    for rep in range(12):
+        s = streams[rep % 3]
+        lo = (rep * 5) % (nq - 16)
+        D = torch.empty((16, k), dtype=torch.float32, device="cuda")
+        I = torch.empty((16, k), dtype=torch.int64, device="cuda")
+        ix.search_async(qd[lo:lo + 16], p["nprobe"], k, D, I, s.cuda_stream)
+        outs.append((lo, D, I))
+    torch.cuda.synchronize()
+    for lo, D, I in outs:
+        assert torch.equal(I, Iref[lo:lo + 16]) and torch.equal(D, Dref[lo:lo + 16])
+
+
 def test_single_query_and_k1_and_nlist1():
     x = O.gaussian(2, 3000, 20)
     ora = O.OracleIndex(20, 1)
