@@ -374,7 +374,92 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const Select
     if (p.cand_count && tid == 0) p.cand_count[q] = total_cand;
 }
 
+// nprobe beyond the select kernel's candidate pool (> 2047, e.g. exhaustive probing of 4096 lists): every centroid is
+// scored in exact fp32 (warp per centroid) and the whole table is sorted by (distance, list id) in shared memory.
+constexpr int WIDE_THREADS = 512;
+
+__global__ void __launch_bounds__(WIDE_THREADS) coarse_wide_kernel(const float* __restrict__ queries,
+                                                                   const float* __restrict__ centroids, uint32_t N,
+                                                                   uint32_t ld, uint32_t np, int metric,
+                                                                   uint32_t* __restrict__ probes,
+                                                                   float* __restrict__ out_d) {
+    extern __shared__ __align__(16) uint8_t wsm[];
+    const uint32_t n2 = dev_next_pow2(N);
+    float* sd = reinterpret_cast<float*>(wsm);          // [n2] distances
+    uint32_t* si = reinterpret_cast<uint32_t*>(sd + n2);  // [n2] list ids
+    float* sq = reinterpret_cast<float*>(si + n2);        // [ld] the query
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ld4 = ld >> 2;
+    for (uint32_t c = tid; c < ld4; c += WIDE_THREADS)
+        reinterpret_cast<float4*>(sq)[c] = reinterpret_cast<const float4*>(queries + (size_t)q * ld)[c];
+    for (uint32_t i = N + tid; i < n2; i += WIDE_THREADS) {
+        sd[i] = INFINITY;
+        si[i] = 0xffffffffu;
+    }
+    __syncthreads();
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    for (uint32_t c = warp; c < N; c += WIDE_THREADS / 32) {
+        const float4* c4 = reinterpret_cast<const float4*>(centroids + (size_t)c * ld);
+        float a = 0.f;
+        for (uint32_t j = lane; j < ld4; j += 32) {
+            const float4 x = c4[j], y = q4[j];
+            if (metric == VDB_METRIC_L2) {
+                float u;
+                u = y.x - x.x; a = fmaf(u, u, a);
+                u = y.y - x.y; a = fmaf(u, u, a);
+                u = y.z - x.z; a = fmaf(u, u, a);
+                u = y.w - x.w; a = fmaf(u, u, a);
+            } else {
+                a = fmaf(y.x, x.x, a); a = fmaf(y.y, x.y, a); a = fmaf(y.z, x.z, a); a = fmaf(y.w, x.w, a);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            sd[c] = metric == VDB_METRIC_L2 ? a : -a;
+            si[c] = c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= n2; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (n2 >> 1); t += WIDE_THREADS) {
+                const uint32_t i = ((t / stride) * (stride << 1)) + (t % stride), j = i + stride;
+                const float di = sd[i], dj = sd[j];
+                const uint32_t ii = si[i], ij = si[j];
+                const bool i_first = di < dj || (di == dj && ii < ij);
+                if (((i & size) == 0) ? !i_first : i_first) {
+                    sd[i] = dj; sd[j] = di;
+                    si[i] = ij; si[j] = ii;
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = tid; i < np; i += WIDE_THREADS) {
+        probes[(size_t)q * np + i] = si[i];
+        if (out_d) out_d[(size_t)q * np + i] = sd[i];
+    }
+}
+
 }  // namespace
+
+bool coarse_wide_supported(uint32_t N, uint32_t ld) {
+    return (size_t)next_pow2(N) * 8 + (size_t)ld * 4 <= 200 * 1024 && ld % 4 == 0;
+}
+
+int32_t coarse_select_wide(const float* queries, uint32_t nq, const float* centroids, uint32_t N, uint32_t ld,
+                           uint32_t np, int metric, uint32_t* probes, float* out_d, cudaStream_t stream) {
+    static bool conf[8] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && !conf[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(coarse_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        conf[dev] = true;
+    }
+    coarse_wide_kernel<<<nq, WIDE_THREADS, (size_t)next_pow2(N) * 8 + (size_t)ld * 4, stream>>>(
+        queries, centroids, N, ld, np, metric, probes, out_d);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
 
 size_t coarse_select_smem(uint32_t N) { return (size_t)((N + 1) & ~1u) * 4 + (size_t)SEL_CAND * 12; }
 

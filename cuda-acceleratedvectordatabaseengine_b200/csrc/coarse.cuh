@@ -18,4 +18,9 @@ int32_t coarse_select(const float* dots, uint32_t ldd, const float* queries, uin
                       const float* cnorm, const uint32_t* cmax_bits, uint32_t N, uint32_t ld, uint32_t np, int metric,
                       uint32_t* probes, float* out_d, uint32_t* cand_count, cudaStream_t stream);
 
+// nprobe beyond the select kernel's pool (> 2047): exact fp32 scores of every centroid + a full sort per query
+bool coarse_wide_supported(uint32_t N, uint32_t ld);
+int32_t coarse_select_wide(const float* queries, uint32_t nq, const float* centroids, uint32_t N, uint32_t ld,
+                           uint32_t np, int metric, uint32_t* probes, float* out_d, cudaStream_t stream);
+
 }  // namespace vdb

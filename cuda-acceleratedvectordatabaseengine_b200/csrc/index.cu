@@ -342,6 +342,13 @@ int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t n
         set_last_error("coarse_mode TENSOR requested but the tensor-core path does not support this shape/driver");
         return VDB_INVALID_ARGUMENT;
     }
+    if (np > (uint32_t)scan_max_k()) {  // wider than the top-k machinery of the other two modes
+        VDB_REQUIRE(coarse_wide_supported(ix->nlist, ix->ld), "nprobe > 2048 needs nlist <= 16384");
+        VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
+        VDB_TRY(ix->probes.reserve((size_t)nq * np));
+        return coarse_select_wide(q_dev, nq, ix->centroids.p, ix->nlist, ix->ld, np, ix->cfg.metric, ix->probes.p,
+                                  ix->coarse_d.p, stream);
+    }
     VDB_TRY(ix->zero_probes.reserve(nq));
     VDB_CUDA_TRY(cudaMemsetAsync(ix->zero_probes.p, 0, (size_t)nq * 4, stream));
     VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));

@@ -553,3 +553,60 @@ def test_every_row_width_instantiation(dim):
     Dr, Ir = ora.search(q, 3, k)
     D, I = ix.search(q, 3, k)
     check_search(D, I, Dr, Ir)
+
+
+def test_nprobe_beyond_the_topk_machinery():
+    """nprobe > 2048 (the select kernels' pool): full sort of the centroid table per query"""
+    dim, nlist, n, nq, k = 16, 3000, 30000, 9, 10
+    x = O.gaussian(55, n + nq, dim)
+    db, q = x[:n], x[n:]
+    cent = db[:nlist].copy()
+    ora = O.OracleIndex(dim, nlist)
+    ora.centroids = cent
+    ora.add(db)
+    ix = new_index(dim, nlist)
+    ix.centroids = cent
+    ix.add(db)
+    for nprobe in (2049, 2500, 3000, 5000):
+        Dr, Ir = ora.search(q, nprobe, k)
+        D, I = ix.search(q, nprobe, k)
+        check_search(D, I, Dr, Ir)
+        ref = np.stack([ora.select_nprobe(q[i], nprobe) for i in range(nq)])
+        check_probes(ix.select_nprobe(q, nprobe), ref, q, cent, 0)
+
+
+def test_full_size_config3_ivf_equals_bruteforce_and_is_monotone():
+    """BASELINE.json configs[2] at FULL size (10M x 768, nlist 4096) through size-independent properties: with
+    nprobe = nlist the IVF path (coarse + grouped list scan + merge over 34 GB of pages) must return exactly what
+    the independent tensor-core brute-force path returns on the same rows; fewer probes can only raise distances;
+    every id sits in the list its row was assigned to; the lists hold every row exactly once."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90 * 2**30:
+        pytest.skip("needs ~70 GB of HBM")
+    n, dim, nlist, nq, k = 10_000_000, 768, 4096, 32, 10
+    gen = torch.Generator(device="cuda").manual_seed(12345)
+    db = torch.empty((n, dim), dtype=torch.float32, device="cuda")
+    for lo in range(0, n, 1_000_000):
+        db[lo:lo + 1_000_000].normal_(generator=gen)
+    q = torch.randn(nq, dim, generator=gen, device="cuda")
+    ix = new_index(dim, nlist)
+    ix.train(db[:262144])
+    for lo in range(0, n, 1_000_000):
+        ix.add(db[lo:lo + 1_000_000], torch.arange(lo, lo + 1_000_000, dtype=torch.int64, device="cuda"))
+    sizes = ix.list_sizes().astype(np.int64)
+    assert int(sizes.sum()) == n and ix.get_total_vectors() == n
+    Dall, Iall = ix.search(q, nlist, k)            # exhaustive IVF
+    Db, Ib = pkg.bruteforce_search(db, q, k)       # tensor-core brute force over the flat copy
+    assert torch.equal(Iall, Ib)
+    assert torch.allclose(Dall, Db, rtol=1e-6, atol=0)
+    D32, I32 = ix.search(q, 32, k)                 # the headline setting: a subset of the candidates
+    assert (D32 >= Dall * (1 - 1e-6)).all()
+    recall = float((I32[:, :, None] == Iall[:, None, :]).any(-1).float().mean())
+    assert recall > 0.03, recall                   # pure noise has no cluster structure: low (~0.1), chance is 32/4096
+    # every returned id is a row of one of the probed lists, at the distance the flat copy gives
+    probes = torch.from_numpy(ix.select_nprobe(q.cpu().numpy(), 32).astype(np.int64)).cuda()
+    owner = ix.assign_device(db[I32.reshape(-1)]).long().reshape(nq, k)
+    assert (owner[:, :, None] == probes[:, None, :]).any(-1).all()
+    d_chk = ((db[I32.reshape(-1)].reshape(nq, k, dim) - q[:, None, :]) ** 2).sum(-1)
+    assert torch.allclose(d_chk, D32, rtol=1e-5)
