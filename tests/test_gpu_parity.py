@@ -555,6 +555,22 @@ def test_every_row_width_instantiation(dim):
     check_search(D, I, Dr, Ir)
 
 
+def test_large_query_batch_and_k():
+    """2000 queries x k = 100 in one call (many query tiles per list, large partial-result buffers)"""
+    dim, nlist, n, nq, k, nprobe = 48, 64, 40000, 2000, 100, 8
+    x = O.gaussian(71, n + nq, dim)
+    db, q = x[:n], x[n:]
+    ora = O.OracleIndex(dim, nlist)
+    ora.train(db[:4000])
+    ora.add(db)
+    ix = new_index(dim, nlist)
+    ix.centroids = ora.centroids
+    ix.add(db)
+    Dr, Ir = ora.search(q, nprobe, k, nthreads=8)
+    D, I = ix.search(q, nprobe, k)
+    check_search(D, I, Dr, Ir)
+
+
 def test_nprobe_beyond_the_topk_machinery():
     """nprobe > 2048 (the select kernels' pool): full sort of the centroid table per query"""
     dim, nlist, n, nq, k = 16, 3000, 30000, 9, 10
