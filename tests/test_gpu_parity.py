@@ -591,6 +591,35 @@ def test_nprobe_beyond_the_topk_machinery():
         check_probes(ix.select_nprobe(q, nprobe), ref, q, cent, 0)
 
 
+def test_full_size_config2_bruteforce_against_float64():
+    """BASELINE.json configs[1] at FULL size (1M x 768, 1024 queries, k = 100): every result row sorted by
+    (distance, id); 32 of the queries checked against a float64 evaluation of all 1M distances (ids equal except
+    ties inside the fp32 tolerance); the result does not depend on how the query batch is split (the tensor path
+    takes >= 16 queries, the scan path fewer)."""
+    import torch
+    n, dim, nq, k = 1_000_000, 768, 1024, 100
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    db = torch.randn(n, dim, generator=gen, device="cuda")
+    q = torch.randn(nq, dim, generator=gen, device="cuda")
+    D, I = pkg.bruteforce_search(db, q, k)
+    assert (D[:, 1:] >= D[:, :-1]).all() and (I >= 0).all() and (I < n).all()
+    same_d = D[:, 1:] == D[:, :-1]
+    assert (I[:, 1:][same_d] > I[:, :-1][same_d]).all()
+    sub = torch.arange(0, nq, 32, device="cuda")
+    q64, d64 = q[sub].double(), None
+    d64 = (q64 * q64).sum(1)[:, None] - 2.0 * q64 @ db.double().T
+    vn = torch.empty(n, dtype=torch.float64, device="cuda")
+    for lo in range(0, n, 100_000):
+        vn[lo:lo + 100_000] = (db[lo:lo + 100_000].double() ** 2).sum(1)
+    d64 += vn[None, :]
+    ref = d64.topk(k, dim=1, largest=False)
+    check_search(D[sub].cpu().numpy(), I[sub].cpu().numpy(), ref.values.float().cpu().numpy(),
+                 ref.indices.cpu().numpy().astype(np.uint64))
+    del d64, vn
+    D8, I8 = pkg.bruteforce_search(db, q[:8], k)   # < 16 queries: the exact scan kernel
+    check_search(D[:8].cpu().numpy(), I[:8].cpu().numpy(), D8.cpu().numpy(), I8.cpu().numpy())
+
+
 def test_full_size_config3_ivf_equals_bruteforce_and_is_monotone():
     """BASELINE.json configs[2] at FULL size (10M x 768, nlist 4096) through size-independent properties: with
     nprobe = nlist the IVF path (coarse + grouped list scan + merge over 34 GB of pages) must return exactly what
