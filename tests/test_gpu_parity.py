@@ -620,6 +620,26 @@ def test_full_size_config2_bruteforce_against_float64():
     check_search(D[:8].cpu().numpy(), I[:8].cpu().numpy(), D8.cpu().numpy(), I8.cpu().numpy())
 
 
+def test_full_size_config4_training_is_bit_identical_to_the_literal_restatement():
+    """BASELINE.json configs[4] training at FULL size (262 144 x 768 sample, nlist 16384): the production path
+    (parallel exact k-means++ sums, TMA distance update, tensor-core assignment with reference-order re-check) must
+    produce the same centroids, bit for bit, as train_mode = EXACT (one-lane sequential sums, scalar fp32 assignment
+    kernel) -- the configuration that is itself pinned to the reference on the golden cases."""
+    import torch
+    dim, nlist, n = 768, 16384, 262144
+    gen = torch.Generator(device="cuda").manual_seed(12345)
+    x = torch.randn(n, dim, generator=gen, device="cuda")
+    a = new_index(dim, nlist)
+    a.train(x)
+    b = new_index(dim, nlist, train_mode=pkg.TrainMode.EXACT)
+    b.train(x)
+    ca, cb = a.centroids, b.centroids
+    assert np.array_equal(ca, cb), f"{int((ca != cb).any(1).sum())} of {nlist} centroids differ"
+    # and add() on top: tensor-core assignment == scalar assignment on fresh rows
+    y = torch.randn(200_000, dim, generator=gen, device="cuda")
+    assert torch.equal(a.assign_device(y), b.assign_device(y))
+
+
 def test_full_size_config3_ivf_equals_bruteforce_and_is_monotone():
     """BASELINE.json configs[2] at FULL size (10M x 768, nlist 4096) through size-independent properties: with
     nprobe = nlist the IVF path (coarse + grouped list scan + merge over 34 GB of pages) must return exactly what
