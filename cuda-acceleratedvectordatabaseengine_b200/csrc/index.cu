@@ -8,6 +8,7 @@
 // page is the unit of scan work.  There is no host copy of the vectors and no
 // CPU fallback.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -375,9 +376,15 @@ int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t
     }
     VDB_TRY(coarse_select(ix, q_dev, nq, np, stream));
     // pages per scan item: longer runs of a list amortise the per-item costs (tile announcement, barriers,
-    // final selection, partial write-out) over up to ~3 MB, as long as every SM still gets >= ~16 items
-    uint32_t ppi = std::max<uint32_t>(1, std::min<uint32_t>(4, ix->pages_used / (NUM_SMS_B200 * 16u)));
+    // final selection, partial write-out, merge input) over up to ~3 MB.  Measured: 4 pages beat 1 and 2 even on a
+    // 1/8 shard of the headline index (scan 0.49 vs 0.50 / 0.56 ms) and 8 loses to the longer tail, so 4 it is
+    // whenever that still leaves a handful of items per SM
+    uint32_t ppi = std::max<uint32_t>(1, std::min<uint32_t>(4, ix->pages_used / (NUM_SMS_B200 * 4u)));
     if (ppi == 3) ppi = 2;
+    if (const char* e = std::getenv("VDB_SCAN_PPI")) {  // tuning knob: pages per scan item (1, 2, 4 or 8)
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) ppi = (uint32_t)v;
+    }
     while (slot_bound(ix, nq, np, ppi) * k * 12 > (1ull << 30)) ppi *= 2;
     const uint64_t slots = slot_bound(ix, nq, np, ppi);
     VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,
