@@ -630,33 +630,49 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
             s_share[par].endS = s_endS;
         }
         cluster.sync();  // every block's outcome is visible
-        if (tid == 0) {
+        if (w == 0) {
+            // lane r reads block r's outcome through distributed shared memory, a few shuffles combine them
             uint32_t fnd = PS_NONE, crs = PS_NONE, crsS = 0, endS = 0;
-            for (uint32_t r = 0; r < PS_CTAS; ++r) {
-                const PsShare* o = cluster.map_shared_rank(&s_share[par], r);
-                fnd = min(fnd, o->found);
-                if (o->cross < crs) {
-                    crs = o->cross;
-                    crsS = o->crossS;
-                }
-                if (r == PS_CTAS - 1) endS = o->endS;
+            if (lane < PS_CTAS) {
+                const PsShare* o = cluster.map_shared_rank(&s_share[par], lane);
+                fnd = o->found;
+                crs = o->cross;
+                crsS = o->crossS;
+                endS = o->endS;
             }
+            endS = __shfl_sync(0xffffffffu, endS, PS_CTAS - 1);
+#pragma unroll
+            for (int o = 1; o < (int)PS_CTAS; o <<= 1) {
+                fnd = min(fnd, __shfl_xor_sync(0xffffffffu, fnd, o));
+                const uint32_t oc = __shfl_xor_sync(0xffffffffu, crs, o), os = __shfl_xor_sync(0xffffffffu, crsS, o);
+                if (oc < crs) {  // crossing indices are distinct rows (or NONE): no tie to break
+                    crs = oc;
+                    crsS = os;
+                }
+            }
+            fnd = __shfl_sync(0xffffffffu, fnd, 0);
+            crs = __shfl_sync(0xffffffffu, crs, 0);
+            crsS = __shfl_sync(0xffffffffu, crsS, 0);
+            // the term that leaves the binade and the stretch behind it, fetched in one go by the warp
+            float xv = 0.f;
+            if (crs != PS_NONE && !(fnd < crs)) xv = (crs + lane < n) ? mind[crs + lane] : 0.f;
+            float nx[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) nx[t] = __shfl_sync(0xffffffffu, xv, t);
+          if (lane == 0) {
             if (fnd < crs) {  // reached the target before leaving the binade (fnd != NONE)
                 s_pos = 0xfffffffeu;
                 s_endS = fnd;
             } else if (crs != PS_NONE) {
                 // the addition that leaves the binade, then a short sequential stretch, both with real fp32 adds
-                float sacc = __fadd_rn(ldexpf((float)crsS, eu), mind[crs]);
+                float sacc = __fadd_rn(ldexpf((float)crsS, eu), nx[0]);
                 uint32_t at = crs, hit = PS_NONE;
                 if (sacc >= target) hit = at;
-                float nx[32];
 #pragma unroll
-                for (int t = 0; t < 32; ++t) nx[t] = (crs + 1 + t < n) ? mind[crs + 1 + t] : 0.f;
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    if (hit == PS_NONE && crs + 1 + t < n) {
+                for (int t = 1; t < 32; ++t) {
+                    if (hit == PS_NONE && crs + t < n) {
                         sacc = __fadd_rn(sacc, nx[t]);
-                        at = crs + 1 + t;
+                        at = crs + t;
                         if (sacc >= target) hit = at;
                     }
                 }
@@ -672,6 +688,7 @@ __device__ uint32_t ps_walk(const float* __restrict__ mind, uint32_t n, float ta
                 s_pos = pos + PS_CTAS * PS_THREADS * E;
             }
             ++s_round;
+          }
         }
         __syncthreads();
         if (s_pos == 0xfffffffeu) {
