@@ -26,7 +26,7 @@ namespace vdb {
 namespace {
 
 constexpr uint32_t EX_MAX_WORLD = 16;
-constexpr unsigned long long EX_TIMEOUT_NS = 5ull * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
+constexpr unsigned long long EX_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
 
 struct Mailbox {  // device pointers into ONE rank's mailbox allocation
     uint32_t* flags;  // [2][world][max_nq]

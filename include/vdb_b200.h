@@ -190,7 +190,7 @@ int32_t vdb_merge_topk(const float* dist_parts_dev, const uint64_t* id_parts_dev
  * two all-gathers plus vdb_merge_topk.  One process per GPU: create on every rank, pass the 64-byte handle of
  * every rank (rank order; e.g. from an all_gather of vdb_exchange_handle) to connect, then call merge_topk
  * collectively (same order and shapes on every rank).  world * max_k <= 4096.  A peer that never arrives makes
- * the call's results padded and the NEXT call return VDB_NCCL_ERROR (5 s timeout). */
+ * the call's results padded and the NEXT call return VDB_NCCL_ERROR (20 s timeout). */
 int32_t vdb_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint32_t max_nq, uint32_t max_k,
                             vdb_exchange** out);
 int32_t vdb_exchange_handle(vdb_exchange* ex, uint8_t* out64);
