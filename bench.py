@@ -48,8 +48,9 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ntrain", type=int, default=262144)
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: peer-memory exchange+merge kernel, or NCCL all-gathers + merge kernel")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-pipelined", "nccl"],
+                    help="N > 1: peer-memory exchange+merge kernel (optionally collected one batch later, after the "
+                         "next batch's scan is enqueued), or NCCL all-gathers + merge kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
     ap.add_argument("--dump-groups", action="store_true", help="stderr: probed-row work by queries-per-list")
@@ -275,7 +276,7 @@ def run_b200(a):
         Im = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
         sharded = importlib.import_module(PKG + ".sharded")
         exch = None
-        if a.exchange == "p2p":
+        if a.exchange.startswith("p2p"):
             # peer mailboxes need CUDA IPC + peer access between all GPUs of the box; if any rank cannot map them,
             # every rank takes the NCCL all-gather path (still all on the GPUs) and the config line says so
             try:
@@ -293,9 +294,25 @@ def run_b200(a):
         dist.all_gather_into_tensor(Ig, I)
         return pkg.merge_topk(Dg, Ig, stream)
 
+    pipelined = world > 1 and a.exchange == "p2p-pipelined"
+    in_flight = [False]
+
     def step_device(s):
         ix.search_async(q_all[s], a.nprobe, a.k, D, I, stream)
+        if pipelined and exch is not None:
+            # every step: scan of batch s, merged result of batch s-1, publish of batch s (one batch in flight;
+            # the publish copies D, I into the peers' mailboxes, so the local buffers are free again)
+            if in_flight[0]:
+                exch.collect_into(Dm, Im, stream)
+            exch.publish(D, I, stream)
+            in_flight[0] = True
+            return Dm, Im
         return exchange_merge() if world > 1 else (D, I)
+
+    def drain():
+        if in_flight[0]:
+            exch.collect_into(Dm, Im, stream)
+            in_flight[0] = False
 
     def sync_all():
         torch.cuda.synchronize()
@@ -351,6 +368,7 @@ def run_b200(a):
             Ih.copy_(Io, non_blocking=True)
             torch.cuda.synchronize()
 
+    drain()
     for s in range(min(a.warmup, 5)):
         step_e2e(s)
     sync_all()
@@ -399,7 +417,9 @@ def run_b200(a):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, " +
                    ("single GPU: no exchange" if world == 1 else
-                    "NVLink peer-memory exchange+merge kernel" if a.exchange == "p2p" else "NCCL all-gather + merge kernel"),
+                    "NVLink peer-memory exchange+merge kernel" if a.exchange == "p2p" else
+                    "NVLink peer-memory exchange, batch i collected after the scan of batch i+1 is enqueued"
+                    if a.exchange == "p2p-pipelined" else "NCCL all-gather + merge kernel"),
                    "cache": f"inputs larger than L2: each batch streams {uniq_bytes / 1e9:.2f} GB of distinct list data",
                    "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
@@ -416,7 +436,7 @@ def run_b200(a):
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
                 "d2h_bytes_per_step": a.batch * a.k * 12},
         # per step: score_gemm (tcgen05) + coarse_select + build_groups + scan + merge (+ the cross-rank merge)
-        "gpu_launches": a.steps * (5 + (1 if world > 1 else 0)),
+        "gpu_launches": a.steps * (5 + (2 if pipelined and exch is not None else 1 if world > 1 else 0)),
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

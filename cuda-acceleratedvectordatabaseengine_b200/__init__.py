@@ -98,6 +98,8 @@ ABI = {
     "vdb_exchange_handle": (_i32, [_vp, _vp]),
     "vdb_exchange_connect": (_i32, [_vp, _vp]),
     "vdb_exchange_merge_topk": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "vdb_exchange_publish": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "vdb_exchange_collect": (_i32, [_vp, _vp, _vp, _vp]),
     "vdb_exchange_destroy": (_i32, [_vp]),
     "vdb_arena_create": (_i32, [_i32, _u64, _u64, _i32, C.POINTER(_vp)]),
     "vdb_arena_destroy": (_i32, [_vp]),

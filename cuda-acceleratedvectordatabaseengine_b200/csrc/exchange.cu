@@ -13,6 +13,11 @@
 // through torch.distributed).  Flags carry a call counter that only grows, so nothing is ever reset; two mailbox
 // halves alternate by call parity, which is enough: a rank cannot publish call e + 2 before every peer has finished
 // reading call e, because its own call e + 1 had to wait for their publish of e + 1.
+// publish and collect can also be issued as two launches (vdb_exchange_publish / vdb_exchange_collect) with other
+// work of the same stream in between -- e.g. the next batch's scan -- so that by the time a rank collects, its peers
+// have long published and nobody waits for the slowest rank of a batch.  One batch may be in flight: collect(i) comes
+// before publish(i + 1) on every rank, which is what keeps two mailbox halves sufficient (a peer's publish(i + 1)
+// follows its collect(i), which needed my publish(i), which followed my collect(i - 1)).
 // The grid never exceeds the number of SMs and a CTA publishes ALL its queries before it waits for any, so every
 // rank's publishes are issued whatever the scheduling order -- no rank can wait on a CTA that is not resident.
 #include "common.cuh"
@@ -38,6 +43,7 @@ struct ExchangeParams {
     Mailbox box[EX_MAX_WORLD];  // box[r] = rank r's mailbox as mapped into this process
     uint32_t rank, world, max_nq, max_k;
     uint32_t nq, k, P, epoch;
+    uint32_t mode;  // 0 = publish + collect (one call), 1 = publish only, 2 = collect only
     const float* local_d;
     const uint64_t* local_i;
     float* out_d;
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Exc
     const size_t slot_stride = (size_t)p.max_nq * p.max_k;
 
     // ---- publish: my rows of every query this CTA owns -> slot [half][my rank] of every mailbox
-    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
+    for (uint32_t q = blockIdx.x; q < p.nq && p.mode != 2u; q += gridDim.x) {
         for (uint32_t e = tid; e < p.world * p.k; e += MERGE_THREADS) {
             const uint32_t r = e / p.k, j = e % p.k;
             const size_t dst = ((size_t)half * p.world + p.rank) * slot_stride + (size_t)q * p.k + j;
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Exc
     }
     // ---- collect + merge, from my own mailbox
     const Mailbox mine = p.box[p.rank];
-    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
+    for (uint32_t q = blockIdx.x; q < p.nq && p.mode != 1u; q += gridDim.x) {
         if (tid == 0) {
             cnt = 0;
             thr = INFINITY;
@@ -145,6 +151,8 @@ struct vdb_exchange {
     uint32_t* d_error = nullptr;
     uint32_t* h_error = nullptr;
     bool connected = false;
+    bool pending = false;  // a batch was published and not yet collected
+    uint32_t pending_nq = 0, pending_k = 0;
 };
 
 namespace {
@@ -231,14 +239,12 @@ int32_t vdb_exchange_connect(vdb_exchange* ex, const uint8_t* handles /* [world]
     return VDB_OK;
 }
 
-int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev,
-                                uint32_t nq, uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream) {
-    VDB_REQUIRE(ex && local_dist_dev && local_ids_dev && distances_dev && indices_dev, "exchange_merge: null buffer");
-    VDB_REQUIRE(ex->connected, "exchange_merge: vdb_exchange_connect has not been called");
-    VDB_REQUIRE(nq >= 1 && nq <= ex->max_nq && k >= 1 && k <= ex->max_k, "exchange_merge: nq or k above the mailbox size");
+static int32_t exchange_launch(vdb_exchange* ex, uint32_t mode, uint32_t epoch, const float* local_d,
+                               const uint64_t* local_i, uint32_t nq, uint32_t k, float* out_d, uint64_t* out_i,
+                               cudaStream_t s) {
     DevGuard g(ex->device);
     if (*ex->h_error) {
-        set_last_error("exchange_merge: an earlier call timed out waiting for a peer");
+        set_last_error("exchange: an earlier call timed out waiting for a peer");
         return VDB_NCCL_ERROR;
     }
     ExchangeParams p{};
@@ -251,8 +257,9 @@ int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, c
     p.rank = ex->rank; p.world = ex->world; p.max_nq = ex->max_nq; p.max_k = ex->max_k;
     p.nq = nq; p.k = k;
     p.P = next_pow2(2 * ex->world * k);  // pool never more than half full: the hashed duplicate screen applies
-    p.epoch = ++ex->epoch;
-    p.local_d = local_dist_dev; p.local_i = local_ids_dev; p.out_d = distances_dev; p.out_i = indices_dev;
+    p.epoch = epoch;
+    p.mode = mode;
+    p.local_d = local_d; p.local_i = local_i; p.out_d = out_d; p.out_i = out_i;
     p.error = ex->d_error;
     const uint32_t smem = p.P * 24;
     static bool conf[16] = {false};
@@ -262,10 +269,43 @@ int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, c
     }
     int sms = NUM_SMS_B200;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ex->device);
-    cudaStream_t s = (cudaStream_t)stream;
     exchange_merge_kernel<<<std::min<uint32_t>(nq, (uint32_t)sms), MERGE_THREADS, smem, s>>>(p);
     VDB_CUDA_TRY(cudaGetLastError());
-    VDB_CUDA_TRY(cudaMemcpyAsync(ex->h_error, ex->d_error, 4, cudaMemcpyDeviceToHost, s));  // seen by the NEXT call
+    if (mode != 1u)
+        VDB_CUDA_TRY(cudaMemcpyAsync(ex->h_error, ex->d_error, 4, cudaMemcpyDeviceToHost, s));  // seen by the NEXT call
+    return VDB_OK;
+}
+
+int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev,
+                                uint32_t nq, uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream) {
+    VDB_REQUIRE(ex && local_dist_dev && local_ids_dev && distances_dev && indices_dev, "exchange_merge: null buffer");
+    VDB_REQUIRE(ex->connected, "exchange_merge: vdb_exchange_connect has not been called");
+    VDB_REQUIRE(!ex->pending, "exchange_merge: a published batch is waiting for vdb_exchange_collect");
+    VDB_REQUIRE(nq >= 1 && nq <= ex->max_nq && k >= 1 && k <= ex->max_k, "exchange_merge: nq or k above the mailbox size");
+    return exchange_launch(ex, 0, ++ex->epoch, local_dist_dev, local_ids_dev, nq, k, distances_dev, indices_dev,
+                           (cudaStream_t)stream);
+}
+
+int32_t vdb_exchange_publish(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev, uint32_t nq,
+                             uint32_t k, void* stream) {
+    VDB_REQUIRE(ex && local_dist_dev && local_ids_dev, "exchange_publish: null buffer");
+    VDB_REQUIRE(ex->connected, "exchange_publish: vdb_exchange_connect has not been called");
+    VDB_REQUIRE(!ex->pending, "exchange_publish: collect the previous batch first (one batch in flight)");
+    VDB_REQUIRE(nq >= 1 && nq <= ex->max_nq && k >= 1 && k <= ex->max_k, "exchange_publish: nq or k above the mailbox size");
+    VDB_TRY(exchange_launch(ex, 1, ++ex->epoch, local_dist_dev, local_ids_dev, nq, k, nullptr, nullptr,
+                            (cudaStream_t)stream));
+    ex->pending = true;
+    ex->pending_nq = nq;
+    ex->pending_k = k;
+    return VDB_OK;
+}
+
+int32_t vdb_exchange_collect(vdb_exchange* ex, float* distances_dev, uint64_t* indices_dev, void* stream) {
+    VDB_REQUIRE(ex && distances_dev && indices_dev, "exchange_collect: null buffer");
+    VDB_REQUIRE(ex->pending, "exchange_collect: nothing was published");
+    VDB_TRY(exchange_launch(ex, 2, ex->epoch, nullptr, nullptr, ex->pending_nq, ex->pending_k, distances_dev,
+                            indices_dev, (cudaStream_t)stream));
+    ex->pending = false;
     return VDB_OK;
 }
 

@@ -92,6 +92,15 @@ class PeerExchange:
         self.pkg._check(self.pkg.lib().vdb_exchange_merge_topk(self._h, D.data_ptr(), I.data_ptr(), nq, k,
                                                                Do.data_ptr(), Io.data_ptr(), stream))
 
+    def publish(self, D, I, stream=0):
+        """first half of merge_topk: store this rank's local [nq][k] block into every peer's mailbox"""
+        nq, k = D.shape
+        self.pkg._check(self.pkg.lib().vdb_exchange_publish(self._h, D.data_ptr(), I.data_ptr(), nq, k, stream))
+
+    def collect_into(self, Do, Io, stream=0):
+        """second half: wait for the peers' blocks of the published batch and merge them into Do, Io"""
+        self.pkg._check(self.pkg.lib().vdb_exchange_collect(self._h, Do.data_ptr(), Io.data_ptr(), stream))
+
     def close(self):
         if getattr(self, "_h", None):
             self.pkg.lib().vdb_exchange_destroy(self._h)

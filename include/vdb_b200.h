@@ -197,6 +197,12 @@ int32_t vdb_exchange_handle(vdb_exchange* ex, uint8_t* out64);
 int32_t vdb_exchange_connect(vdb_exchange* ex, const uint8_t* handles);
 int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev,
                                 uint32_t nq, uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
+/* The same in two launches, so that other work of the stream (the next batch's scan) runs between them and nobody
+ * waits for the slowest rank of a batch: publish(i) ... collect(i) -> merged results of batch i.  One batch in
+ * flight: every rank calls collect(i) before publish(i + 1). */
+int32_t vdb_exchange_publish(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev, uint32_t nq,
+                             uint32_t k, void* stream);
+int32_t vdb_exchange_collect(vdb_exchange* ex, float* distances_dev, uint64_t* indices_dev, void* stream);
 int32_t vdb_exchange_destroy(vdb_exchange* ex);
 
 /* TransferManager rewrite (transfer_manager.h:42-88): one HBM slab and one

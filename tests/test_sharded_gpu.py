@@ -54,6 +54,29 @@ def _worker(rank, port, ret):
     D3, I3 = ix.search_device(qd[:7], nlist, 64)
     ix.exchange = ex
     assert torch.equal(D2, D3) and torch.equal(I2, I3)
+    # publish / collect as two launches with the next batch's search in between (one batch in flight)
+    ex = ix.exchange
+    st = torch.cuda.current_stream().cuda_stream
+    batches = [qd[lo:lo + 10] for lo in (0, 10, 20, 30)]
+    want = [ix.search_device(b, nprobe, k) for b in batches]
+    got, Dl, Il = [], [None, None], [None, None]
+    for i, b in enumerate(batches):
+        Dl[i & 1] = torch.empty((10, k), dtype=torch.float32, device="cuda")
+        Il[i & 1] = torch.empty((10, k), dtype=torch.int64, device="cuda")
+        ix.local.search_async(b, nprobe, k, Dl[i & 1], Il[i & 1], st)
+        if i:
+            Do = torch.empty((10, k), dtype=torch.float32, device="cuda")
+            Io = torch.empty((10, k), dtype=torch.int64, device="cuda")
+            ex.collect_into(Do, Io, st)
+            got.append((Do, Io))
+        ex.publish(Dl[i & 1], Il[i & 1], st)
+    Do = torch.empty((10, k), dtype=torch.float32, device="cuda")
+    Io = torch.empty((10, k), dtype=torch.int64, device="cuda")
+    ex.collect_into(Do, Io, st)
+    got.append((Do, Io))
+    torch.cuda.synchronize()
+    for (Dw, Iw), (Dg_, Ig_) in zip(want, got):
+        assert torch.equal(Dw, Dg_) and torch.equal(Iw, Ig_), "pipelined exchange differs from the one-launch form"
     sizes = ix.local.list_sizes()
     assert (sizes[owners != rank] == 0).all()
     tot = torch.tensor([int(sizes.sum())], device="cuda")
