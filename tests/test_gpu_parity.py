@@ -646,6 +646,7 @@ def test_full_size_config3_ivf_equals_bruteforce_and_is_monotone():
     the independent tensor-core brute-force path returns on the same rows; fewer probes can only raise distances;
     every id sits in the list its row was assigned to; the lists hold every row exactly once."""
     import torch
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 90 * 2**30:
         pytest.skip("needs ~70 GB of HBM")
