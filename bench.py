@@ -48,9 +48,13 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ntrain", type=int, default=262144)
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-pipelined", "nccl"],
-                    help="N > 1: peer-memory exchange+merge kernel (optionally collected one batch later, after the "
-                         "next batch's scan is enqueued), or NCCL all-gathers + merge kernel")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: peer-memory mailboxes written by the merge kernel + collect kernel, pipelined over "
+                         "batches (default), or the portable form: NCCL all-gathers + merge kernel per batch")
+    ap.add_argument("--depth", type=int, default=4, help="batches in flight (vdb_index_search_submit)")
+    ap.add_argument("--emulate-shards", type=int, default=1,
+                    help="tuning aid, 1 GPU: hold only shard 0 of W (what one rank of a W-GPU run scans), no exchange")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
     ap.add_argument("--dump-groups", action="store_true", help="stderr: probed-row work by queries-per-list")
@@ -226,27 +230,40 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
+        # NCCL's init lines (ranks, transports) go to stderr, not stdout: rank 0 prints exactly one JSON line there
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module(PKG)
     pkg.lib()
 
     # ---- build: synthetic N(0,1) rows generated on the device, trained + added by the CUDA path
     t_build = time.perf_counter()
+    shard_rank, shard_count = (0, a.emulate_shards) if a.emulate_shards > 1 and world == 1 else (rank, world)
     ix = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, metric=pkg.Metric.L2 if a.metric == "l2" else pkg.Metric.InnerProduct, device=local,
-                                     shard_rank=rank, shard_count=world))
+                                     shard_rank=shard_rank, shard_count=shard_count, pipeline_depth=a.depth))
     gen = torch.Generator(device=dev).manual_seed(12345)
     chunk = 1_000_000
     t_train = t_add = 0.0
+    # N > 1: rank 0 also holds an UNSHARDED index of the same rows (if it fits next to its shard) -- the untimed
+    # parity check below compares the sharded answer with it
+    ref = None
+    if world > 1 and rank == 0 and not a.no_parity_check and a.n * (a.dim * 4 + 8) * 1.2 < 120e9:
+        ref = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, device=local, metric=pkg.Metric.L2 if a.metric == "l2" else pkg.Metric.InnerProduct))
     for lo in range(0, a.n, chunk):
         x = torch.randn(min(chunk, a.n - lo), a.dim, generator=gen, device=dev)
         if lo == 0:
             t = time.perf_counter()
             ix.train(x[: min(a.ntrain, x.shape[0])])  # every rank trains on the same rows: identical centroids
             t_train = time.perf_counter() - t
+            if ref is not None:
+                ref.centroids = ix.centroids
         t = time.perf_counter()
         ix.add(x)  # ids = row numbers; a sharded index keeps only the lists it owns
         t_add += time.perf_counter() - t
+        if ref is not None:
+            ref.add(x)
         del x
     nb = a.warmup + a.steps
     q_all = torch.randn(nb, a.batch, a.dim, generator=gen, device=dev)
@@ -267,16 +284,15 @@ def run_b200(a):
                   f"pair-rows share {float((sizes[m] * g[m]).sum()) / tot:.3f}", file=sys.stderr)
 
     stream = torch.cuda.current_stream().cuda_stream
-    D = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
-    I = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
+    depth = a.depth
+    Dd = [torch.empty((a.batch, a.k), dtype=torch.float32, device=dev) for _ in range(depth)]
+    Id = [torch.empty((a.batch, a.k), dtype=torch.int64, device=dev) for _ in range(depth)]
+    exch = None
     if world > 1:
+        sharded = importlib.import_module(PKG + ".sharded")
         Dg = torch.empty((world, a.batch, a.k), dtype=torch.float32, device=dev)
         Ig = torch.empty((world, a.batch, a.k), dtype=torch.int64, device=dev)
-        Dm = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
-        Im = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
-        sharded = importlib.import_module(PKG + ".sharded")
-        exch = None
-        if a.exchange.startswith("p2p"):
+        if a.exchange == "p2p":
             # peer mailboxes need CUDA IPC + peer access between all GPUs of the box; if any rank cannot map them,
             # every rank takes the NCCL all-gather path (still all on the GPUs) and the config line says so
             try:
@@ -284,35 +300,8 @@ def run_b200(a):
             except RuntimeError as e:
                 print(f"rank {rank}: {e}; using NCCL all-gather", file=sys.stderr)
                 exch, a.exchange = None, "nccl"
-
-    def exchange_merge():
-        # every rank's local top-k -> all ranks, merged by (distance, id)
-        if exch is not None:  # one kernel per rank: peer-memory publish + wait + merge (csrc/exchange.cu)
-            exch.merge_topk_into(D, I, Dm, Im, stream)
-            return Dm, Im
-        dist.all_gather_into_tensor(Dg, D)
-        dist.all_gather_into_tensor(Ig, I)
-        return pkg.merge_topk(Dg, Ig, stream)
-
-    pipelined = world > 1 and a.exchange == "p2p-pipelined"
-    in_flight = [False]
-
-    def step_device(s):
-        ix.search_async(q_all[s], a.nprobe, a.k, D, I, stream)
-        if pipelined and exch is not None:
-            # every step: scan of batch s, merged result of batch s-1, publish of batch s (one batch in flight;
-            # the publish copies D, I into the peers' mailboxes, so the local buffers are free again)
-            if in_flight[0]:
-                exch.collect_into(Dm, Im, stream)
-            exch.publish(D, I, stream)
-            in_flight[0] = True
-            return Dm, Im
-        return exchange_merge() if world > 1 else (D, I)
-
-    def drain():
-        if in_flight[0]:
-            exch.collect_into(Dm, Im, stream)
-            in_flight[0] = False
+    ix.reserve_search(a.batch, a.nprobe, a.k)
+    pipelined = world == 1 or exch is not None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -320,27 +309,65 @@ def run_b200(a):
             dist.barrier()
             torch.cuda.synchronize()
 
-    if world > 1 and exch is not None:
-        # untimed self-check: the peer-memory exchange must reproduce the all-gather + merge-kernel result bit for bit
-        sync_all()  # ranks finish building at different times; the exchange kernel gives a peer 20 s to show up
-        ix.search_async(q_all[0], a.nprobe, a.k, D, I, stream)
-        exch.merge_topk_into(D, I, Dm, Im, stream)
+    def nccl_step(q, D, I):
+        # the portable form: local search, two all-gathers, merge kernel -- all on the current stream
+        ix.search_async(q, a.nprobe, a.k, D, I, stream)
         dist.all_gather_into_tensor(Dg, D)
         dist.all_gather_into_tensor(Ig, I)
-        Dn, In = pkg.merge_topk(Dg, Ig, stream)
+        return pkg.merge_topk(Dg, Ig, stream)
+
+    def run_device(first, count):
+        """`count` batches, device-resident queries and results, as many in flight as the index pipelines;
+        returns when the last one is ordered before the current stream"""
+        if not pipelined:
+            for s in range(first, first + count):
+                nccl_step(q_all[s], Dd[0], Id[0])
+            return
+        t = 0
+        for s in range(first, first + count):
+            t = ix.search_submit(q_all[s], a.nprobe, a.k, Dd[s % depth], Id[s % depth])
+        ix.search_wait_stream(t, stream)  # the back stream is in order: the last ticket covers them all
+
+    # ---- untimed checks: (1) N > 1: the sharded answer equals the answer of an UNSHARDED index of the same rows
+    # built on rank 0; (2) the peer-memory exchange reproduces the all-gather + merge-kernel result bit for bit
+    sync_all()
+    parity = None
+    if world > 1:
+        if exch is not None:
+            ix.attach_exchange(exch._h)
+        run_device(0, 1) if pipelined else None
+        Ds, Is = (Dd[0].clone(), Id[0].clone()) if pipelined else nccl_step(q_all[0], Dd[0], Id[0])
         torch.cuda.synchronize()
-        if not (torch.equal(Dm, Dn) and torch.equal(Im, In)):
-            raise SystemExit(f"rank {rank}: peer-memory exchange and NCCL all-gather merge disagree")
+        if exch is not None:
+            exch.check()
+            ix.attach_exchange(None)
+            Dn, In = nccl_step(q_all[0], Dd[1 % depth], Id[1 % depth])
+            torch.cuda.synchronize()
+            ix.attach_exchange(exch._h)
+            if not (torch.equal(Ds, Dn) and torch.equal(Is, In)):
+                raise SystemExit(f"rank {rank}: peer-memory exchange and NCCL all-gather merge disagree")
+        if rank == 0 and ref is not None:
+            Dr = torch.empty_like(Ds)
+            Ir = torch.empty_like(Is)
+            ref.search_async(q_all[0], a.nprobe, a.k, Dr, Ir, stream)
+            torch.cuda.synchronize()
+            same_ids = bool(torch.equal(Is, Ir))
+            same_d = bool(torch.equal(Ds, Dr))
+            parity = {"sharded_equals_unsharded": same_ids and same_d, "queries": a.batch,
+                      "checked_on": f"batch 0 against an unsharded {a.n}-row index on rank 0"}
+            if not (same_ids and same_d):
+                bad = int((Is != Ir).any(dim=1).sum())
+                raise SystemExit(f"rank 0: sharded search differs from the unsharded index on {bad} of {a.batch} queries")
+            ref.close()
+        sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
-    for s in range(a.warmup):
-        step_device(s)
+    run_device(0, a.warmup)
     sync_all()
     ix.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
-    for s in range(a.steps):
-        step_device(a.warmup + s)
+    run_device(a.warmup, a.steps)
     e1.record()
     sync_all()
     t1 = time.time()
@@ -350,31 +377,37 @@ def run_b200(a):
     ms = float(ms.item())
     prof = ix.read_profile()
     ix.set_profiling(False)
+    if exch is not None:
+        exch.check()
     qps = a.batch * a.steps / (ms / 1e3)
 
-    # ---- e2e: host buffers through the public call, copies inside the timed region
+    # ---- e2e: HOST buffers through the public call a serving thread makes (search_submit / search_wait on pinned
+    # memory: H2D of the queries and D2H of ids + distances inside the timed region, `depth` batches in flight)
     q_host = q_all.cpu().pin_memory()
-    Dh = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
-    Ih = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
+    Dh = [torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory() for _ in range(depth)]
+    Ih = [torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory() for _ in range(depth)]
 
-    def step_e2e(s):
-        if world == 1:
-            ix.search(q_host[s], a.nprobe, a.k, distances=Dh, indices=Ih)  # H2D + search + D2H + sync inside
-        else:
-            qd = q_host[s].to(dev, non_blocking=True)
-            ix.search_async(qd, a.nprobe, a.k, D, I, stream)
-            Do, Io = exchange_merge()
-            Dh.copy_(Do, non_blocking=True)
-            Ih.copy_(Io, non_blocking=True)
-            torch.cuda.synchronize()
+    def run_e2e(first, count):
+        if not pipelined:
+            for s in range(first, first + count):
+                qd = q_host[s].to(dev, non_blocking=True)
+                Do, Io = nccl_step(qd, Dd[0], Id[0])
+                Dh[0].copy_(Do, non_blocking=True)
+                Ih[0].copy_(Io, non_blocking=True)
+                torch.cuda.synchronize()
+            return
+        tickets = []
+        for s in range(first, first + count):
+            if len(tickets) >= depth:
+                ix.search_wait(tickets[len(tickets) - depth])  # the buffers of that batch are about to be reused
+            tickets.append(ix.search_submit(q_host[s], a.nprobe, a.k, Dh[s % depth], Ih[s % depth]))
+        for t in tickets[-depth:]:
+            ix.search_wait(t)
 
-    drain()
-    for s in range(min(a.warmup, 5)):
-        step_e2e(s)
+    run_e2e(0, min(a.warmup, 5))
     sync_all()
     te = time.perf_counter()
-    for s in range(a.steps):
-        step_e2e(a.warmup + s)
+    run_e2e(a.warmup, a.steps)
     sync_all()
     te = torch.tensor([time.perf_counter() - te], device=dev, dtype=torch.float64)
     if world > 1:
@@ -383,19 +416,29 @@ def run_b200(a):
     clocks = sampler.stop(t0, time.time()) if sampler else None
 
     # ---- byte accounting of the timed batches (untimed replay; stats come from the grouping kernel)
+    if exch is not None:
+        ix.attach_exchange(None)  # the replay is local: no collective needed for the byte counts
     alg_rows = uniq_rows = items = 0
+    scan_ctas = 0
     for s in range(a.steps):
-        ix.search_async(q_all[a.warmup + s], a.nprobe, a.k, D, I, stream)
+        ix.search_async(q_all[a.warmup + s], a.nprobe, a.k, Dd[0], Id[0], stream)
         ss = ix.last_search_stats()
         alg_rows += ss.algorithmic_rows
         uniq_rows += ss.unique_rows
         items += ss.scan_items
+    t = ix.search_submit(q_all[0], a.nprobe, a.k, Dd[0], Id[0])
+    ix.search_wait(t)
+    scan_ctas = int(ix.last_search_stats().scan_ctas)
     bpr = 4 * a.dim + 8
     peak, peak_src = measured_peak()
-    scan_ms = prof["scan_ms"] / max(prof["searches"], 1)
+    nsearch = max(prof["searches"], 1)
+    # kernel time: the scan streams' busy time per launch (first scan start .. last scan end over the timed
+    # region).  With batches in flight consecutive scan launches overlap (batch i+1's CTAs start on the SMs batch
+    # i's tail frees), so the per-launch event brackets (`kernel_ms_bracketed`) count the overlap twice.
+    scan_ms = (prof["scan_span_ms"] / nsearch) if (pipelined and prof["scan_span_ms"] > 0) else prof["scan_ms"] / nsearch
     alg_bytes = alg_rows * bpr / a.steps
     uniq_bytes = uniq_rows * bpr / a.steps
-    achieved = alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    achieved = uniq_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
 
     rank_scan_ms = None
     if world > 1:  # per-rank scan time and distinct bytes: shows how well the list ownership balances
@@ -411,32 +454,44 @@ def run_b200(a):
     if world == 1 and not a.no_cpu_baseline:
         r = reference_sample(a, steps=3, warmup=1, max_seconds=20.0)
         cpu = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    headline = (a.n, a.dim, a.metric, a.nlist, a.nprobe, a.k, a.batch) == (10_000_000, 768, "l2", 4096, 32, 10, 64)
+    launches_per_step = 5 + (1 if world > 1 else 0)
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, " +
+        "config": {"workload": workload_name(a) + (f" [shard 0 of {a.emulate_shards} only: tuning run]" if shard_count != world else ""),
+                   "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, " +
                    ("single GPU: no exchange" if world == 1 else
-                    "NVLink peer-memory exchange+merge kernel" if a.exchange == "p2p" else
-                    "NVLink peer-memory exchange, batch i collected after the scan of batch i+1 is enqueued"
-                    if a.exchange == "p2p-pipelined" else "NCCL all-gather + merge kernel"),
+                    "merge kernel stores into the peers' NVLink mailboxes + collect kernel, pipelined over batches"
+                    if exch is not None else "NCCL all-gather + merge kernel per batch"),
+                   "pipeline": (f"{depth} batches in flight: coarse/grouping of batch i+1 and merge/exchange of batch i-1 "
+                                f"overlap the scan of batch i ({scan_ctas} scan CTAs of 148 SMs)") if pipelined else "none",
                    "cache": f"inputs larger than L2: each batch streams {uniq_bytes / 1e9:.2f} GB of distinct list data",
                    "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
                    "index_gb": round(st.gpu_memory_bytes / 1e9, 2),
-                   **({"rank_scan_ms_and_unique_gb": rank_scan_ms} if rank_scan_ms else {})},
+                   **({"rank_scan_ms_and_unique_gb": rank_scan_ms} if rank_scan_ms else {}),
+                   **({"parity": parity} if parity else {})},
+        # frac = distinct probed bytes / scan time / peak: a list probed by several queries of the batch streams from
+        # HBM once.  `reuse` = algorithmic bytes (every query's probed rows) / distinct bytes.
         "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": profiled_traffic() if (headline and world == 1 and shard_count == 1) else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "unique_bytes_per_launch": uniq_bytes,
-                     "unique_frac": uniq_bytes / (scan_ms / 1e3) / 1e9 / peak if scan_ms > 0 else 0.0,
-                     "kernel_ms": scan_ms, "scan_items_per_launch": items / a.steps,
-                     "step_breakdown_ms": {k_: prof[k_] / max(prof["searches"], 1)
-                                           for k_ in ("coarse_ms", "group_ms", "scan_ms", "merge_ms")}},
+                     "reuse": alg_bytes / uniq_bytes if uniq_bytes else None,
+                     "algorithmic_gbs": alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0,
+                     "kernel_ms": scan_ms, "kernel_ms_bracketed": prof["scan_ms"] / nsearch,
+                     "scan_items_per_launch": items / a.steps, "scan_ctas": scan_ctas,
+                     "step_breakdown_ms": {k_: prof[k_] / nsearch
+                                           for k_ in ("coarse_ms", "group_ms", "scan_ms", "merge_ms", "collect_ms")}},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
                 "d2h_bytes_per_step": a.batch * a.k * 12},
-        # per step: score_gemm (tcgen05) + coarse_select + build_groups + scan + merge (+ the cross-rank merge)
-        "gpu_launches": a.steps * (5 + (2 if pipelined and exch is not None else 1 if world > 1 else 0)),
+        # per step: score_gemm (tcgen05) + coarse_select + build_groups + scan + merge (+ collect, or merge of the
+        # all-gathered parts)
+        "gpu_launches": a.steps * launches_per_step,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

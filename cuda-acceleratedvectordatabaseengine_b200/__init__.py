@@ -47,7 +47,7 @@ class _Config(C.Structure):
     _fields_ = [("dimension", C.c_uint32), ("nlist", C.c_uint32), ("metric", C.c_int32), ("device", C.c_int32),
                 ("max_gpu_memory", C.c_uint64), ("train_mode", C.c_int32), ("coarse_mode", C.c_int32),
                 ("page_rows", C.c_uint32), ("shard_rank", C.c_uint32), ("shard_count", C.c_uint32),
-                ("reserved", C.c_uint32 * 5)]
+                ("pipeline_depth", C.c_uint32), ("reserve_sms", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class _Stats(C.Structure):
@@ -59,7 +59,7 @@ class _Stats(C.Structure):
 
 class _SearchStats(C.Structure):
     _fields_ = [("algorithmic_rows", C.c_uint64), ("unique_rows", C.c_uint64), ("scan_items", C.c_uint64),
-                ("bytes_per_row", C.c_uint64)]
+                ("bytes_per_row", C.c_uint64), ("scan_ctas", C.c_uint64)]
 
 
 # every symbol include/vdb_b200.h declares: name -> (restype, argtypes)
@@ -76,6 +76,11 @@ ABI = {
     "vdb_index_add_assigned": (_i32, [_vp, _vp, _vp, _vp, _u64, _u64]),
     "vdb_index_search": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "vdb_index_search_async": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "vdb_index_search_submit": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, C.POINTER(_u64)]),
+    "vdb_index_search_wait": (_i32, [_vp, _u64]),
+    "vdb_index_search_wait_stream": (_i32, [_vp, _u64, _vp]),
+    "vdb_index_reserve_search": (_i32, [_vp, _u32, _u32, _u32]),
+    "vdb_index_attach_exchange": (_i32, [_vp, _vp]),
     "vdb_index_select_nprobe": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "vdb_index_assign": (_i32, [_vp, _vp, _u64, _vp]),
     "vdb_index_get_centroids": (_i32, [_vp, _vp]),
@@ -100,6 +105,9 @@ ABI = {
     "vdb_exchange_merge_topk": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "vdb_exchange_publish": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "vdb_exchange_collect": (_i32, [_vp, _vp, _vp, _vp]),
+    "vdb_exchange_connect_local": (_i32, [_vp, _u32, _u32]),
+    "vdb_exchange_status": (_i32, [_vp]),
+    "vdb_exchange_reset": (_i32, [_vp]),
     "vdb_exchange_destroy": (_i32, [_vp]),
     "vdb_arena_create": (_i32, [_i32, _u64, _u64, _i32, C.POINTER(_vp)]),
     "vdb_arena_destroy": (_i32, [_vp]),
@@ -186,6 +194,8 @@ class Config:
     page_rows: int = 0
     shard_rank: int = 0
     shard_count: int = 1
+    pipeline_depth: int = 0       # searches in flight (search_submit), 0 = 4
+    reserve_sms: int = 0          # SMs a pipelined scan leaves to the neighbouring batches' small kernels, 0 = 8
 
 
 @dataclass
@@ -206,6 +216,7 @@ class IVFFlatIndex:
         c.dimension, c.nlist, c.metric, c.device = config.dimension, config.nlist, int(config.metric), config.device
         c.max_gpu_memory, c.train_mode, c.coarse_mode = config.max_gpu_memory, int(config.train_mode), config.coarse_mode
         c.page_rows, c.shard_rank, c.shard_count = config.page_rows, config.shard_rank, config.shard_count
+        c.pipeline_depth, c.reserve_sms = config.pipeline_depth, config.reserve_sms
         self.config = config
         self._tm = tm  # borrowed, like the reference's TransferManager*
         self._h = _vp()
@@ -272,8 +283,48 @@ class IVFFlatIndex:
 
     def search_async(self, queries, nprobe, k, distances, indices, stream=0):
         """Device tensors only, enqueued on `stream` (int handle), no host sync."""
+        self._check_device_args(queries, distances, indices, k)
         _check(lib().vdb_index_search_async(self._h, _ptr(queries), queries.shape[0], nprobe, k, _ptr(distances),
                                             _ptr(indices), stream))
+
+    def _check_device_args(self, queries, distances, indices, k):
+        import torch
+        nq = queries.shape[0]
+        if not (queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous() and
+                queries.shape[-1] == self.config.dimension):
+            raise ValueError("queries must be a contiguous float32 CUDA tensor [nq][dimension]")
+        if not (distances.is_cuda and distances.dtype == torch.float32 and distances.is_contiguous() and
+                distances.numel() == nq * k):
+            raise ValueError("distances must be a contiguous float32 CUDA tensor [nq][k]")
+        if not (indices.is_cuda and indices.dtype in (torch.int64, torch.uint64) and indices.is_contiguous() and
+                indices.numel() == nq * k):
+            raise ValueError("indices must be a contiguous int64 CUDA tensor [nq][k]")
+
+    def search_submit(self, queries, nprobe, k, distances, indices):
+        """Pipelined search (vdb_index_search_submit): enqueue one batch on the index's own streams and return a
+        ticket; up to pipeline_depth batches overlap.  queries / outputs: float32 numpy arrays or torch tensors
+        (host, pinned or CUDA), kept alive and untouched by the caller until search_wait(ticket)."""
+        if isinstance(queries, np.ndarray):
+            assert queries.dtype == np.float32 and queries.flags.c_contiguous
+        nq = queries.shape[0]
+        t = _u64()
+        _check(lib().vdb_index_search_submit(self._h, _ptr(queries), nq, nprobe, k, _ptr(distances), _ptr(indices),
+                                             C.byref(t)))
+        return t.value
+
+    def search_wait(self, ticket):
+        _check(lib().vdb_index_search_wait(self._h, ticket))
+
+    def search_wait_stream(self, ticket, stream=0):
+        """make `stream` (int handle) wait for the ticket instead of the host"""
+        _check(lib().vdb_index_search_wait_stream(self._h, ticket, stream))
+
+    def reserve_search(self, max_nq, max_nprobe, max_k):
+        _check(lib().vdb_index_reserve_search(self._h, max_nq, max_nprobe, max_k))
+
+    def attach_exchange(self, exchange_handle):
+        """one process per GPU: searches become collective and return the merged result of all shards"""
+        _check(lib().vdb_index_attach_exchange(self._h, exchange_handle))
 
     def get_gpu_memory_usage(self):
         return self.stats().gpu_memory_bytes
@@ -306,11 +357,13 @@ class IVFFlatIndex:
         _check(lib().vdb_index_set_profiling(self._h, int(enable)))
 
     def read_profile(self):
-        """-> dict of summed ms (coarse, group, scan, merge) and the number of searches covered"""
-        ms = (C.c_float * 4)()
+        """-> dict of summed ms (coarse, group, scan, merge, collect), the scan streams' busy span, and the number
+        of searches covered"""
+        ms = (C.c_float * 8)()
         n = C.c_uint32()
         _check(lib().vdb_index_read_profile(self._h, ms, C.byref(n)))
-        return {"coarse_ms": ms[0], "group_ms": ms[1], "scan_ms": ms[2], "merge_ms": ms[3], "searches": n.value}
+        return {"coarse_ms": ms[0], "group_ms": ms[1], "scan_ms": ms[2], "merge_ms": ms[3], "collect_ms": ms[4],
+                "scan_span_ms": ms[5], "searches": n.value}
 
     @property
     def centroids(self):

@@ -21,6 +21,7 @@
 // The grid never exceeds the number of SMs and a CTA publishes ALL its queries before it waits for any, so every
 // rank's publishes are issued whatever the scheduling order -- no rank can wait on a CTA that is not resident.
 #include "common.cuh"
+#include "exchange.cuh"
 #include "topk.cuh"
 
 #include <cstring>
@@ -30,19 +31,11 @@
 namespace vdb {
 namespace {
 
-constexpr uint32_t EX_MAX_WORLD = 16;
 constexpr unsigned long long EX_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
 
-struct Mailbox {  // device pointers into ONE rank's mailbox allocation
-    uint32_t* flags;  // [2][world][max_nq]
-    float* dist;      // [2][world][max_nq * max_k]
-    uint64_t* ids;    // [2][world][max_nq * max_k]
-};
-
 struct ExchangeParams {
-    Mailbox box[EX_MAX_WORLD];  // box[r] = rank r's mailbox as mapped into this process
-    uint32_t rank, world, max_nq, max_k;
-    uint32_t nq, k, P, epoch;
+    PublishTarget pub;  // mailboxes, rank/world, epoch
+    uint32_t nq, k, P;
     uint32_t mode;  // 0 = publish + collect (one call), 1 = publish only, 2 = collect only
     const float* local_d;
     const uint64_t* local_i;
@@ -51,14 +44,6 @@ struct ExchangeParams {
     uint32_t* error;  // set to 1 when a wait timed out
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -76,24 +61,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Exc
     __shared__ uint32_t s_scan[MERGE_THREADS / 32 + 1];
     __shared__ uint32_t s_fail;
     const MergePool pool{pd, pi, &cnt, &thr};
-    const uint32_t tid = threadIdx.x, half = p.epoch & 1u;
-    const size_t slot_stride = (size_t)p.max_nq * p.max_k;
+    const uint32_t tid = threadIdx.x, half = p.pub.epoch & 1u, world = p.pub.world;
+    const size_t slot_stride = (size_t)p.pub.max_nq * p.pub.max_k;
 
-    // ---- publish: my rows of every query this CTA owns -> slot [half][my rank] of every mailbox
+    // ---- publish: my rows of every query this CTA owns -> slot [half][my rank] of every target mailbox
     for (uint32_t q = blockIdx.x; q < p.nq && p.mode != 2u; q += gridDim.x) {
-        for (uint32_t e = tid; e < p.world * p.k; e += MERGE_THREADS) {
-            const uint32_t r = e / p.k, j = e % p.k;
-            const size_t dst = ((size_t)half * p.world + p.rank) * slot_stride + (size_t)q * p.k + j;
-            p.box[r].dist[dst] = p.local_d[(size_t)q * p.k + j];
-            p.box[r].ids[dst] = p.local_i[(size_t)q * p.k + j];
-        }
-        __threadfence_system();
+        publish_query(p.pub, q, p.k, p.local_d + (size_t)q * p.k, p.local_i + (size_t)q * p.k, p.k, MERGE_THREADS);
         __syncthreads();
-        if (tid < p.world)
-            st_release_sys(&p.box[tid].flags[((size_t)half * p.world + p.rank) * p.max_nq + q], p.epoch);
     }
     // ---- collect + merge, from my own mailbox
-    const Mailbox mine = p.box[p.rank];
+    const Mailbox mine = p.pub.box[p.pub.rank];
     for (uint32_t q = blockIdx.x; q < p.nq && p.mode != 1u; q += gridDim.x) {
         if (tid == 0) {
             cnt = 0;
@@ -101,10 +78,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Exc
             s_fail = 0;
         }
         __syncthreads();
-        if (tid < p.world) {
-            const uint32_t* f = &mine.flags[((size_t)half * p.world + tid) * p.max_nq + q];
+        if (tid < world) {
+            const uint32_t* f = &mine.flags[((size_t)half * world + tid) * p.pub.max_nq + q];
             const unsigned long long t0 = global_ns();
-            while (ld_acquire_sys(f) != p.epoch) {
+            while (ld_acquire_sys(f) != p.pub.epoch) {
                 if (global_ns() - t0 > EX_TIMEOUT_NS) {
                     s_fail = 1;
                     break;
@@ -122,8 +99,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Exc
             __syncthreads();
             continue;
         }
-        for (uint32_t r = 0; r < p.world; ++r) {
-            const size_t src = ((size_t)half * p.world + r) * slot_stride + (size_t)q * p.k;
+        for (uint32_t r = 0; r < world; ++r) {
+            const size_t src = ((size_t)half * world + r) * slot_stride + (size_t)q * p.k;
             pool_push_block(pool, p.P, mine.dist + src, mine.ids + src, p.k);
         }
         pool_compact_block(pool, p.P, p.k, true, td, ti, s_scan);
@@ -147,12 +124,15 @@ struct vdb_exchange {
     void* local = nullptr;  // this rank's mailbox allocation
     size_t bytes = 0;
     std::vector<void*> peer_base;  // [world] (own entry = local)
-    std::vector<bool> opened;
+    std::vector<bool> opened;      // mapped through a CUDA IPC handle (to be closed)
     uint32_t* d_error = nullptr;
     uint32_t* h_error = nullptr;
     bool connected = false;
     bool pending = false;  // a batch was published and not yet collected
     uint32_t pending_nq = 0, pending_k = 0;
+    // publish only into rank `root`'s mailbox (single-process sharded index: the root device alone collects)
+    bool root_only = false;
+    uint32_t root = 0;
 };
 
 namespace {
@@ -172,7 +152,85 @@ struct DevGuard {
     ~DevGuard() { cudaSetDevice(prev); }
 };
 
+void fill_target(const vdb_exchange* ex, uint32_t epoch, PublishTarget* t) {
+    std::memset(t, 0, sizeof(*t));
+    for (uint32_t r = 0; r < ex->world; ++r) {
+        uint8_t* base = static_cast<uint8_t*>(ex->peer_base[r]);
+        if (!base) continue;  // root_only: peers other than the root are never addressed
+        t->box[r].flags = reinterpret_cast<uint32_t*>(base);
+        t->box[r].dist = reinterpret_cast<float*>(base + dist_off(ex));
+        t->box[r].ids = reinterpret_cast<uint64_t*>(base + ids_off(ex));
+    }
+    t->rank = ex->rank; t->world = ex->world; t->max_nq = ex->max_nq; t->max_k = ex->max_k;
+    t->epoch = epoch;
+    t->dst_lo = ex->root_only ? ex->root : 0;
+    t->dst_hi = ex->root_only ? ex->root + 1 : ex->world;
+    t->enabled = 1;
+}
+
+int32_t check_healthy(const vdb_exchange* ex) {
+    if (*ex->h_error) {
+        set_last_error("exchange: a call timed out waiting for a peer (vdb_exchange_reset clears the state)");
+        return VDB_NCCL_ERROR;
+    }
+    return VDB_OK;
+}
+
+int32_t exchange_launch(vdb_exchange* ex, uint32_t mode, uint32_t epoch, const float* local_d, const uint64_t* local_i,
+                        uint32_t nq, uint32_t k, float* out_d, uint64_t* out_i, cudaStream_t s) {
+    DevGuard g(ex->device);
+    ExchangeParams p{};
+    fill_target(ex, epoch, &p.pub);
+    p.nq = nq; p.k = k;
+    p.P = next_pow2(2 * ex->world * k);  // pool never more than half full: the hashed duplicate screen applies
+    p.mode = mode;
+    p.local_d = local_d; p.local_i = local_i; p.out_d = out_d; p.out_i = out_i;
+    p.error = ex->d_error;
+    const uint32_t smem = p.P * 24;
+    static bool conf[16] = {false};
+    if (ex->device < 16 && !conf[ex->device]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24));
+        conf[ex->device] = true;
+    }
+    int sms = NUM_SMS_B200;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ex->device);
+    // a collect-only launch just waits and merges 7.7 KB per rank: a few CTAs looping over the queries leave the
+    // SMs to the scans it overlaps with (and a waiting CTA never blocks a publish: those are separate launches)
+    const uint32_t grid = mode == 2u ? std::min<uint32_t>(nq, 16u) : std::min<uint32_t>(nq, (uint32_t)sms);
+    exchange_merge_kernel<<<grid, MERGE_THREADS, smem, s>>>(p);
+    VDB_CUDA_TRY(cudaGetLastError());
+    if (mode != 1u)  // the host sees a timeout after synchronising with `s` (vdb_exchange_status)
+        VDB_CUDA_TRY(cudaMemcpyAsync(ex->h_error, ex->d_error, 4, cudaMemcpyDeviceToHost, s));
+    return VDB_OK;
+}
+
 }  // namespace
+
+namespace vdb {
+
+int32_t exchange_begin_publish(vdb_exchange* ex, uint32_t nq, uint32_t k, PublishTarget* t) {
+    VDB_REQUIRE(ex && t, "exchange: null argument");
+    VDB_REQUIRE(ex->connected, "exchange: vdb_exchange_connect has not been called");
+    VDB_REQUIRE(!ex->pending, "exchange: collect the previous batch first (one batch in flight)");
+    VDB_REQUIRE(nq >= 1 && nq <= ex->max_nq && k >= 1 && k <= ex->max_k, "exchange: nq or k above the mailbox size");
+    VDB_TRY(check_healthy(ex));
+    fill_target(ex, ex->epoch + 1, t);
+    ++ex->epoch;  // the caller's launch is what publishes; a failed launch there is fatal for the index anyway
+    ex->pending = true;
+    ex->pending_nq = nq;
+    ex->pending_k = k;
+    return VDB_OK;
+}
+
+int32_t exchange_collect(vdb_exchange* ex, float* out_d, uint64_t* out_i, cudaStream_t s) {
+    VDB_REQUIRE(ex && out_d && out_i, "exchange_collect: null buffer");
+    VDB_REQUIRE(ex->pending, "exchange_collect: nothing was published");
+    VDB_TRY(exchange_launch(ex, 2, ex->epoch, nullptr, nullptr, ex->pending_nq, ex->pending_k, out_d, out_i, s));
+    ex->pending = false;
+    return VDB_OK;
+}
+
+}  // namespace vdb
 
 extern "C" {
 
@@ -205,6 +263,7 @@ int32_t vdb_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint3
     if ((e = cudaMalloc(&ex->d_error, 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMemset(ex->d_error, 0, 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMallocHost(&ex->h_error, 4)) != cudaSuccess) return fail(e);
+    *ex->h_error = 0;
     ex->peer_base.assign(world, nullptr);
     ex->opened.assign(world, false);
     ex->peer_base[rank] = ex->local;
@@ -239,40 +298,35 @@ int32_t vdb_exchange_connect(vdb_exchange* ex, const uint8_t* handles /* [world]
     return VDB_OK;
 }
 
-static int32_t exchange_launch(vdb_exchange* ex, uint32_t mode, uint32_t epoch, const float* local_d,
-                               const uint64_t* local_i, uint32_t nq, uint32_t k, float* out_d, uint64_t* out_i,
-                               cudaStream_t s) {
-    DevGuard g(ex->device);
-    if (*ex->h_error) {
-        set_last_error("exchange: an earlier call timed out waiting for a peer");
-        return VDB_NCCL_ERROR;
+int32_t vdb_exchange_connect_local(vdb_exchange** all, uint32_t world, uint32_t root) {
+    VDB_REQUIRE(all && world >= 1 && world <= EX_MAX_WORLD && root < world, "exchange_connect_local: bad arguments");
+    for (uint32_t r = 0; r < world; ++r)
+        VDB_REQUIRE(all[r] && all[r]->rank == r && all[r]->world == world && all[r]->max_nq == all[0]->max_nq &&
+                        all[r]->max_k == all[0]->max_k,
+                    "exchange_connect_local: exchanges must be given in rank order with equal shapes");
+    // same process: the root's mailbox is addressed directly once peer access is on (no IPC mapping); only the
+    // root collects, so every rank publishes into the root's mailbox alone
+    for (uint32_t r = 0; r < world; ++r) {
+        vdb_exchange* ex = all[r];
+        if (r != root && ex->device != all[root]->device) {
+            DevGuard g(ex->device);
+            int can = 0;
+            VDB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ex->device, all[root]->device));
+            if (!can) {
+                set_last_error("exchange_connect_local: no peer access between the shard devices");
+                return VDB_CUDA_ERROR;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[root]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) VDB_CUDA_TRY(e);
+            cudaGetLastError();
+        }
+        ex->peer_base.assign(world, nullptr);
+        ex->peer_base[r] = ex->local;
+        ex->peer_base[root] = all[root]->local;
+        ex->root_only = true;
+        ex->root = root;
+        ex->connected = true;
     }
-    ExchangeParams p{};
-    for (uint32_t r = 0; r < ex->world; ++r) {
-        uint8_t* base = static_cast<uint8_t*>(ex->peer_base[r]);
-        p.box[r].flags = reinterpret_cast<uint32_t*>(base);
-        p.box[r].dist = reinterpret_cast<float*>(base + dist_off(ex));
-        p.box[r].ids = reinterpret_cast<uint64_t*>(base + ids_off(ex));
-    }
-    p.rank = ex->rank; p.world = ex->world; p.max_nq = ex->max_nq; p.max_k = ex->max_k;
-    p.nq = nq; p.k = k;
-    p.P = next_pow2(2 * ex->world * k);  // pool never more than half full: the hashed duplicate screen applies
-    p.epoch = epoch;
-    p.mode = mode;
-    p.local_d = local_d; p.local_i = local_i; p.out_d = out_d; p.out_i = out_i;
-    p.error = ex->d_error;
-    const uint32_t smem = p.P * 24;
-    static bool conf[16] = {false};
-    if (ex->device < 16 && !conf[ex->device]) {
-        VDB_CUDA_TRY(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24));
-        conf[ex->device] = true;
-    }
-    int sms = NUM_SMS_B200;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ex->device);
-    exchange_merge_kernel<<<std::min<uint32_t>(nq, (uint32_t)sms), MERGE_THREADS, smem, s>>>(p);
-    VDB_CUDA_TRY(cudaGetLastError());
-    if (mode != 1u)
-        VDB_CUDA_TRY(cudaMemcpyAsync(ex->h_error, ex->d_error, 4, cudaMemcpyDeviceToHost, s));  // seen by the NEXT call
     return VDB_OK;
 }
 
@@ -280,10 +334,14 @@ int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, c
                                 uint32_t nq, uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream) {
     VDB_REQUIRE(ex && local_dist_dev && local_ids_dev && distances_dev && indices_dev, "exchange_merge: null buffer");
     VDB_REQUIRE(ex->connected, "exchange_merge: vdb_exchange_connect has not been called");
+    VDB_REQUIRE(!ex->root_only, "exchange_merge: a root-only exchange publishes and collects separately");
     VDB_REQUIRE(!ex->pending, "exchange_merge: a published batch is waiting for vdb_exchange_collect");
     VDB_REQUIRE(nq >= 1 && nq <= ex->max_nq && k >= 1 && k <= ex->max_k, "exchange_merge: nq or k above the mailbox size");
-    return exchange_launch(ex, 0, ++ex->epoch, local_dist_dev, local_ids_dev, nq, k, distances_dev, indices_dev,
-                           (cudaStream_t)stream);
+    VDB_TRY(check_healthy(ex));
+    VDB_TRY(exchange_launch(ex, 0, ex->epoch + 1, local_dist_dev, local_ids_dev, nq, k, distances_dev, indices_dev,
+                            (cudaStream_t)stream));
+    ++ex->epoch;  // only a launch that went out advances the call counter (the ranks' epochs must stay in step)
+    return VDB_OK;
 }
 
 int32_t vdb_exchange_publish(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev, uint32_t nq,
@@ -292,8 +350,10 @@ int32_t vdb_exchange_publish(vdb_exchange* ex, const float* local_dist_dev, cons
     VDB_REQUIRE(ex->connected, "exchange_publish: vdb_exchange_connect has not been called");
     VDB_REQUIRE(!ex->pending, "exchange_publish: collect the previous batch first (one batch in flight)");
     VDB_REQUIRE(nq >= 1 && nq <= ex->max_nq && k >= 1 && k <= ex->max_k, "exchange_publish: nq or k above the mailbox size");
-    VDB_TRY(exchange_launch(ex, 1, ++ex->epoch, local_dist_dev, local_ids_dev, nq, k, nullptr, nullptr,
+    VDB_TRY(check_healthy(ex));
+    VDB_TRY(exchange_launch(ex, 1, ex->epoch + 1, local_dist_dev, local_ids_dev, nq, k, nullptr, nullptr,
                             (cudaStream_t)stream));
+    ++ex->epoch;
     ex->pending = true;
     ex->pending_nq = nq;
     ex->pending_k = k;
@@ -301,10 +361,20 @@ int32_t vdb_exchange_publish(vdb_exchange* ex, const float* local_dist_dev, cons
 }
 
 int32_t vdb_exchange_collect(vdb_exchange* ex, float* distances_dev, uint64_t* indices_dev, void* stream) {
-    VDB_REQUIRE(ex && distances_dev && indices_dev, "exchange_collect: null buffer");
-    VDB_REQUIRE(ex->pending, "exchange_collect: nothing was published");
-    VDB_TRY(exchange_launch(ex, 2, ex->epoch, nullptr, nullptr, ex->pending_nq, ex->pending_k, distances_dev,
-                            indices_dev, (cudaStream_t)stream));
+    return exchange_collect(ex, distances_dev, indices_dev, (cudaStream_t)stream);
+}
+
+int32_t vdb_exchange_status(vdb_exchange* ex) {
+    VDB_REQUIRE(ex, "exchange_status: null handle");
+    return check_healthy(ex);
+}
+
+int32_t vdb_exchange_reset(vdb_exchange* ex) {
+    VDB_REQUIRE(ex, "exchange_reset: null handle");
+    DevGuard g(ex->device);
+    VDB_CUDA_TRY(cudaDeviceSynchronize());
+    VDB_CUDA_TRY(cudaMemset(ex->d_error, 0, 4));
+    *ex->h_error = 0;
     ex->pending = false;
     return VDB_OK;
 }

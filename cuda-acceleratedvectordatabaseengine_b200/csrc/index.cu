@@ -15,9 +15,13 @@
 #include <numeric>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "bruteforce_tc.cuh"
 #include "coarse.cuh"
 #include "common.cuh"
+#include "exchange.cuh"
+#include "index_internal.cuh"
 #include "kmeans.cuh"
 #include "scan.cuh"
 
@@ -25,12 +29,6 @@ namespace vdb {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
-
-namespace {
-
-constexpr uint64_t SLAB_BYTES = 64ull << 20;
-constexpr uint32_t CENTROID_PAGE_ROWS = 64;
-constexpr uint64_t ADD_CHUNK_BYTES = 1ull << 30;
 
 bool is_device_ptr(const void* p) {
     if (!p) return false;
@@ -42,103 +40,27 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    int32_t reserve(size_t n) {
-        if (n <= cap) return VDB_OK;
-        cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = n + n / 4 + 16;
-        VDB_CUDA_TRY(cudaMalloc(&p, want * sizeof(T)));
-        cap = want;
-        return VDB_OK;
+bool is_pinned_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
     }
-    void release() {
-        cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    size_t bytes() const { return cap * sizeof(T); }
-};
+    return a.type == cudaMemoryTypeHost;
+}
 
-struct DeviceGuard {
-    int prev = 0;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() { cudaSetDevice(prev); }
-};
+namespace {
+
+constexpr uint64_t SLAB_BYTES = 64ull << 20;
+constexpr uint32_t CENTROID_PAGE_ROWS = 64;
+constexpr uint64_t ADD_CHUNK_BYTES = 1ull << 30;
+constexpr uint64_t PARTIAL_BYTES_CAP = 1ull << 30;  // partial-result buffer of one search
 
 }  // namespace
 }  // namespace vdb
 
 using namespace vdb;
-
-struct vdb_index {
-    vdb_config cfg{};
-    uint32_t dim = 0, ld = 0, nlist = 0, page_rows = 0;
-    uint64_t page_bytes = 0, ids_off = 0;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool trained = false;
-    std::mutex mu;
-
-    DevBuf<float> centroids;  // [nlist][ld]
-    DevBuf<float> cnorm;      // [nlist] |c|^2 (tensor-core coarse path)
-    DevBuf<uint32_t> cmax_bits;
-    DevBuf<float> dots;       // [nq][nlist] q.c from the tensor cores
-    bool tensor_ok = false;
-    // flat paged view of the centroid table (the coarse step scans it like a list)
-    DevBuf<uint32_t> c_rows, c_page_off;
-    DevBuf<uint64_t> c_page_vec, c_page_ids;
-    uint32_t c_npages = 0;
-
-    // inverted lists: host mirror of the page chains + device tables
-    std::vector<uint32_t> h_rows;
-    std::vector<std::vector<uint32_t>> h_pages;
-    std::vector<void*> slabs;
-    std::vector<uint64_t> page_addr;
-    uint32_t pages_per_slab = 0, pages_used = 0;
-    DevBuf<uint32_t> d_rows, d_page_off;
-    DevBuf<uint64_t> d_page_vec, d_page_ids;
-    std::vector<uint32_t> npages_desc;  // page counts, descending (search slot bound)
-
-    uint64_t total_vectors = 0, local_vectors = 0, slab_bytes_total = 0;
-    // sharding: owner[l] = rank that holds list l (null on an unsharded index)
-    std::vector<uint8_t> h_owner;
-    DevBuf<uint8_t> d_owner;
-
-    ScanWorkspace ws_coarse, ws_scan;
-    DevBuf<float> q_buf, coarse_d, out_d;
-    DevBuf<uint64_t> coarse_i, out_i;
-    DevBuf<uint32_t> probes, zero_probes, assign_buf, hist_buf, fill_buf;
-    DevBuf<float> stage_buf;
-    DevBuf<uint64_t> ids_stage;
-    ScanLaunchInfo last_scan_info{};
-    bool have_search = false;
-    // the search workspace above is one per index: a search enqueued on another stream than the previous one first
-    // waits (on the device) for that one to finish
-    cudaEvent_t ws_event = nullptr;
-    cudaStream_t ws_stream = nullptr;
-    bool ws_used = false;
-    AssignTcScratch tc_assign;
-    // profiling: event quintuples (coarse start, then the four scan_search marks) per search
-    bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;
-    uint32_t prof_used = 0;
-
-    uint64_t hbm_bytes() const {
-        return slab_bytes_total + centroids.bytes() + cnorm.bytes() + dots.bytes() + c_rows.bytes() + c_page_off.bytes() + c_page_vec.bytes() +
-               c_page_ids.bytes() + d_rows.bytes() + d_page_off.bytes() + d_page_vec.bytes() + d_page_ids.bytes() +
-               ws_coarse.bytes + ws_scan.bytes + q_buf.bytes() + coarse_d.bytes() + out_d.bytes() +
-               coarse_i.bytes() + out_i.bytes() + probes.bytes() + zero_probes.bytes() + assign_buf.bytes() +
-               hist_buf.bytes() + fill_buf.bytes() + stage_buf.bytes() + ids_stage.bytes();
-    }
-};
 
 namespace {
 
@@ -199,13 +121,17 @@ int32_t build_flat_view(const float* base, uint64_t n, uint32_t ld, uint32_t pag
     return VDB_OK;
 }
 
-int32_t upload_owners(vdb_index* ix) {
+}  // namespace
+
+int32_t vdb::index_upload_owners(vdb_index* ix) {
     if (ix->cfg.shard_count <= 1) return VDB_OK;
     VDB_TRY(ix->d_owner.reserve(ix->nlist));
     VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_owner.p, ix->h_owner.data(), ix->nlist, cudaMemcpyHostToDevice, ix->stream));
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
     return VDB_OK;
 }
+
+namespace {
 
 // Greedy (largest first) byte balancing of the lists over the shards from per-list row counts: iid data
 // clusters very unevenly, so `l % world` can leave one GPU with far more to scan than another.
@@ -236,7 +162,14 @@ int32_t refresh_centroid_view(vdb_index* ix) {
                            ix->c_page_vec, ix->c_page_ids, &ix->c_npages, ix->stream);
 }
 
-int32_t alloc_page(vdb_index* ix, uint32_t* page) {
+}  // namespace
+
+int32_t vdb::index_refresh_centroids(vdb_index* ix) {
+    VDB_TRY(refresh_centroid_view(ix));
+    return refresh_centroid_aux(ix);
+}
+
+int32_t vdb::index_alloc_page(vdb_index* ix, uint32_t* page) {
     if (ix->pages_used == ix->page_addr.size()) {
         // slabs grow geometrically: 64 MiB first, doubling the resident total, capped at 2 GiB
         const uint64_t want = std::min<uint64_t>(2ull << 30, std::max<uint64_t>(SLAB_BYTES, ix->slab_bytes_total));
@@ -257,7 +190,7 @@ int32_t alloc_page(vdb_index* ix, uint32_t* page) {
     return VDB_OK;
 }
 
-int32_t upload_list_tables(vdb_index* ix) {
+int32_t vdb::index_upload_list_tables(vdb_index* ix) {
     const uint32_t nlist = ix->nlist;
     std::vector<uint32_t> off(nlist + 1, 0);
     for (uint32_t l = 0; l < nlist; ++l) off[l + 1] = off[l] + (uint32_t)ix->h_pages[l].size();
@@ -283,6 +216,8 @@ int32_t upload_list_tables(vdb_index* ix) {
     std::sort(ix->npages_desc.begin(), ix->npages_desc.end(), std::greater<uint32_t>());
     return VDB_OK;
 }
+
+namespace {
 
 // rows [n][dim] at `src` (host or device) -> device [n][ld], zero padded; returns the device pointer
 // (src itself when it already is a device array with dim == ld)
@@ -313,31 +248,37 @@ uint64_t slot_bound(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t ppi)
     return s * nq;
 }
 
-int32_t ws_acquire(vdb_index* ix, cudaStream_t stream) {
-    if (!ix->ws_event) VDB_CUDA_TRY(cudaEventCreateWithFlags(&ix->ws_event, cudaEventDisableTiming));
-    if (ix->ws_used && ix->ws_stream != stream) VDB_CUDA_TRY(cudaStreamWaitEvent(stream, ix->ws_event, 0));
-    return VDB_OK;
+// pages per scan item and the number of queries one pass may take so that the partial-result buffer
+// (slots x k x 12 bytes) stays under PARTIAL_BYTES_CAP.  Longer runs of a list amortise the per-item costs (tile
+// announcement, barriers, final selection, partial write-out, merge input) over up to ~3 MB.  Measured: 4 pages
+// beat 1 and 2 even on a 1/8 shard of the headline index and 8 loses to the longer tail, so 4 it is whenever that
+// still leaves a handful of items per SM.  Widening stops at the longest list (beyond it the bound no longer
+// falls: every non-empty probed list keeps one range); what still does not fit is split over query chunks.
+void choose_ppi(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t k, uint32_t* ppi_out, uint32_t* nq_chunk) {
+    uint32_t ppi = std::max<uint32_t>(1, std::min<uint32_t>(4, ix->pages_used / (NUM_SMS_B200 * 4u)));
+    if (ppi == 3) ppi = 2;
+    if (ix->ppi_override) ppi = ix->ppi_override;
+    const uint32_t longest = ix->npages_desc.empty() ? 1u : std::max(1u, ix->npages_desc[0]);
+    while (slot_bound(ix, nq, np, ppi) * k * 12 > PARTIAL_BYTES_CAP && ppi < longest) ppi *= 2;
+    const uint64_t per_query = std::max<uint64_t>(1, slot_bound(ix, 1, np, ppi)) * k * 12;
+    const uint64_t fit = std::max<uint64_t>(1, PARTIAL_BYTES_CAP / per_query);
+    *ppi_out = ppi;
+    *nq_chunk = (uint32_t)std::min<uint64_t>(nq, fit);
 }
 
-int32_t ws_release(vdb_index* ix, cudaStream_t stream) {
-    VDB_CUDA_TRY(cudaEventRecord(ix->ws_event, stream));
-    ix->ws_stream = stream;
-    ix->ws_used = true;
-    return VDB_OK;
-}
-
-// coarse: top-np centroids of every query = select_nprobe_lists (ivf_flat_index.cpp:298-336)
-int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t np, cudaStream_t stream) {
+// coarse: top-np centroids of every query = select_nprobe_lists (ivf_flat_index.cpp:298-336) -> s.probes
+int32_t slot_coarse_select(vdb_index* ix, SearchSlot& s, const float* q_dev, uint32_t nq, uint32_t np,
+                      cudaStream_t stream) {
     const bool tensor = ix->cfg.coarse_mode == VDB_COARSE_TENSOR ||
                         (ix->cfg.coarse_mode == VDB_COARSE_AUTO && ix->nlist >= 256);
+    VDB_TRY(s.coarse_d.reserve((size_t)nq * np));
+    VDB_TRY(s.probes.reserve((size_t)nq * np));
     if (tensor && coarse_tensor_supported(ix->nlist, ix->ld, np)) {
         const uint32_t ldd = round_up(ix->nlist, 4);
-        VDB_TRY(ix->dots.reserve((size_t)nq * ldd));
-        VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
-        VDB_TRY(ix->probes.reserve((size_t)nq * np));
-        VDB_TRY(score_gemm(q_dev, nq, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->ld, ix->dots.p, ldd, stream));
-        return vdb::coarse_select(ix->dots.p, ldd, q_dev, nq, ix->centroids.p, ix->cnorm.p, ix->cmax_bits.p, ix->nlist,
-                                  ix->ld, np, ix->cfg.metric, ix->probes.p, ix->coarse_d.p, nullptr, stream);
+        VDB_TRY(s.dots.reserve((size_t)nq * ldd));
+        VDB_TRY(score_gemm(q_dev, nq, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->ld, s.dots.p, ldd, stream));
+        return vdb::coarse_select(s.dots.p, ldd, q_dev, nq, ix->centroids.p, ix->cnorm.p, ix->cmax_bits.p, ix->nlist,
+                                  ix->ld, np, ix->cfg.metric, s.probes.p, s.coarse_d.p, nullptr, stream);
     }
     if (ix->cfg.coarse_mode == VDB_COARSE_TENSOR) {
         set_last_error("coarse_mode TENSOR requested but the tensor-core path does not support this shape/driver");
@@ -345,52 +286,265 @@ int32_t coarse_select(vdb_index* ix, const float* q_dev, uint32_t nq, uint32_t n
     }
     if (np > (uint32_t)scan_max_k()) {  // wider than the top-k machinery of the other two modes
         VDB_REQUIRE(coarse_wide_supported(ix->nlist, ix->ld), "nprobe > 2048 needs nlist <= 16384");
-        VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
-        VDB_TRY(ix->probes.reserve((size_t)nq * np));
-        return coarse_select_wide(q_dev, nq, ix->centroids.p, ix->nlist, ix->ld, np, ix->cfg.metric, ix->probes.p,
-                                  ix->coarse_d.p, stream);
+        return coarse_select_wide(q_dev, nq, ix->centroids.p, ix->nlist, ix->ld, np, ix->cfg.metric, s.probes.p,
+                                  s.coarse_d.p, stream);
     }
-    VDB_TRY(ix->zero_probes.reserve(nq));
-    VDB_CUDA_TRY(cudaMemsetAsync(ix->zero_probes.p, 0, (size_t)nq * 4, stream));
-    VDB_TRY(ix->coarse_d.reserve((size_t)nq * np));
-    VDB_TRY(ix->coarse_i.reserve((size_t)nq * np));
-    VDB_TRY(ix->probes.reserve((size_t)nq * np));
-    // keep the partial-result buffer below ~64 MiB by widening the page range per item
+    VDB_TRY(s.zero_probes.reserve(nq));
+    VDB_CUDA_TRY(cudaMemsetAsync(s.zero_probes.p, 0, (size_t)nq * 4, stream));
+    VDB_TRY(s.coarse_i.reserve((size_t)nq * np));
+    // keep the partial-result buffer below ~64 MiB by widening the page range per item (one range per query at most)
     uint32_t ppi = 1;
-    while ((uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi) * np * 12 > (64ull << 20)) ppi *= 2;
+    while ((uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi) * np * 12 > (64ull << 20) && ppi < ix->c_npages) ppi *= 2;
     const uint64_t slots = (uint64_t)nq * ((ix->c_npages + ppi - 1) / ppi);
-    return scan_search(centroid_table(ix), q_dev, nq, ix->zero_probes.p, 1, np, ix->cfg.metric, ppi, slots,
-                       ix->ws_coarse, false, ix->coarse_d.p, ix->coarse_i.p, ix->probes.p, stream);
+    return scan_search(centroid_table(ix), q_dev, nq, s.zero_probes.p, 1, np, ix->cfg.metric, ppi, slots,
+                       s.ws_coarse, false, s.coarse_d.p, s.coarse_i.p, s.probes.p, stream);
 }
 
-int32_t search_device(vdb_index* ix, const float* q_dev /* [nq][ld] */, uint32_t nq, uint32_t nprobe, uint32_t k,
-                      float* out_d, uint64_t* out_i, cudaStream_t stream) {
+int32_t ensure_slot_events(SearchSlot& s) {
+    if (!s.ev_done) {
+        VDB_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_front, cudaEventDisableTiming));
+        VDB_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_scan, cudaEventDisableTiming));
+        VDB_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    return VDB_OK;
+}
+
+int32_t ensure_slot_timers(SearchSlot& s) {
+    if (!s.tm[0])
+        for (uint32_t i = 0; i < SLOT_TIMERS; ++i) VDB_CUDA_TRY(cudaEventCreate(&s.tm[i]));
+    return VDB_OK;
+}
+
+// add the phase times of a completed search to the index's sums
+void harvest_timers(vdb_index* ix, SearchSlot& s) {
+    if (!s.timed) return;
+    s.timed = false;
+    static const int pairs[5][2] = {{0, 1}, {1, 2}, {3, 4}, {5, 6}, {6, 7}};
+    for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.tm[pairs[i][0]], s.tm[pairs[i][1]]) == cudaSuccess) ix->prof_ms[i] += ms;
+        else cudaGetLastError();
+    }
+    ++ix->prof_searches;
+}
+
+}  // namespace
+
+// Block the host until the search in slot `s` is complete, hand host results to the caller's arrays, report a
+// peer-exchange timeout of this search, and make the slot reusable.  Caller holds ix->mu or owns the ticket.
+int32_t vdb::index_finish_slot(vdb_index* ix, SearchSlot& s) {
+    if (!s.busy) return VDB_OK;
+    DeviceGuard g(ix->device);
+    VDB_CUDA_TRY(cudaEventSynchronize(s.ev_done));
+    s.busy = false;
+    harvest_timers(ix, s);
+    if (s.deliver) {
+        std::memcpy(s.user_d, s.h_d.p, s.out_elems * 4);
+        std::memcpy(s.user_i, s.h_i.p, s.out_elems * 8);
+        s.deliver = false;
+    }
+    if (s.used_exchange && ix->exchange) return vdb_exchange_status(ix->exchange);
+    return VDB_OK;
+}
+
+int32_t vdb::index_acquire_slot(vdb_index* ix, SearchSlot** out, uint64_t* ticket) {
+    const uint64_t t = ++ix->next_ticket;
+    SearchSlot& s = ix->slots[t % ix->depth];
+    VDB_TRY(ensure_slot_events(s));
+    const int32_t st = index_finish_slot(ix, s);  // the search that used this slot `depth` tickets ago
+    s.ticket = t;
+    ix->last_slot = (int)(t % ix->depth);
+    *out = &s;
+    *ticket = t;
+    return st;
+}
+
+// One search, three phases (SearchSlot).  `queries`: host or device, [nq][dim]; a device array must already hold
+// its values (or be ordered before st.front by the caller).  distances / indices: host or device, or null when
+// the merged local result is only published (collect = false).
+int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* queries, uint32_t nq, uint32_t nprobe,
+                                  uint32_t k, float* distances, uint64_t* indices, const SearchStreams& st,
+                                  bool collect) {
     const uint32_t np = std::min(nprobe, ix->nlist);  // the reference reads past probe_lists instead (:221-222)
-    VDB_TRY(ws_acquire(ix, stream));
-    cudaEvent_t* ev = nullptr;
-    if (ix->profiling && (ix->prof_used + 1) * 5 <= ix->prof_events.size()) {
-        ev = ix->prof_events.data() + (size_t)ix->prof_used * 5;
-        ++ix->prof_used;
-        cudaEventRecord(ev[0], stream);
-        ++ev;
+    const bool prof = ix->profiling;
+    if (prof) VDB_TRY(ensure_slot_timers(s));
+    vdb_exchange* ex = ix->exchange;
+    const bool out_dev = distances ? is_device_ptr(distances) : true;
+    if (distances) VDB_REQUIRE(out_dev == is_device_ptr(indices), "search: distances and indices must live on the same side");
+    VDB_REQUIRE(collect || ex, "search: publishing without an exchange");
+
+    // ---- front: queries -> [nq][ld] on the device, coarse selection, probe grouping
+    nvtxRangePushA("vdb.search.front");
+    if (prof) cudaEventRecord(s.tm[0], st.front);
+    const float* q = nullptr;
+    const bool q_dev = is_device_ptr(queries);
+    if (q_dev && ix->dim == ix->ld && !((uintptr_t)queries & 15)) {
+        q = queries;
+    } else {
+        VDB_TRY(s.q_buf.reserve((size_t)nq * ix->ld));
+        if (q_dev) {
+            VDB_TRY(launch_pad_rows(queries, ix->dim, ix->dim, s.q_buf.p, ix->ld, nq, st.front));
+        } else {
+            const float* src = queries;
+            if (!is_pinned_ptr(queries)) {  // pageable memory would make the copy synchronous: stage it
+                VDB_TRY(s.h_q.reserve((size_t)nq * ix->dim * 4));
+                std::memcpy(s.h_q.p, queries, (size_t)nq * ix->dim * 4);
+                src = static_cast<const float*>(s.h_q.p);
+            }
+            if (ix->dim == ix->ld) {
+                VDB_CUDA_TRY(cudaMemcpyAsync(s.q_buf.p, src, (size_t)nq * ix->ld * 4, cudaMemcpyHostToDevice, st.front));
+            } else {
+                VDB_CUDA_TRY(cudaMemsetAsync(s.q_buf.p, 0, (size_t)nq * ix->ld * 4, st.front));
+                VDB_CUDA_TRY(cudaMemcpy2DAsync(s.q_buf.p, (size_t)ix->ld * 4, src, (size_t)ix->dim * 4,
+                                               (size_t)ix->dim * 4, nq, cudaMemcpyHostToDevice, st.front));
+            }
+        }
+        q = s.q_buf.p;
     }
-    VDB_TRY(coarse_select(ix, q_dev, nq, np, stream));
-    // pages per scan item: longer runs of a list amortise the per-item costs (tile announcement, barriers,
-    // final selection, partial write-out, merge input) over up to ~3 MB.  Measured: 4 pages beat 1 and 2 even on a
-    // 1/8 shard of the headline index (scan 0.49 vs 0.50 / 0.56 ms) and 8 loses to the longer tail, so 4 it is
-    // whenever that still leaves a handful of items per SM
-    uint32_t ppi = std::max<uint32_t>(1, std::min<uint32_t>(4, ix->pages_used / (NUM_SMS_B200 * 4u)));
-    if (ppi == 3) ppi = 2;
-    if (const char* e = std::getenv("VDB_SCAN_PPI")) {  // tuning knob: pages per scan item (1, 2, 4 or 8)
-        const int v = std::atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) ppi = (uint32_t)v;
+    VDB_TRY(slot_coarse_select(ix, s, q, nq, np, st.front));
+    if (prof) cudaEventRecord(s.tm[1], st.front);
+    uint32_t ppi = 1, nq_chunk = nq;
+    choose_ppi(ix, nq, np, k, &ppi, &nq_chunk);
+    VDB_REQUIRE(nq_chunk == nq, "search: internal error, batch not chunked");
+    // a pipelined scan leaves a few SMs to the front / back kernels of the neighbouring batches
+    int sms = NUM_SMS_B200;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+    const uint32_t max_ctas = st.split && (uint32_t)sms > 2 * ix->reserve_sms ? (uint32_t)sms - ix->reserve_sms : 0u;
+    ScanPlan plan;
+    VDB_TRY(scan_plan(list_table(ix), q, nq, s.probes.p, np, k, ix->cfg.metric, ppi, slot_bound(ix, nq, np, ppi), true,
+                      max_ctas, s.ws_scan, &plan));
+    VDB_TRY(scan_enqueue_groups(plan, s.ws_scan, st.front));
+    if (prof) cudaEventRecord(s.tm[2], st.front);
+    if (st.split) {
+        VDB_CUDA_TRY(cudaEventRecord(s.ev_front, st.front));
+        VDB_CUDA_TRY(cudaStreamWaitEvent(st.scan, s.ev_front, 0));
     }
-    while (slot_bound(ix, nq, np, ppi) * k * 12 > (1ull << 30)) ppi *= 2;
-    const uint64_t slots = slot_bound(ix, nq, np, ppi);
-    VDB_TRY(scan_search(list_table(ix), q_dev, nq, ix->probes.p, np, k, ix->cfg.metric, ppi, slots, ix->ws_scan,
-                        true, out_d, out_i, nullptr, stream, &ix->last_scan_info, ev));
-    ix->have_search = true;
-    return ws_release(ix, stream);
+    nvtxRangePop();
+
+    // ---- scan
+    nvtxRangePushA("vdb.search.scan");
+    if (prof) {
+        if (!ix->span_open) {
+            cudaEventRecord(ix->span_start, st.scan);
+            ix->span_open = true;
+        }
+        cudaEventRecord(s.tm[3], st.scan);
+    }
+    VDB_TRY(scan_enqueue_scan(plan, s.ws_scan, st.scan));
+    if (prof) {
+        cudaEventRecord(s.tm[4], st.scan);
+        cudaEventRecord(ix->span_end, st.scan);
+    }
+    if (st.split) {
+        VDB_CUDA_TRY(cudaEventRecord(s.ev_scan, st.scan));
+        VDB_CUDA_TRY(cudaStreamWaitEvent(st.back, s.ev_scan, 0));
+    }
+    nvtxRangePop();
+
+    // ---- back: merge (+ publish into the peers' mailboxes, + collect), results to the caller
+    nvtxRangePushA("vdb.search.back");
+    if (prof) cudaEventRecord(s.tm[5], st.back);
+    float* od = distances;
+    uint64_t* oi = indices;
+    if (collect && !out_dev) {
+        VDB_TRY(s.out_d.reserve((size_t)nq * k));
+        VDB_TRY(s.out_i.reserve((size_t)nq * k));
+        od = s.out_d.p;
+        oi = s.out_i.p;
+    }
+    s.used_exchange = ex != nullptr;
+    if (ex) {
+        PublishTarget pub;
+        VDB_TRY(exchange_begin_publish(ex, nq, k, &pub));
+        VDB_TRY(scan_enqueue_merge(plan, s.ws_scan, nullptr, nullptr, nullptr, &pub, st.back));
+        if (prof) cudaEventRecord(s.tm[6], st.back);
+        if (collect) VDB_TRY(exchange_collect(ex, od, oi, st.back));
+    } else {
+        VDB_TRY(scan_enqueue_merge(plan, s.ws_scan, od, oi, nullptr, nullptr, st.back));
+        if (prof) cudaEventRecord(s.tm[6], st.back);
+    }
+    if (prof) cudaEventRecord(s.tm[7], st.back);
+    s.deliver = false;
+    if (collect && !out_dev) {
+        const size_t ne = (size_t)nq * k;
+        float* hd = distances;
+        uint64_t* hi = indices;
+        if (!is_pinned_ptr(distances) || !is_pinned_ptr(indices)) {
+            VDB_TRY(s.h_d.reserve(ne * 4));
+            VDB_TRY(s.h_i.reserve(ne * 8));
+            hd = static_cast<float*>(s.h_d.p);
+            hi = static_cast<uint64_t*>(s.h_i.p);
+            s.user_d = distances;
+            s.user_i = indices;
+            s.out_elems = ne;
+            s.deliver = true;
+        }
+        VDB_CUDA_TRY(cudaMemcpyAsync(hd, od, ne * 4, cudaMemcpyDeviceToHost, st.back));
+        VDB_CUDA_TRY(cudaMemcpyAsync(hi, oi, ne * 8, cudaMemcpyDeviceToHost, st.back));
+    }
+    VDB_CUDA_TRY(cudaEventRecord(s.ev_done, st.back));
+    nvtxRangePop();
+    s.busy = true;
+    s.timed = prof;
+    s.info = plan.info;
+    return VDB_OK;
+}
+
+namespace {
+
+// every slot's buffers for searches of up to (rs_nq, rs_np, rs_k), so that no cudaMalloc (an implicit device
+// synchronisation) happens inside a search; add() repeats it because longer lists mean more partial-result slots
+int32_t reserve_slots(vdb_index* ix) {
+    if (!ix->rs_nq) return VDB_OK;
+    const uint32_t nq = ix->rs_nq, np = std::min(ix->rs_np, ix->nlist), k = ix->rs_k;
+    uint32_t ppi = 1, nq_chunk = nq;
+    choose_ppi(ix, nq, np, k, &ppi, &nq_chunk);
+    const uint64_t slots = std::max<uint64_t>(1, slot_bound(ix, nq_chunk, np, ppi));
+    for (uint32_t i = 0; i < ix->depth; ++i) {
+        SearchSlot& s = ix->slots[i];
+        VDB_TRY(index_finish_slot(ix, s));
+        VDB_TRY(ensure_slot_events(s));
+        VDB_TRY(ensure_slot_timers(s));
+        VDB_TRY(s.q_buf.reserve((size_t)nq * ix->ld));
+        VDB_TRY(s.dots.reserve((size_t)nq * round_up(ix->nlist, 4)));
+        VDB_TRY(s.coarse_d.reserve((size_t)nq * np));
+        VDB_TRY(s.probes.reserve((size_t)nq * np));
+        VDB_TRY(s.out_d.reserve((size_t)nq * k));
+        VDB_TRY(s.out_i.reserve((size_t)nq * k));
+        VDB_TRY(s.h_q.reserve((size_t)nq * ix->dim * 4));
+        VDB_TRY(s.h_d.reserve((size_t)nq * k * 4));
+        VDB_TRY(s.h_i.reserve((size_t)nq * k * 8));
+        VDB_TRY(s.ws_scan.reserve(ix->nlist, nq_chunk * np, slots, k, nq_chunk));
+    }
+    return VDB_OK;
+}
+
+SearchStreams pipeline_streams(vdb_index* ix, uint64_t ticket) {
+    return SearchStreams{ix->s_front, ix->s_scan[ticket & 1], ix->s_back, true};
+}
+
+// the shapes one pass cannot take (partial-result buffer) are split over query chunks, each a pass of its own
+int32_t search_chunked(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k, float* distances,
+                       uint64_t* indices, uint32_t nq_chunk) {
+    for (uint32_t lo = 0; lo < nq; lo += nq_chunk) {
+        const uint32_t m = std::min(nq_chunk, nq - lo);
+        SearchSlot* s = nullptr;
+        uint64_t t = 0;
+        VDB_TRY(index_acquire_slot(ix, &s, &t));
+        VDB_TRY(index_enqueue_search(ix, *s, queries + (size_t)lo * ix->dim, m, nprobe, k, distances + (size_t)lo * k,
+                                     indices + (size_t)lo * k, pipeline_streams(ix, t), true));
+        VDB_TRY(index_finish_slot(ix, *s));
+    }
+    return VDB_OK;
+}
+
+int32_t check_search_args(vdb_index* ix, const void* q, const void* d, const void* i, uint32_t nq, uint32_t nprobe,
+                          uint32_t k) {
+    VDB_REQUIRE(q && d && i, "search: null buffer");
+    VDB_REQUIRE(nq >= 1 && k >= 1 && nprobe >= 1, "search: nq, k and nprobe must be >= 1");
+    VDB_REQUIRE(k <= (uint32_t)scan_max_k(), "search: k must be <= 2048");
+    (void)ix;
+    return VDB_OK;
 }
 
 int32_t check_index(vdb_index* ix) {
@@ -467,16 +621,37 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     ix->h_pages.resize(ix->nlist);
     DeviceGuard g(ix->device);
     VDB_CUDA_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    // search pipeline: the short front / back kernels run at high priority so that they take the first SM a
+    // scan CTA frees; consecutive scans alternate between two streams so that batch i+1 fills the tail of batch i
+    int prio_lo = 0, prio_hi = 0;
+    VDB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_front, cudaStreamNonBlocking, prio_hi));
+    VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_back, cudaStreamNonBlocking, prio_hi));
+    VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_scan[0], cudaStreamNonBlocking, prio_lo));
+    VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_scan[1], cudaStreamNonBlocking, prio_lo));
+    VDB_CUDA_TRY(cudaEventCreate(&ix->span_start));
+    VDB_CUDA_TRY(cudaEventCreate(&ix->span_end));
+    ix->depth = cfg->pipeline_depth ? cfg->pipeline_depth : 4;
+    ix->reserve_sms = cfg->reserve_sms == 0xffffffffu ? 0 : cfg->reserve_sms ? cfg->reserve_sms : 8;
+    // tuning knobs, read once: pages per scan item, pipeline depth, SMs left to the side kernels
+    if (const char* e = std::getenv("VDB_SCAN_PPI")) {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) ix->ppi_override = (uint32_t)v;
+    }
+    if (const char* e = std::getenv("VDB_PIPELINE_DEPTH")) ix->depth = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("VDB_RESERVE_SMS")) ix->reserve_sms = (uint32_t)std::atoi(e);
+    VDB_REQUIRE(ix->depth >= 1 && ix->depth <= MAX_SEARCH_SLOTS, "pipeline_depth must be in [1, 8]");
+    VDB_REQUIRE(ix->reserve_sms <= 64, "reserve_sms must be <= 64");
     VDB_TRY(ix->centroids.reserve((size_t)ix->nlist * ix->ld));
     VDB_CUDA_TRY(cudaMemsetAsync(ix->centroids.p, 0, ix->centroids.bytes(), ix->stream));  // centroids_ value-init (:22)
     if (cfg->shard_count > 1) {
         ix->h_owner.resize(ix->nlist);
         for (uint32_t l = 0; l < ix->nlist; ++l) ix->h_owner[l] = (uint8_t)(l % cfg->shard_count);
-        VDB_TRY(upload_owners(ix.get()));
+        VDB_TRY(index_upload_owners(ix.get()));
     }
     VDB_TRY(refresh_centroid_view(ix.get()));
     VDB_TRY(refresh_centroid_aux(ix.get()));
-    VDB_TRY(upload_list_tables(ix.get()));
+    VDB_TRY(index_upload_list_tables(ix.get()));
     *out = ix.release();
     return VDB_OK;
 }
@@ -486,19 +661,28 @@ int32_t vdb_index_destroy(vdb_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        for (void* s : ix->slabs) cudaFree(s);
-        ix->centroids.release(); ix->cnorm.release(); ix->cmax_bits.release(); ix->dots.release(); ix->c_rows.release(); ix->c_page_off.release(); ix->c_page_vec.release();
-        ix->c_page_ids.release(); ix->d_rows.release(); ix->d_page_off.release(); ix->d_page_vec.release();
-        ix->d_page_ids.release(); ix->q_buf.release(); ix->coarse_d.release(); ix->out_d.release();
-        ix->coarse_i.release(); ix->out_i.release(); ix->probes.release(); ix->zero_probes.release();
+        for (void* sl : ix->slabs) cudaFree(sl);
+        ix->centroids.release(); ix->cnorm.release(); ix->cmax_bits.release(); ix->c_rows.release();
+        ix->c_page_off.release(); ix->c_page_vec.release(); ix->c_page_ids.release(); ix->d_rows.release();
+        ix->d_page_off.release(); ix->d_page_vec.release(); ix->d_page_ids.release();
         ix->assign_buf.release(); ix->hist_buf.release(); ix->fill_buf.release(); ix->stage_buf.release();
         ix->ids_stage.release(); ix->d_owner.release();
         ix->tc_assign.release();
-        ix->ws_coarse.release();
-        ix->ws_scan.release();
-        for (auto e : ix->prof_events) cudaEventDestroy(e);
-        if (ix->ws_event) cudaEventDestroy(ix->ws_event);
-        if (ix->stream) cudaStreamDestroy(ix->stream);
+        for (auto& s : ix->slots) {
+            s.ws_scan.release(); s.ws_coarse.release();
+            s.q_buf.release(); s.dots.release(); s.coarse_d.release(); s.out_d.release();
+            s.coarse_i.release(); s.out_i.release(); s.probes.release(); s.zero_probes.release();
+            s.h_q.release(); s.h_d.release(); s.h_i.release();
+            if (s.ev_front) cudaEventDestroy(s.ev_front);
+            if (s.ev_scan) cudaEventDestroy(s.ev_scan);
+            if (s.ev_done) cudaEventDestroy(s.ev_done);
+            for (auto e : s.tm)
+                if (e) cudaEventDestroy(e);
+        }
+        if (ix->span_start) cudaEventDestroy(ix->span_start);
+        if (ix->span_end) cudaEventDestroy(ix->span_end);
+        for (cudaStream_t st : {ix->stream, ix->s_front, ix->s_back, ix->s_scan[0], ix->s_scan[1]})
+            if (st) cudaStreamDestroy(st);
     }
     delete ix;
     return VDB_OK;
@@ -536,8 +720,8 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
         // list sizes of the training sample under the final centroids -> byte-balanced list ownership
         std::vector<uint32_t> counts(ix->nlist, 0);
         st = assign_rows(ix, x, n, sc.assign, ix->stream);
-        if (st == VDB_OK) st = ix->hist_buf.reserve(ix->nlist);
-        if (st == VDB_OK && cudaMemsetAsync(ix->hist_buf.p, 0, ix->nlist * 4, ix->stream) != cudaSuccess) st = VDB_CUDA_ERROR;
+        if (st == VDB_OK) st = ix->hist_buf.reserve(ix->nlist + 1);
+        if (st == VDB_OK && cudaMemsetAsync(ix->hist_buf.p, 0, (ix->nlist + 1) * 4, ix->stream) != cudaSuccess) st = VDB_CUDA_ERROR;
         if (st == VDB_OK) st = launch_hist(sc.assign, n, ix->nlist, 0, nullptr, ix->hist_buf.p, ix->stream);
         if (st == VDB_OK && cudaMemcpyAsync(counts.data(), ix->hist_buf.p, ix->nlist * 4, cudaMemcpyDeviceToHost,
                                             ix->stream) != cudaSuccess)
@@ -545,7 +729,7 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
         if (st == VDB_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) st = VDB_CUDA_ERROR;
         if (st == VDB_OK) {
             balance_owners(ix, counts);
-            st = upload_owners(ix);
+            st = index_upload_owners(ix);
         }
     }
     if (st == VDB_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) {
@@ -585,14 +769,16 @@ static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids
             asg = ix->assign_buf.p;
         }
         // per-list counts -> grow the page chains
-        VDB_TRY(ix->hist_buf.reserve(ix->nlist));
+        VDB_TRY(ix->hist_buf.reserve(ix->nlist + 1));
         VDB_TRY(ix->fill_buf.reserve(ix->nlist));
-        VDB_CUDA_TRY(cudaMemsetAsync(ix->hist_buf.p, 0, ix->nlist * 4, ix->stream));
+        VDB_CUDA_TRY(cudaMemsetAsync(ix->hist_buf.p, 0, (ix->nlist + 1) * 4, ix->stream));
         VDB_CUDA_TRY(cudaMemsetAsync(ix->fill_buf.p, 0, ix->nlist * 4, ix->stream));
         VDB_TRY(launch_hist(asg, m, ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->hist_buf.p, ix->stream));
-        std::vector<uint32_t> hist(ix->nlist);
-        VDB_CUDA_TRY(cudaMemcpyAsync(hist.data(), ix->hist_buf.p, ix->nlist * 4, cudaMemcpyDeviceToHost, ix->stream));
+        std::vector<uint32_t> hist(ix->nlist + 1);
+        VDB_CUDA_TRY(cudaMemcpyAsync(hist.data(), ix->hist_buf.p, (ix->nlist + 1) * 4, cudaMemcpyDeviceToHost, ix->stream));
         VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        // caller-supplied assignments (add_assigned) naming no list: nothing of this chunk has been stored yet
+        VDB_REQUIRE(hist[ix->nlist] == 0, "add: an assignment is >= nlist");
         std::vector<uint32_t> new_rows = ix->h_rows;
         uint64_t added = 0;
         for (uint32_t l = 0; l < ix->nlist; ++l) {
@@ -603,15 +789,15 @@ static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids
             const uint32_t need = (new_rows[l] + ix->page_rows - 1) / ix->page_rows;
             while (ix->h_pages[l].size() < need) {
                 uint32_t pg;
-                VDB_TRY(alloc_page(ix, &pg));
+                VDB_TRY(index_alloc_page(ix, &pg));
                 ix->h_pages[l].push_back(pg);
             }
         }
         // device tables: page chains now, old row counts as the append base
-        VDB_TRY(upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
+        VDB_TRY(index_upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
         VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, asg, ix->d_rows.p, ix->fill_buf.p,
                                     ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p, ix->page_rows, ix->ld,
-                                    ix->cfg.shard_rank, ix->d_owner.p, ix->stream));
+                                    ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->stream));
         ix->h_rows = new_rows;
         VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), ix->nlist * 4, cudaMemcpyHostToDevice,
                                      ix->stream));
@@ -619,7 +805,7 @@ static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids
         ix->local_vectors += added;
     }
     ix->total_vectors += counted;  // total_vectors_ += n_vectors (:200)
-    return VDB_OK;
+    return reserve_slots(ix);
 }
 
 int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
@@ -645,48 +831,91 @@ int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64
 int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe, uint32_t k,
                                float* distances_dev, uint64_t* indices_dev, void* stream) {
     VDB_TRY(check_index(ix));
-    VDB_REQUIRE(queries_dev && distances_dev && indices_dev, "search: null buffer");
-    VDB_REQUIRE(nq >= 1 && k >= 1 && nprobe >= 1, "search: nq, k and nprobe must be >= 1");
+    VDB_TRY(check_search_args(ix, queries_dev, distances_dev, indices_dev, nq, nprobe, k));
+    VDB_REQUIRE(is_device_ptr(distances_dev) && is_device_ptr(indices_dev), "search_async: outputs must be device arrays");
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    VDB_TRY(ws_acquire(ix, s));
-    const float* q = queries_dev;
-    if (ix->dim != ix->ld || ((uintptr_t)queries_dev & 15)) {
-        VDB_TRY(ix->q_buf.reserve((size_t)nq * ix->ld));
-        VDB_TRY(launch_pad_rows(queries_dev, ix->dim, ix->dim, ix->q_buf.p, ix->ld, nq, s));
-        q = ix->q_buf.p;
+    uint32_t ppi = 1, nq_chunk = nq;
+    choose_ppi(ix, nq, std::min(nprobe, ix->nlist), k, &ppi, &nq_chunk);
+    VDB_REQUIRE(nq_chunk == nq, "search_async: nq * nprobe * k too large for one pass; use vdb_index_search");
+    SearchSlot* s = nullptr;
+    uint64_t t = 0;
+    VDB_TRY(index_acquire_slot(ix, &s, &t));
+    cudaStream_t st = (cudaStream_t)stream;
+    return index_enqueue_search(ix, *s, queries_dev, nq, nprobe, k, distances_dev, indices_dev,
+                                SearchStreams{st, st, st, false}, true);
+}
+
+int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
+                                float* distances, uint64_t* indices, uint64_t* ticket) {
+    VDB_TRY(check_index(ix));
+    VDB_TRY(check_search_args(ix, queries, distances, indices, nq, nprobe, k));
+    VDB_REQUIRE(ticket, "search_submit: null ticket");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    uint32_t ppi = 1, nq_chunk = nq;
+    choose_ppi(ix, nq, std::min(nprobe, ix->nlist), k, &ppi, &nq_chunk);
+    if (nq_chunk < nq) {  // too large for one pass: done chunk by chunk right here, the ticket is already complete
+        VDB_TRY(search_chunked(ix, queries, nq, nprobe, k, distances, indices, nq_chunk));
+        *ticket = ix->next_ticket;
+        return VDB_OK;
     }
-    return search_device(ix, q, nq, nprobe, k, distances_dev, indices_dev, s);
+    SearchSlot* s = nullptr;
+    VDB_TRY(index_acquire_slot(ix, &s, ticket));
+    return index_enqueue_search(ix, *s, queries, nq, nprobe, k, distances, indices, pipeline_streams(ix, *ticket), true);
+}
+
+int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket) {
+    VDB_TRY(check_index(ix));
+    SearchSlot* s = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        VDB_REQUIRE(ticket >= 1 && ticket <= ix->next_ticket, "search_wait: unknown ticket");
+        s = &ix->slots[ticket % ix->depth];
+        if (s->ticket != ticket || !s->busy) return VDB_OK;  // finished (and delivered) when its slot was recycled
+    }
+    {
+        DeviceGuard g(ix->device);
+        VDB_CUDA_TRY(cudaEventSynchronize(s->ev_done));  // without the lock: other threads keep submitting
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (s->ticket != ticket) return VDB_OK;
+    return index_finish_slot(ix, *s);
+}
+
+int32_t vdb_index_search_wait_stream(vdb_index* ix, uint64_t ticket, void* stream) {
+    VDB_TRY(check_index(ix));
+    std::lock_guard<std::mutex> lock(ix->mu);
+    VDB_REQUIRE(ticket >= 1 && ticket <= ix->next_ticket, "search_wait_stream: unknown ticket");
+    SearchSlot& s = ix->slots[ticket % ix->depth];
+    if (s.ticket != ticket || !s.busy) return VDB_OK;
+    DeviceGuard g(ix->device);
+    VDB_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s.ev_done, 0));
+    return VDB_OK;
 }
 
 int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
                          float* distances, uint64_t* indices) {
+    uint64_t ticket = 0;
+    VDB_TRY(vdb_index_search_submit(ix, queries, nq, nprobe, k, distances, indices, &ticket));
+    return vdb_index_search_wait(ix, ticket);
+}
+
+int32_t vdb_index_reserve_search(vdb_index* ix, uint32_t max_nq, uint32_t max_nprobe, uint32_t max_k) {
     VDB_TRY(check_index(ix));
-    VDB_REQUIRE(queries && distances && indices, "search: null buffer");
-    VDB_REQUIRE(nq >= 1 && k >= 1 && nprobe >= 1, "search: nq, k and nprobe must be >= 1");
-    VDB_REQUIRE(k <= (uint32_t)scan_max_k(), "search: k must be <= 2048");
+    VDB_REQUIRE(max_nq >= 1 && max_nprobe >= 1 && max_k >= 1 && max_k <= (uint32_t)scan_max_k(), "reserve_search: bad shape");
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
-    const float* q = nullptr;
-    VDB_TRY(ws_acquire(ix, ix->stream));
-    VDB_TRY(stage_rows(ix, queries, nq, ix->q_buf, &q, ix->stream));
-    const bool out_dev = is_device_ptr(distances);
-    VDB_REQUIRE(out_dev == is_device_ptr(indices), "search: distances and indices must live on the same side");
-    float* od = distances;
-    uint64_t* oi = indices;
-    if (!out_dev) {
-        VDB_TRY(ix->out_d.reserve((size_t)nq * k));
-        VDB_TRY(ix->out_i.reserve((size_t)nq * k));
-        od = ix->out_d.p;
-        oi = ix->out_i.p;
-    }
-    VDB_TRY(search_device(ix, q, nq, nprobe, k, od, oi, ix->stream));
-    if (!out_dev) {
-        VDB_CUDA_TRY(cudaMemcpyAsync(distances, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-        VDB_CUDA_TRY(cudaMemcpyAsync(indices, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
-    }
-    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->rs_nq = max_nq; ix->rs_np = max_nprobe; ix->rs_k = max_k;
+    return reserve_slots(ix);
+}
+
+int32_t vdb_index_attach_exchange(vdb_index* ix, vdb_exchange* ex) {
+    VDB_TRY(check_index(ix));
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    for (uint32_t i = 0; i < ix->depth; ++i) VDB_TRY(index_finish_slot(ix, ix->slots[i]));
+    ix->exchange = ex;
     return VDB_OK;
 }
 
@@ -696,11 +925,13 @@ int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     const uint32_t np = std::min(nprobe, ix->nlist);
+    SearchSlot* s = nullptr;
+    uint64_t t = 0;
+    VDB_TRY(index_acquire_slot(ix, &s, &t));
     const float* q = nullptr;
-    VDB_TRY(ws_acquire(ix, ix->stream));
-    VDB_TRY(stage_rows(ix, queries, nq, ix->q_buf, &q, ix->stream));
-    VDB_TRY(coarse_select(ix, q, nq, np, ix->stream));
-    VDB_CUDA_TRY(cudaMemcpyAsync(lists, ix->probes.p, (size_t)nq * np * 4,
+    VDB_TRY(stage_rows(ix, queries, nq, s->q_buf, &q, ix->stream));
+    VDB_TRY(slot_coarse_select(ix, *s, q, nq, np, ix->stream));
+    VDB_CUDA_TRY(cudaMemcpyAsync(lists, s->probes.p, (size_t)nq * np * 4,
                                  is_device_ptr(lists) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                                  ix->stream));
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
@@ -768,7 +999,7 @@ int32_t vdb_index_set_owners(vdb_index* ix, const uint8_t* in) {
         VDB_REQUIRE(in[l] < ix->cfg.shard_count, "set_owners: rank out of range");
         ix->h_owner[l] = in[l];
     }
-    return upload_owners(ix);
+    return index_upload_owners(ix);
 }
 
 int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out) {
@@ -820,15 +1051,17 @@ int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
     DeviceGuard g(ix->device);
     std::memset(out, 0, sizeof(*out));
     out->bytes_per_row = 4ull * ix->dim + 8;
-    if (!ix->have_search) return VDB_OK;
+    if (ix->last_slot < 0) return VDB_OK;
+    SearchSlot& s = ix->slots[ix->last_slot];
+    VDB_TRY(index_finish_slot(ix, s));
     unsigned long long st[2] = {0, 0};
     uint32_t tot[2] = {0, 0};
-    VDB_CUDA_TRY(cudaDeviceSynchronize());
-    VDB_CUDA_TRY(cudaMemcpy(st, ix->ws_scan.stats, 16, cudaMemcpyDeviceToHost));
-    VDB_CUDA_TRY(cudaMemcpy(tot, ix->ws_scan.totals, 8, cudaMemcpyDeviceToHost));
+    VDB_CUDA_TRY(cudaMemcpy(st, s.ws_scan.stats, 16, cudaMemcpyDeviceToHost));
+    VDB_CUDA_TRY(cudaMemcpy(tot, s.ws_scan.totals, 8, cudaMemcpyDeviceToHost));
     out->algorithmic_rows = st[0];
     out->unique_rows = st[1];
     out->scan_items = tot[0];
+    out->scan_ctas = s.info.grid;
     return VDB_OK;
 }
 
@@ -836,12 +1069,11 @@ int32_t vdb_index_set_profiling(vdb_index* ix, int32_t enable) {
     VDB_TRY(check_index(ix));
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
+    for (uint32_t i = 0; i < ix->depth; ++i) VDB_TRY(index_finish_slot(ix, ix->slots[i]));
     ix->profiling = enable != 0;
-    ix->prof_used = 0;
-    if (ix->profiling && ix->prof_events.empty()) {
-        ix->prof_events.resize(5 * 4096);
-        for (auto& e : ix->prof_events) VDB_CUDA_TRY(cudaEventCreate(&e));
-    }
+    for (double& v : ix->prof_ms) v = 0.0;
+    ix->prof_searches = 0;
+    ix->span_open = false;
     return VDB_OK;
 }
 
@@ -850,18 +1082,18 @@ int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms, uint32_t* searches)
     VDB_REQUIRE(out_ms && searches, "read_profile: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
-    VDB_CUDA_TRY(cudaDeviceSynchronize());
-    for (int i = 0; i < 4; ++i) out_ms[i] = 0.f;
-    for (uint32_t sidx = 0; sidx < ix->prof_used; ++sidx) {
-        cudaEvent_t* e = ix->prof_events.data() + (size_t)sidx * 5;
-        for (int i = 0; i < 4; ++i) {
-            float ms = 0.f;
-            VDB_CUDA_TRY(cudaEventElapsedTime(&ms, e[i], e[i + 1]));
-            out_ms[i] += ms;
-        }
+    for (uint32_t i = 0; i < ix->depth; ++i) VDB_TRY(index_finish_slot(ix, ix->slots[i]));
+    for (int i = 0; i < 5; ++i) out_ms[i] = (float)ix->prof_ms[i];
+    out_ms[5] = 0.f;
+    if (ix->span_open) {  // first scan start .. last scan end: the scan streams' busy time when batches overlap
+        VDB_CUDA_TRY(cudaEventSynchronize(ix->span_end));
+        VDB_CUDA_TRY(cudaEventElapsedTime(&out_ms[5], ix->span_start, ix->span_end));
     }
-    *searches = ix->prof_used;
-    ix->prof_used = 0;
+    out_ms[6] = out_ms[7] = 0.f;
+    *searches = ix->prof_searches;
+    for (double& v : ix->prof_ms) v = 0.0;
+    ix->prof_searches = 0;
+    ix->span_open = false;
     return VDB_OK;
 }
 

@@ -905,13 +905,18 @@ __global__ void centroid_divide_kernel(const float* __restrict__ sums, const uin
 
 // ----------------------------------------------------------------------- add
 
-// owner == nullptr: every list counts; else only the lists this shard owns
+// owner == nullptr: every list counts; else only the lists this shard owns.  hist has nlist + 1 entries: the last
+// one counts assignments that name no list (caller-supplied assignments, vdb_index_add_assigned)
 __global__ void hist_kernel(const uint32_t* __restrict__ assign, uint64_t n, uint32_t nlist, uint32_t shard_rank,
                             const uint8_t* __restrict__ owner, uint32_t* __restrict__ hist) {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t l = assign[v];
-    if (l < nlist && (!owner || owner[l] == shard_rank)) atomicAdd(&hist[l], 1u);
+    if (l >= nlist) {
+        atomicAdd(&hist[nlist], 1u);
+        return;
+    }
+    if (!owner || owner[l] == shard_rank) atomicAdd(&hist[l], 1u);
 }
 
 // one warp per new row: claim the next slot of its list, copy row + id into the page
@@ -923,12 +928,13 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
                                                            const uint32_t* __restrict__ page_off,
                                                            const uint64_t* __restrict__ page_vec,
                                                            const uint64_t* __restrict__ page_ids, uint32_t page_rows,
-                                                           uint32_t ld, uint32_t shard_rank,
+                                                           uint32_t ld, uint32_t nlist, uint32_t shard_rank,
                                                            const uint8_t* __restrict__ owner) {
     const uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (v >= n) return;
     const uint32_t l = assign[v];
+    if (l >= nlist) return;  // no page was allocated for it (hist_kernel counted it as invalid)
     if (owner && owner[l] != shard_rank) return;
     uint32_t pos = 0;
     if (lane == 0) pos = old_rows[l] + atomicAdd(&fill[l], 1u);
@@ -1159,12 +1165,12 @@ int32_t launch_hist(const uint32_t* assign, uint64_t n, uint32_t nlist, uint32_t
 int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, uint64_t id_base, uint64_t n,
                             const uint32_t* assign, const uint32_t* old_rows, uint32_t* fill,
                             const uint32_t* page_off, const uint64_t* page_vec, const uint64_t* page_ids,
-                            uint32_t page_rows, uint32_t ld, uint32_t shard_rank, const uint8_t* owner,
-                            cudaStream_t stream) {
+                            uint32_t page_rows, uint32_t ld, uint32_t nlist, uint32_t shard_rank,
+                            const uint8_t* owner, cudaStream_t stream) {
     if (n == 0) return VDB_OK;
     const uint64_t blocks = (n * 32 + 255) / 256;
     scatter_rows_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, ldx, ids, id_base, n, assign, old_rows, fill,
-                                                              page_off, page_vec, page_ids, page_rows, ld,
+                                                              page_off, page_vec, page_ids, page_rows, ld, nlist,
                                                               shard_rank, owner);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;

@@ -60,13 +60,14 @@ int32_t kmeans_cluster_sums(const float* x, uint32_t n, uint32_t ldx, const uint
                             uint32_t ld, float* sums, uint32_t* counts, KMeansScratch& sc, cudaStream_t stream);
 int32_t kmeans_divide(const float* sums, const uint32_t* counts, uint32_t nc, uint32_t ld, float* centroids,
                       cudaStream_t stream);
+// hist: [nlist + 1]; hist[nlist] counts assignments >= nlist
 int32_t launch_hist(const uint32_t* assign, uint64_t n, uint32_t nlist, uint32_t shard_rank, const uint8_t* owner,
                     uint32_t* hist, cudaStream_t stream);
 int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, uint64_t id_base, uint64_t n,
                             const uint32_t* assign, const uint32_t* old_rows, uint32_t* fill,
                             const uint32_t* page_off, const uint64_t* page_vec, const uint64_t* page_ids,
-                            uint32_t page_rows, uint32_t ld, uint32_t shard_rank, const uint8_t* owner,
-                            cudaStream_t stream);
+                            uint32_t page_rows, uint32_t ld, uint32_t nlist, uint32_t shard_rank,
+                            const uint8_t* owner, cudaStream_t stream);
 int32_t launch_pad_rows(const float* src, uint32_t lds, uint32_t dim, float* dst, uint32_t ld, uint64_t n,
                         cudaStream_t stream);
 

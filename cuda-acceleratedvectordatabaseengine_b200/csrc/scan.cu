@@ -27,6 +27,7 @@
 //      (multiset, as search_list_cpu returns it) -> sort by (dist,id), drop
 //      duplicate ids, pad: merge_results.
 #include "scan.cuh"
+#include "exchange.cuh"
 #include "topk.cuh"
 
 namespace vdb {
@@ -40,6 +41,7 @@ constexpr int SCAN_THREADS = CONSUMER_THREADS + 128;  // 2 consumer warpgroups +
 constexpr int MAX_QT = 32;  // queries per CTA tile: register tile (tile_queries) x up to 8 warp groups
 constexpr uint32_t MAX_K = 2048;
 constexpr uint32_t SMEM_BUDGET = 227 * 1024;
+constexpr uint32_t ITEM_CLASSES = 320;  // cost classes of the longest-first item order: 40 binades x 8
 
 struct WorkList {
     uint32_t *gcount, *gfill, *goff, *ioff, *gpairs, *pair_slot;
@@ -103,6 +105,7 @@ template <bool SMEM>
 __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const uint32_t* __restrict__ probes,
                                                             uint32_t npairs, uint32_t ppi, WorkList wl) {
     __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_cls[ITEM_CLASSES];
     extern __shared__ uint32_t s_lists[];
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
     const uint32_t nlist = lt.nlist;
@@ -211,24 +214,64 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
         dst[0] = lo;
         dst[1] = hi;
     };
-    if (SMEM) {
-        // thread per item: the owning list is found by binary search in the (shared-memory) item offsets
-        const uint32_t total = wl.ioff[nlist];
-        for (uint32_t idx = tid; idx < total; idx += NT) {
-            uint32_t lo = 0, hi = nlist;  // last l with ioff[l] <= idx (empty lists share their successor's offset)
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (wl.ioff[mid] <= idx) lo = mid; else hi = mid - 1;
+    // Items are handed to the scan in DESCENDING order of estimated cost (longest processing time first): the
+    // persistent CTAs claim them dynamically, so the scan ends on the cheapest items and every SM finishes within
+    // one small item of the others -- on a 1/8 shard (7 items per SM) the unordered tail cost ~10 % of the kernel.
+    // Cost ~ rows x (8 + queries probing the list): HBM time per row plus the per-(row, query) arithmetic.  A
+    // counting sort over logarithmic cost classes (3 mantissa bits) is all the precision the schedule needs.
+    auto item_class = [&](uint32_t l, uint32_t r) -> uint32_t {
+        const uint32_t npages = lt.page_off[l + 1] - lt.page_off[l];
+        const uint32_t npg = min(ppi, npages - r * ppi);
+        const uint32_t rows = min(npg * lt.page_rows, lt.rows[l] - r * ppi * lt.page_rows);
+        const float cost = (float)rows * (float)(8u + wl.gcount[l]);
+        int c = (int)(__float_as_uint(cost) >> 20) - (127 << 3);
+        c = max(0, min(c, (int)ITEM_CLASSES - 1));
+        return (ITEM_CLASSES - 1) - (uint32_t)c;  // class 0 = most expensive
+    };
+    // f(list, range) for every item, each item visited by exactly one thread (same thread in every pass)
+    auto for_each_item = [&](auto&& f) {
+        if (SMEM) {
+            // thread per item: the owning list is found by binary search in the (shared-memory) item offsets
+            const uint32_t total = wl.ioff[nlist];
+            for (uint32_t idx = tid; idx < total; idx += NT) {
+                uint32_t lo = 0, hi = nlist;  // last l with ioff[l] <= idx (empty lists share their successor's offset)
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (wl.ioff[mid] <= idx) lo = mid; else hi = mid - 1;
+                }
+                f(lo, idx - wl.ioff[lo]);
             }
-            write_item(lo, idx - wl.ioff[lo], idx);
+        } else {
+            for (uint32_t l = tid; l < nlist; l += NT) {
+                if (!wl.gcount[l]) continue;
+                const uint32_t nr = n_ranges(lt, l, ppi);
+                for (uint32_t r = 0; r < nr; ++r) f(l, r);
+            }
         }
-    } else {
-        for (uint32_t l = tid; l < nlist; l += NT) {
-            if (!wl.gcount[l]) continue;
-            const uint32_t nr = n_ranges(lt, l, ppi), o = wl.ioff[l];
-            for (uint32_t r = 0; r < nr; ++r) write_item(l, r, o + r);
+    };
+    for (uint32_t c = tid; c < ITEM_CLASSES; c += NT) s_cls[c] = 0;
+    __syncthreads();
+    for_each_item([&](uint32_t l, uint32_t r) { atomicAdd(&s_cls[item_class(l, r)], 1u); });
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the class counts (ITEM_CLASSES / 32 per lane)
+        constexpr uint32_t PER = ITEM_CLASSES / 32;
+        uint32_t sum = 0;
+        for (uint32_t i = 0; i < PER; ++i) sum += s_cls[tid * PER + i];
+        uint32_t x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (tid >= (uint32_t)o) x += y;
+        }
+        uint32_t run = x - sum;
+        for (uint32_t i = 0; i < PER; ++i) {
+            const uint32_t c = s_cls[tid * PER + i];
+            s_cls[tid * PER + i] = run;
+            run += c;
         }
     }
+    __syncthreads();
+    for_each_item([&](uint32_t l, uint32_t r) { write_item(l, r, atomicAdd(&s_cls[item_class(l, r)], 1u)); });
 }
 
 // ------------------------------------------------------------ 2. list scan
@@ -905,9 +948,10 @@ struct MergeParams {
     const uint32_t* part_cnt;   // valid entries per slot; null: k, padding skipped
     const uint32_t* qthr;       // per-query bound on the final k-th distance proved by the scan (ordered keys), or null
     uint32_t nq, np, k, P;
-    float* out_d;
+    float* out_d;      // may be null when the result is only published
     uint64_t* out_i;
     uint32_t* out_u32;
+    PublishTarget pub;  // sharded search: the merged local top-k goes straight into the peers' mailboxes
 };
 
 constexpr uint32_t MERGE_W = 256;  // per-warp scratch entries for the per-list selection
@@ -1107,23 +1151,26 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const MergeParams 
     }
     pool_compact_block(L2, P, k, true, d3, i3, s_scan);
     const uint32_t nc = cnt2;
-    for (uint32_t i = tid; i < k; i += MERGE_THREADS) {
-        const float d = i < nc ? d2[i] : FLT_MAX;
-        const uint64_t id = i < nc ? i2[i] : ID_PAD;
-        p.out_d[(size_t)q * k + i] = d;
-        p.out_i[(size_t)q * k + i] = id;
-        if (p.out_u32) p.out_u32[(size_t)q * k + i] = (id == ID_PAD) ? 0xffffffffu : (uint32_t)id;
+    if (p.out_d) {
+        for (uint32_t i = tid; i < k; i += MERGE_THREADS) {
+            const float d = i < nc ? d2[i] : FLT_MAX;
+            const uint64_t id = i < nc ? i2[i] : ID_PAD;
+            p.out_d[(size_t)q * k + i] = d;
+            p.out_i[(size_t)q * k + i] = id;
+            if (p.out_u32) p.out_u32[(size_t)q * k + i] = (id == ID_PAD) ? 0xffffffffu : (uint32_t)id;
+        }
     }
+    if (p.pub.enabled) publish_query(p.pub, q, k, d2, i2, nc, MERGE_THREADS);
 }
 
 uint32_t merge_pool_size(uint32_t k) { return next_pow2(k * 2 < 1024 ? 1024 : k * 2); }
 
 template <int NJ>
 int32_t launch_scan(const ScanParams& sp, uint32_t grid, uint32_t smem, cudaStream_t stream) {
-    static bool configured[8] = {false};
+    static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 8 && !configured[dev]) {
+    if (dev < 16 && !configured[dev]) {
         VDB_CUDA_TRY(cudaFuncSetAttribute(scan_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)SMEM_BUDGET));
         configured[dev] = true;
@@ -1199,10 +1246,9 @@ void ScanWorkspace::release() {
     *this = ScanWorkspace();
 }
 
-int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
-                    uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
-                    bool has_ids, float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
-                    ScanLaunchInfo* info, cudaEvent_t* ev) {
+int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev, uint32_t np,
+                  uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, bool has_ids, uint32_t max_ctas,
+                  ScanWorkspace& ws, ScanPlan* out) {
     VDB_REQUIRE(k >= 1 && k <= MAX_K, "k must be in [1, 2048]");
     VDB_REQUIRE(lt.ld % 4 == 0 && lt.ld >= 4 && lt.ld <= 2048, "row stride must be a multiple of 4 floats, <= 2048");
     VDB_REQUIRE(lt.page_rows % STAGE_ROWS == 0, "page_rows must be a multiple of 16");
@@ -1210,7 +1256,6 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     VDB_REQUIRE(nq >= 1 && np >= 1 && ppi >= 1, "empty search");
     const uint64_t npairs64 = (uint64_t)nq * np;
     VDB_REQUIRE(npairs64 < (1ull << 31) && max_slots < (1ull << 31), "search too large for one call");
-    const uint32_t npairs = (uint32_t)npairs64;
 
     // shared-memory plan: pool size P (per query), query tile QT (fixed by the row width), ring depth S
     const uint32_t nj_need = (lt.ld / 4 + 31) / 32;
@@ -1219,7 +1264,7 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     // CTA tile = register tile (tile_queries) x warp groups, as wide as shared memory allows with a 3-deep
     // ring; shrunk below the register tile when the pools of a large k need the room
     const uint32_t QTreg = (uint32_t)tile_queries((int)NJ);
-    uint32_t P = next_pow2(std::max(k + 64, 2 * k));
+    const uint32_t P = next_pow2(std::max(k + 64, 2 * k));
     const uint32_t stage_rows = lt.ld > 1024 ? STAGE_ROWS / 2 : STAGE_ROWS;
     auto fits = [&](uint32_t s_, uint32_t qt_) { return scan_smem_bytes(lt.ld, s_, qt_, P, stage_rows) <= SMEM_BUDGET; };
     uint32_t ngroups = CONSUMER_WARPS;
@@ -1229,39 +1274,61 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     uint32_t S = 4;
     while (S > 2 && !fits(S, QT)) --S;
     VDB_REQUIRE(fits(S, QT), "dimension * k too large for the scan kernel's shared memory");
-    const uint32_t check_interval = std::max(1u, std::min(64u, (P - k) / STAGE_ROWS));
-    const uint32_t smem = scan_smem_bytes(lt.ld, S, QT, P, stage_rows);
 
-    VDB_TRY(ws.reserve(lt.nlist, npairs, std::max<uint64_t>(max_slots, 1), k, nq));
+    VDB_TRY(ws.reserve(lt.nlist, (uint32_t)npairs64, std::max<uint64_t>(max_slots, 1), k, nq));
 
+    int dev = 0, sms = NUM_SMS_B200;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t grid = std::min<uint64_t>((uint64_t)sms, std::max<uint64_t>(max_slots, 1));
+    if (max_ctas) grid = std::min<uint64_t>(grid, max_ctas);
+
+    ScanPlan pl;
+    pl.lt = lt;
+    pl.queries = queries_dev;
+    pl.probes = probes_dev;
+    pl.nq = nq; pl.np = np; pl.k = k; pl.metric = metric; pl.ppi = ppi;
+    pl.has_ids = has_ids;
+    pl.info = ScanLaunchInfo{QT, P, S, NJ, (uint32_t)grid, scan_smem_bytes(lt.ld, S, QT, P, stage_rows),
+                             std::max(1u, std::min(64u, (P - k) / STAGE_ROWS))};
+    pl.stage_rows = stage_rows;
+    *out = pl;
+    return VDB_OK;
+}
+
+int32_t scan_enqueue_groups(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t stream) {
+    const ListTable& lt = pl.lt;
+    const uint32_t npairs = pl.nq * pl.np;
     WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats,
-                ws.qthr, nq};
-    if (ev) cudaEventRecord(ev[0], stream);
+                ws.qthr, pl.nq};
     // running top-k of every query: "empty" = (3.39e38, UINT64_MAX), i.e. bytes 0x7f / 0xff; locks open
-    VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_d, 0x7f, (size_t)nq * k * 4, stream));
-    VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_i, 0xff, (size_t)nq * k * 8, stream));
-    VDB_CUDA_TRY(cudaMemsetAsync(ws.glock, 0, (size_t)nq * 4, stream));
+    VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_d, 0x7f, (size_t)pl.nq * pl.k * 4, stream));
+    VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_i, 0xff, (size_t)pl.nq * pl.k * 8, stream));
+    VDB_CUDA_TRY(cudaMemsetAsync(ws.glock, 0, (size_t)pl.nq * 4, stream));
     if (lt.nlist <= 8192) {
         const uint32_t gsm = 4 * (lt.nlist + 1) * 4;
-        static bool gconf[8] = {false};
+        static bool gconf[16] = {false};
         int gdev = 0;
         cudaGetDevice(&gdev);
-        if (gdev < 8 && !gconf[gdev]) {
+        if (gdev < 16 && !gconf[gdev]) {
             VDB_CUDA_TRY(cudaFuncSetAttribute(build_groups_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               4 * 8193 * 4));
             VDB_CUDA_TRY(cudaFuncSetAttribute(build_groups_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
             gconf[gdev] = true;
         }
-        build_groups_kernel<true><<<1, 1024, gsm, stream>>>(lt, probes_dev, npairs, ppi, wl);
+        build_groups_kernel<true><<<1, 1024, gsm, stream>>>(lt, pl.probes, npairs, pl.ppi, wl);
     } else {
-        build_groups_kernel<false><<<1, 1024, 0, stream>>>(lt, probes_dev, npairs, ppi, wl);
+        build_groups_kernel<false><<<1, 1024, 0, stream>>>(lt, pl.probes, npairs, pl.ppi, wl);
     }
     VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
 
+int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t stream) {
     ScanParams sp;
-    sp.lt = lt;
-    sp.queries = queries_dev;
+    sp.lt = pl.lt;
+    sp.queries = pl.queries;
     sp.items = ws.items;
     sp.totals = ws.totals;
     sp.gpairs = ws.gpairs;
@@ -1273,20 +1340,15 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
     sp.gtop_d = ws.gtop_d;
     sp.gtop_i = ws.gtop_i;
     sp.glock = ws.glock;
-    sp.k = k; sp.P = P; sp.S = S; sp.np = np;
-    sp.has_ids = has_ids ? 1u : 0u;
-    sp.qt = QT;
-    sp.stage_rows = stage_rows;
+    sp.k = pl.k; sp.P = pl.info.P; sp.S = pl.info.S; sp.np = pl.np;
+    sp.has_ids = pl.has_ids ? 1u : 0u;
+    sp.qt = pl.info.QT;
+    sp.stage_rows = pl.stage_rows;
     sp.work_counter = ws.totals + 2;
-    sp.check_interval = check_interval;
-    sp.metric = metric;
-
-    int dev = 0, sms = NUM_SMS_B200;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, std::max<uint64_t>(max_slots, 1));
-    if (ev) cudaEventRecord(ev[1], stream);
-    switch (NJ) {
+    sp.check_interval = pl.info.check_interval;
+    sp.metric = pl.metric;
+    const uint32_t grid = pl.info.grid, smem = pl.info.smem_bytes;
+    switch (pl.info.NJ) {
         case 1: VDB_TRY(launch_scan<1>(sp, grid, smem, stream)); break;
         case 2: VDB_TRY(launch_scan<2>(sp, grid, smem, stream)); break;
         case 4: VDB_TRY(launch_scan<4>(sp, grid, smem, stream)); break;
@@ -1295,40 +1357,61 @@ int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, 
         case 12: VDB_TRY(launch_scan<12>(sp, grid, smem, stream)); break;
         default: VDB_TRY(launch_scan<16>(sp, grid, smem, stream)); break;
     }
+    return VDB_OK;
+}
 
-    if (ev) cudaEventRecord(ev[2], stream);
-    MergeParams mp;
-    mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot; mp.part_cnt = ws.part_cnt;
-    mp.qthr = ws.qthr;
-    mp.nq = nq; mp.np = np; mp.k = k; mp.P = merge_pool_size(k);
-    mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = out_u32;
-    const uint32_t msmem = mp.P * 36 + (MERGE_THREADS / 32) * MERGE_W * 12;
-    static bool mconf[8] = {false};
-    if (dev < 8 && !mconf[dev]) {
-        VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36 + (MERGE_THREADS / 32) * MERGE_W * 12));
+static int32_t configure_merge() {
+    static bool mconf[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !mconf[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          4096 * 36 + (MERGE_THREADS / 32) * MERGE_W * 12));
         // every kernel of the search pipeline asks for the same (maximum) shared-memory carve-out, so the SMs
-        // are not reconfigured between the back-to-back launches
+        // are not reconfigured between launches
         VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
         mconf[dev] = true;
     }
-    merge_kernel<<<nq, MERGE_THREADS, msmem, stream>>>(mp);
+    return VDB_OK;
+}
+
+int32_t scan_enqueue_merge(const ScanPlan& pl, ScanWorkspace& ws, float* out_d, uint64_t* out_i, uint32_t* out_u32,
+                           const PublishTarget* pub, cudaStream_t stream) {
+    MergeParams mp{};
+    mp.part_d = ws.part_d; mp.part_i = ws.part_i; mp.pair_slot = ws.pair_slot; mp.part_cnt = ws.part_cnt;
+    mp.qthr = ws.qthr;
+    mp.nq = pl.nq; mp.np = pl.np; mp.k = pl.k; mp.P = merge_pool_size(pl.k);
+    mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = out_u32;
+    if (pub) mp.pub = *pub;
+    VDB_TRY(configure_merge());
+    const uint32_t msmem = mp.P * 36 + (MERGE_THREADS / 32) * MERGE_W * 12;
+    merge_kernel<<<pl.nq, MERGE_THREADS, msmem, stream>>>(mp);
     VDB_CUDA_TRY(cudaGetLastError());
-    if (ev) cudaEventRecord(ev[3], stream);
-    if (info) *info = ScanLaunchInfo{QT, P, S, NJ, grid, smem, check_interval};
+    return VDB_OK;
+}
+
+int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
+                    uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
+                    bool has_ids, float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
+                    ScanLaunchInfo* info) {
+    ScanPlan pl;
+    VDB_TRY(scan_plan(lt, queries_dev, nq, probes_dev, np, k, metric, ppi, max_slots, has_ids, 0, ws, &pl));
+    VDB_TRY(scan_enqueue_groups(pl, ws, stream));
+    VDB_TRY(scan_enqueue_scan(pl, ws, stream));
+    VDB_TRY(scan_enqueue_merge(pl, ws, out_d, out_i, out_u32, nullptr, stream));
+    if (info) *info = pl.info;
     return VDB_OK;
 }
 
 int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts, uint32_t nq, uint32_t k,
                     float* out_d, uint64_t* out_i, cudaStream_t stream) {
     VDB_REQUIRE(k >= 1 && k <= MAX_K && parts >= 1 && nq >= 1, "merge: bad shape");
-    MergeParams mp;
+    MergeParams mp{};
     mp.part_d = dparts; mp.part_i = iparts; mp.pair_slot = nullptr; mp.part_cnt = nullptr; mp.qthr = nullptr;
     mp.nq = nq; mp.np = parts; mp.k = k; mp.P = merge_pool_size(k);
     mp.out_d = out_d; mp.out_i = out_i; mp.out_u32 = nullptr;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    VDB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 36 + (MERGE_THREADS / 32) * MERGE_W * 12));
+    VDB_TRY(configure_merge());
     merge_kernel<<<nq, MERGE_THREADS, mp.P * 36 + (MERGE_THREADS / 32) * MERGE_W * 12, stream>>>(mp);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;

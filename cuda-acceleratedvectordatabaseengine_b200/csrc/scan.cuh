@@ -50,15 +50,41 @@ struct ScanLaunchInfo {
     uint32_t QT, P, S, NJ, grid, smem_bytes, check_interval;
 };
 
+struct PublishTarget;  // exchange.cuh
+
+// One search's launch plan: the scan kernel's shared-memory layout for this shape plus the call's arguments.
+struct ScanPlan {
+    ListTable lt;
+    const float* queries;
+    const uint32_t* probes;
+    uint32_t nq, np, k, ppi, stage_rows;
+    int metric;
+    bool has_ids;
+    ScanLaunchInfo info;
+};
+
 // probes_dev: [nq][np] list ids (entries >= nlist or naming empty lists are
 // skipped).  max_slots: caller's upper bound on sum over pairs of page ranges.
 // ppi: pages per scan item.  has_ids: every page of `lt` carries an id block
-// (false for flat views, whose ids are implicit or in lt.ids_flat).  Results (device): out_d/out_i [nq][k]; optional
-// out_u32 receives the ids narrowed to 32 bits (probe lists).
+// (false for flat views, whose ids are implicit or in lt.ids_flat).  max_ctas: cap on the persistent scan
+// grid (0 = one CTA per SM) -- a pipelined index leaves a few SMs to the kernels of the neighbouring batches.
+// The three phases may go to different streams (the caller orders them with events):
+//   groups  memsets + build_groups_kernel (needs the probes)
+//   scan    scan_kernel
+//   merge   merge_kernel -> out_d/out_i [nq][k] (device; optional out_u32 = ids narrowed to 32 bits), and/or
+//           straight into the peers' mailboxes (`pub`)
+int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev, uint32_t np,
+                  uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, bool has_ids, uint32_t max_ctas,
+                  ScanWorkspace& ws, ScanPlan* out);
+int32_t scan_enqueue_groups(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t stream);
+int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t stream);
+int32_t scan_enqueue_merge(const ScanPlan& pl, ScanWorkspace& ws, float* out_d, uint64_t* out_i, uint32_t* out_u32,
+                           const PublishTarget* pub, cudaStream_t stream);
+// all three on one stream
 int32_t scan_search(const ListTable& lt, const float* queries_dev, uint32_t nq, const uint32_t* probes_dev,
                     uint32_t np, uint32_t k, int metric, uint32_t ppi, uint64_t max_slots, ScanWorkspace& ws,
                     bool has_ids, float* out_d, uint64_t* out_i, uint32_t* out_u32, cudaStream_t stream,
-                    ScanLaunchInfo* info = nullptr, cudaEvent_t* ev = nullptr);  // ev[0..3]: start, scan start, scan end, merge end
+                    ScanLaunchInfo* info = nullptr);
 
 // merge_results across `parts` blocks of [nq][k]
 int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts, uint32_t nq, uint32_t k,

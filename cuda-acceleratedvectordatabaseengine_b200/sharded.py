@@ -101,6 +101,13 @@ class PeerExchange:
         """second half: wait for the peers' blocks of the published batch and merge them into Do, Io"""
         self.pkg._check(self.pkg.lib().vdb_exchange_collect(self._h, Do.data_ptr(), Io.data_ptr(), stream))
 
+    def check(self):
+        """raise if a call timed out waiting for a peer (valid after synchronising with the call's stream)"""
+        self.pkg._check(self.pkg.lib().vdb_exchange_status(self._h))
+
+    def reset(self):
+        self.pkg._check(self.pkg.lib().vdb_exchange_reset(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             self.pkg.lib().vdb_exchange_destroy(self._h)
@@ -119,7 +126,10 @@ class ShardedIVFFlatIndex:
     train(): every rank trains on the same rows (deterministic -> identical centroids and owner table);
     add():   every rank sees the batch, assigns it, and keeps only the rows of the lists it owns;
     add_distributed(): each rank assigns its own slice, one all-to-all routes rows to the owning ranks;
-    search(): local search + all-gather + merge; every rank returns the full answer."""
+    search(): collective; every rank returns the full answer.  With the peer-memory exchange the index itself is
+              collective (vdb_index_attach_exchange): the shard's merge kernel stores its top-k into the peers'
+              mailboxes and a collect kernel merges the world's blocks, pipelined over batches by search_submit /
+              search_wait.  Otherwise: local search + NCCL all-gather + merge kernel."""
 
     def __init__(self, pkg, config, group=None, exchange="auto", max_nq=1024, max_k=64):
         self.pkg, self.group = pkg, group
@@ -140,18 +150,38 @@ class ShardedIVFFlatIndex:
             except RuntimeError:
                 if not auto:
                     raise  # asked for explicitly: report it; "auto" falls back to the all-gather path
+        self._attached = False
+        self._synced = False
+        self._set_attached(self.exchange is not None)
+
+    def _set_attached(self, on):
+        if on != self._attached:
+            self.local.attach_exchange(self.exchange._h if on else None)
+            self._attached = on
+
+    def _sync_once(self):
+        # ranks finish building at different times and the exchange kernel gives a peer 20 s to show up: meet
+        # once after every build step before the first collective search
+        if not self._synced and self.world > 1:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self._synced = True
 
     def train(self, vectors):
         self.local.train(vectors)
+        self._synced = False
 
     def add(self, vectors, ids=None):
         self.local.add(vectors, ids)
+        self._synced = False
 
     def add_distributed(self, vectors, ids):
         """Data-parallel add: every rank passes ITS OWN slice of the batch (CUDA tensors [n_r][dim] f32 and
         [n_r] int64 ids).  Each rank assigns only its slice (tensor cores), rows are routed to the ranks that
         own their lists with one all-to-all over NVLink, and land in the owners' HBM pages."""
         world = self.world
+        self._synced = False
         a = self.local.assign_device(vectors)
         if world == 1:
             self.local.add_assigned(vectors.contiguous(), ids.contiguous(), a, vectors.shape[0])
@@ -175,25 +205,49 @@ class ShardedIVFFlatIndex:
         dist.all_reduce(total, group=self.group)
         self.local.add_assigned(rv, ri, ra, int(total.item()))
 
+    def _fits_mailbox(self, nq, k):
+        ex = self.exchange
+        return ex is not None and nq <= ex.max_nq and k <= ex.max_k
+
     def search_device(self, queries, nprobe, k, stream=None):
-        """queries: CUDA tensor [nq][dim]; returns CUDA tensors ([nq][k] f32, [nq][k] i64 view of u64 ids)."""
+        """queries: float32 CUDA tensor [nq][dim]; returns CUDA tensors ([nq][k] f32, [nq][k] i64 view of u64 ids)."""
         s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        queries = self.local._rows(queries)
         nq = queries.shape[0]
         D = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
         I = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
-        self.local.search_async(queries, nprobe, k, D, I, s)
-        if self.world == 1:
+        self._sync_once()
+        if self.world == 1 or self._fits_mailbox(nq, k):
+            self._set_attached(self.exchange is not None)
+            self.local.search_async(queries, nprobe, k, D, I, s)  # collective inside when the exchange is attached
             return D, I
-        ex = self.exchange
-        if ex is not None and nq <= ex.max_nq and k <= ex.max_k:
-            return ex.merge_topk(D, I, s)
+        self._set_attached(False)
+        self.local.search_async(queries, nprobe, k, D, I, s)
         Dg, Ig = gather_topk(D, I, self.group)
         return self.pkg.merge_topk(Dg, Ig, s)
 
+    def search_submit(self, queries, nprobe, k, distances, indices):
+        """pipelined collective search (same order on every rank); see IVFFlatIndex.search_submit"""
+        nq = queries.shape[0]
+        if self.world > 1 and not self._fits_mailbox(nq, k):
+            raise ValueError("search_submit on a sharded index needs the peer-memory exchange and nq, k within its mailbox")
+        self._sync_once()
+        self._set_attached(self.exchange is not None)
+        return self.local.search_submit(queries, nprobe, k, distances, indices)
+
+    def search_wait(self, ticket):
+        self.local.search_wait(ticket)
+
     def search(self, queries, nprobe, k):
-        """host or device queries in, numpy out on every rank"""
-        q = queries if hasattr(queries, "data_ptr") else torch.from_numpy(queries)
+        """host (numpy, any float dtype / layout) or device queries in, numpy out on every rank"""
+        if hasattr(queries, "data_ptr"):
+            q = self.local._rows(queries.float())
+        else:
+            q = torch.from_numpy(self.local._rows(queries))  # float32, contiguous, [nq][dim]
         D, I = self.search_device(q.cuda(non_blocking=True), nprobe, k)
+        torch.cuda.current_stream().synchronize()
+        if self.exchange is not None:
+            self.exchange.check()  # a peer that never showed up: raise instead of returning padding
         return D.cpu().numpy(), I.cpu().numpy().view("uint64")
 
     def get_total_vectors(self):
@@ -204,3 +258,12 @@ class ShardedIVFFlatIndex:
                          device="cuda" if torch.cuda.is_available() else "cpu")
         dist.all_reduce(t, group=self.group)
         return int(t.item())
+
+    def close(self):
+        if getattr(self, "local", None) is not None:
+            if self._attached:
+                self._set_attached(False)
+            self.local.close()
+        if self.exchange is not None:
+            self.exchange.close()
+            self.exchange = None

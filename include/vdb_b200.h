@@ -72,7 +72,10 @@ typedef struct {
     uint32_t page_rows;      /* rows per inverted-list page, 0 = auto */
     uint32_t shard_rank;     /* this process holds the lists whose owner is shard_rank (see vdb_index_get_owners) */
     uint32_t shard_count;    /* 1 = unsharded, at most 255 */
-    uint32_t reserved[5];
+    uint32_t pipeline_depth; /* searches in flight (vdb_index_search_submit), 0 = 4, at most 8 */
+    uint32_t reserve_sms;    /* SMs a pipelined list scan leaves to the coarse / merge kernels of the neighbouring
+                                batches, 0 = 8, 0xffffffff = none */
+    uint32_t reserved[3];
 } vdb_config;
 
 typedef struct {
@@ -92,6 +95,7 @@ typedef struct {
     uint64_t unique_rows;
     uint64_t scan_items;
     uint64_t bytes_per_row; /* 4*dim + 8 */
+    uint64_t scan_ctas;     /* persistent CTAs of the list-scan launch */
 } vdb_search_stats;
 
 typedef struct vdb_index vdb_index;
@@ -125,13 +129,38 @@ int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64
  * nprobe is clamped to nlist.  Thread-safe against concurrent searches. */
 int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
                          float* distances, uint64_t* indices);
-/* Same, device pointers only, enqueued on `stream` (a cudaStream_t) without a
- * host synchronisation: the form the sharded path and the benchmark use.  The
- * index owns one search workspace: a search enqueued on a different stream than
- * the previous one waits on the device for that one to finish (correct from any
- * stream, but searches of one index do not overlap each other). */
+/* Same, device pointers only, every launch enqueued on `stream` (a cudaStream_t)
+ * in stream order, without a host synchronisation of this call (the call may
+ * block on the search issued pipeline_depth calls earlier, whose scratch it
+ * reuses).  Searches enqueued on different streams overlap. */
 int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe,
                                uint32_t k, float* distances_dev, uint64_t* indices_dev, void* stream);
+/* Pipelined search: the serving form (the reference server's intended 64-query
+ * batches in flight, query_service.h:26-27).  submit() enqueues the batch on the
+ * index's own streams and returns a ticket at once; up to pipeline_depth batches
+ * are in flight and overlap: while batch i's list scan streams from HBM, batch
+ * i+1's coarse selection / probe grouping and batch i-1's merge (and cross-GPU
+ * exchange) run on the SMs the scan leaves free, and batch i+1's scan CTAs start
+ * on the SMs batch i's tail releases.  queries / outputs may be host or device
+ * memory; a device query array must already hold its values and, like the
+ * outputs, stay valid until the ticket is waited for.  wait() blocks the host
+ * until the batch is complete (host outputs are filled in by then);
+ * wait_stream() instead makes `stream` wait for it (device outputs).  Results
+ * are identical to vdb_index_search; vdb_index_search is submit + wait, so
+ * concurrent host threads overlap the same way. */
+int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
+                                float* distances, uint64_t* indices, uint64_t* ticket);
+int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket);
+int32_t vdb_index_search_wait_stream(vdb_index* ix, uint64_t ticket, void* stream);
+/* Allocate every search buffer for batches of up to (max_nq, max_nprobe, max_k)
+ * now (and again after each add()), so that no allocation happens inside a search. */
+int32_t vdb_index_reserve_search(vdb_index* ix, uint32_t max_nq, uint32_t max_nprobe, uint32_t max_k);
+/* One process per GPU: attach this rank's connected vdb_exchange (borrowed, may
+ * be NULL to detach).  From then on every search is collective -- same calls in
+ * the same order on every rank -- and returns the merged result of all shards:
+ * the merge kernel stores the shard's top-k straight into the peers' mailboxes
+ * and a small collect kernel merges the world's blocks. */
+int32_t vdb_index_attach_exchange(vdb_index* ix, vdb_exchange* ex);
 /* select_nprobe_lists, ivf_flat_index.cpp:298-336: [nq][min(nprobe,nlist)] list ids. */
 int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe,
                                 uint32_t* lists);
@@ -151,11 +180,14 @@ int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out /* [list 
 int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out);
 int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out);
 /* Profiling for the roofline report: when enabled, CUDA events on the launching
- * stream bracket, for every search, [0] the coarse step, [1] probe grouping,
- * [2] the list-scan kernel, [3] the merge.  read_profile synchronises, returns
- * the summed milliseconds since the last call and the number of searches. */
+ * streams bracket, for every search, [0] the coarse step, [1] probe grouping,
+ * [2] the list-scan kernel, [3] the merge (+ publish), [4] the cross-GPU collect;
+ * [5] = first scan start .. last scan end (the scan streams' busy time: with
+ * batches in flight consecutive scans overlap, so this, not the sum of [2], is
+ * the time the scans took).  read_profile synchronises, returns the summed
+ * milliseconds since the last call and the number of searches. */
 int32_t vdb_index_set_profiling(vdb_index* ix, int32_t enable);
-int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms /* [4] */, uint32_t* searches);
+int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms /* [8] */, uint32_t* searches);
 /* warmup_lists()/warmup_all() of the server contract (query_service.cpp:191,195):
  * lists are always HBM-resident here, so this only validates ids. */
 int32_t vdb_index_warmup(vdb_index* ix, const uint32_t* lists, uint32_t n);
@@ -189,8 +221,9 @@ int32_t vdb_merge_topk(const float* dist_parts_dev, const uint64_t* id_parts_dev
  * the rank's local [nq][k] block into every peer's mailbox, waits for the peers' blocks and merges -- instead of
  * two all-gathers plus vdb_merge_topk.  One process per GPU: create on every rank, pass the 64-byte handle of
  * every rank (rank order; e.g. from an all_gather of vdb_exchange_handle) to connect, then call merge_topk
- * collectively (same order and shapes on every rank).  world * max_k <= 4096.  A peer that never arrives makes
- * the call's results padded and the NEXT call return VDB_NCCL_ERROR (20 s timeout). */
+ * collectively (same order and shapes on every rank).  world * max_k <= 4096.  A peer that never arrives (20 s
+ * timeout) makes the call's results padded; vdb_exchange_status() -- after synchronising with the stream -- and
+ * every later call return VDB_NCCL_ERROR until vdb_exchange_reset(). */
 int32_t vdb_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint32_t max_nq, uint32_t max_k,
                             vdb_exchange** out);
 int32_t vdb_exchange_handle(vdb_exchange* ex, uint8_t* out64);
@@ -203,6 +236,13 @@ int32_t vdb_exchange_merge_topk(vdb_exchange* ex, const float* local_dist_dev, c
 int32_t vdb_exchange_publish(vdb_exchange* ex, const float* local_dist_dev, const uint64_t* local_ids_dev, uint32_t nq,
                              uint32_t k, void* stream);
 int32_t vdb_exchange_collect(vdb_exchange* ex, float* distances_dev, uint64_t* indices_dev, void* stream);
+/* Exchanges of ONE process (a single-process sharded index): `all` in rank order.  No IPC: the root's mailbox is
+ * addressed directly through peer access, every rank publishes into it and the root alone collects. */
+int32_t vdb_exchange_connect_local(vdb_exchange** all, uint32_t world, uint32_t root);
+/* VDB_NCCL_ERROR once a wait on a peer has timed out (valid after synchronising with the stream of the call);
+ * reset clears that state (all ranks must call it, then continue in step). */
+int32_t vdb_exchange_status(vdb_exchange* ex);
+int32_t vdb_exchange_reset(vdb_exchange* ex);
 int32_t vdb_exchange_destroy(vdb_exchange* ex);
 
 /* TransferManager rewrite (transfer_manager.h:42-88): one HBM slab and one

@@ -11,10 +11,64 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle_lib as O
-from parity import check_search
+from parity import check_search, ip_scale
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 WORLD = 2
+
+
+def _nccl_answer(ix, qd, nprobe, k):
+    """the portable exchange (local search, two all-gathers, merge kernel) on the same shards"""
+    ex, ix.exchange = ix.exchange, None
+    try:
+        return ix.search_device(qd, nprobe, k)
+    finally:
+        ix.exchange = ex
+
+
+def _case(pkg, sharded, rank, name, metric, dim, nlist, n, nq, nprobe, k, ntrain, centroids=None):
+    x = O.gaussian(31 + dim, n + nq, dim)
+    db, q = x[:n], x[n:]
+    ix = sharded.ShardedIVFFlatIndex(pkg, pkg.Config(dimension=dim, nlist=nlist, device=rank, metric=pkg.Metric(metric)))
+    if centroids is None:
+        ix.train(db[:ntrain])
+    else:
+        ix.local.centroids = centroids
+    owners = ix.local.owners()
+    # first half replicated add (every rank sees the rows), second half data-parallel add (each rank a slice)
+    half = n // 2
+    ix.add(db[:half], np.arange(half, dtype=np.uint64))
+    mine = np.arange(half + rank, n, WORLD)
+    ix.add_distributed(torch.from_numpy(db[mine]).cuda(), torch.from_numpy(mine.astype(np.int64)).cuda())
+    assert ix.get_total_vectors() == n
+    assert ix.exchange is not None, "an NCCL group of 2 ranks must take the peer-memory exchange"
+    D, I = ix.search(q.astype(np.float64), nprobe, k)  # any float dtype in: coerced, not reinterpreted
+    qd = torch.from_numpy(q).cuda()
+    for rep in range(3):
+        Dp, Ip = ix.search_device(qd, nprobe, k)
+        Dn, In = _nccl_answer(ix, qd, nprobe, k)
+        assert torch.equal(Dp, Dn) and torch.equal(Ip, In), f"{name}: p2p and nccl exchange differ (rep {rep})"
+    assert np.array_equal(Dp.cpu().numpy(), D) and np.array_equal(Ip.cpu().numpy().view(np.uint64), I)
+    # pipelined collective search: batches in flight, device and host buffers
+    bs = 8
+    starts = list(range(0, nq - bs + 1, bs))
+    Dd = [torch.empty((bs, k), dtype=torch.float32, device="cuda") for _ in starts]
+    Id = [torch.empty((bs, k), dtype=torch.int64, device="cuda") for _ in starts]
+    tickets = [ix.search_submit(qd[lo:lo + bs], nprobe, k, Dd[i], Id[i]) for i, lo in enumerate(starts)]
+    for t in tickets:
+        ix.search_wait(t)
+    for i, lo in enumerate(starts):
+        assert torch.equal(Dd[i], Dp[lo:lo + bs]) and torch.equal(Id[i], Ip[lo:lo + bs]), f"{name}: pipelined differs"
+    Dh = np.empty((bs, k), np.float32)
+    Ih = np.empty((bs, k), np.uint64)
+    ix.search_wait(ix.search_submit(np.ascontiguousarray(q[:bs]), nprobe, k, Dh, Ih))
+    assert np.array_equal(Dh, D[:bs]) and np.array_equal(Ih, I[:bs])
+    sizes = ix.local.list_sizes()
+    assert (sizes[owners != rank] == 0).all()
+    tot = torch.tensor([int(sizes.sum())], device="cuda")
+    dist.all_reduce(tot)
+    assert int(tot.item()) == n
+    return ix, db, q, D, I, owners
 
 
 def _worker(rank, port, ret):
@@ -25,76 +79,59 @@ def _worker(rank, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
     pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
     sharded = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200.sharded")
-    dim, nlist, n, nq, nprobe, k = 64, 48, 20000, 40, 12, 10
-    x = O.gaussian(31, n + nq, dim)
-    db, q = x[:n], x[n:]
-    ix = sharded.ShardedIVFFlatIndex(pkg, pkg.Config(dimension=dim, nlist=nlist, device=rank))
-    ix.train(db[:4000])
-    owners = ix.local.owners()
-    # first half replicated add (every rank sees the rows), second half data-parallel add (each rank a slice)
-    half = n // 2
-    ix.add(db[:half], np.arange(half, dtype=np.uint64))
-    mine = np.arange(half + rank, n, WORLD)
-    ix.add_distributed(torch.from_numpy(db[mine]).cuda(), torch.from_numpy(mine.astype(np.int64)).cuda())
-    assert ix.get_total_vectors() == n
-    assert ix.exchange is not None, "an NCCL group of 2 ranks must take the peer-memory exchange"
-    D, I = ix.search(q, nprobe, k)
-    # the portable exchange (two all-gathers + merge kernel) must give the same bits, call after call
-    qd = torch.from_numpy(q).cuda()
-    for rep in range(5):
-        Dp, Ip = ix.search_device(qd, nprobe, k)
-        ex, ix.exchange = ix.exchange, None
-        Dn, In = ix.search_device(qd, nprobe, k)
-        ix.exchange = ex
-        assert torch.equal(Dp, Dn) and torch.equal(Ip, In), f"p2p and nccl exchange differ (rep {rep})"
-    assert np.array_equal(Dp.cpu().numpy(), D) and np.array_equal(Ip.cpu().numpy().view(np.uint64), I)
-    # ragged shapes through the mailbox: fewer queries, larger k (padding travels too)
-    D2, I2 = ix.search_device(qd[:7], nlist, 64)
-    ex, ix.exchange = ix.exchange, None
-    D3, I3 = ix.search_device(qd[:7], nlist, 64)
-    ix.exchange = ex
-    assert torch.equal(D2, D3) and torch.equal(I2, I3)
-    # publish / collect as two launches with the next batch's search in between (one batch in flight)
-    ex = ix.exchange
-    st = torch.cuda.current_stream().cuda_stream
-    batches = [qd[lo:lo + 10] for lo in (0, 10, 20, 30)]
-    want = [ix.search_device(b, nprobe, k) for b in batches]
-    got, Dl, Il = [], [None, None], [None, None]
-    for i, b in enumerate(batches):
-        Dl[i & 1] = torch.empty((10, k), dtype=torch.float32, device="cuda")
-        Il[i & 1] = torch.empty((10, k), dtype=torch.int64, device="cuda")
-        ix.local.search_async(b, nprobe, k, Dl[i & 1], Il[i & 1], st)
-        if i:
-            Do = torch.empty((10, k), dtype=torch.float32, device="cuda")
-            Io = torch.empty((10, k), dtype=torch.int64, device="cuda")
-            ex.collect_into(Do, Io, st)
-            got.append((Do, Io))
-        ex.publish(Dl[i & 1], Il[i & 1], st)
-    Do = torch.empty((10, k), dtype=torch.float32, device="cuda")
-    Io = torch.empty((10, k), dtype=torch.int64, device="cuda")
-    ex.collect_into(Do, Io, st)
-    got.append((Do, Io))
-    torch.cuda.synchronize()
-    for (Dw, Iw), (Dg_, Ig_) in zip(want, got):
-        assert torch.equal(Dw, Dg_) and torch.equal(Iw, Ig_), "pipelined exchange differs from the one-launch form"
-    sizes = ix.local.list_sizes()
-    assert (sizes[owners != rank] == 0).all()
-    tot = torch.tensor([int(sizes.sum())], device="cuda")
-    dist.all_reduce(tot)
-    if rank == 0:
-        ora = O.OracleIndex(dim, nlist)
-        ora.train(db[:4000])
-        ora.add(db)
-        Dr, Ir = ora.search(q, nprobe, k)
-        try:
-            assert int(tot.item()) == n
+    try:
+        # --- L2, trained on the device
+        dim, nlist, n, nq, nprobe, k = 64, 48, 20000, 40, 12, 10
+        ix, db, q, D, I, owners = _case(pkg, sharded, rank, "l2", O.METRIC_L2, dim, nlist, n, nq, nprobe, k, 4000)
+        qd = torch.from_numpy(q).cuda()
+        # ragged shapes through the mailbox: fewer queries, larger k (padding travels too)
+        D2, I2 = ix.search_device(qd[:7], nlist, 64)
+        D3, I3 = _nccl_answer(ix, qd[:7], nlist, 64)
+        assert torch.equal(D2, D3) and torch.equal(I2, I3)
+        # beyond the mailbox (k > max_k): falls back to the all-gather path and still agrees with the oracle below
+        D4, I4 = ix.search_device(qd[:5], nprobe, 100)
+        if rank == 0:
+            ora = O.OracleIndex(dim, nlist)
+            ora.train(db[:4000])
+            ora.add(db)
+            Dr, Ir = ora.search(q, nprobe, k)
             check_search(D, I, Dr, Ir)
+            Dr4, Ir4 = ora.search(q[:5], nprobe, 100)
+            check_search(D4.cpu().numpy(), I4.cpu().numpy().view(np.uint64), Dr4, Ir4)
             full = ora.list_sizes().astype(np.int64)
             load = [int(full[owners == r].sum()) for r in range(WORLD)]
             assert max(load) - min(load) <= max(full.max(), n // 20), load  # byte-balanced ownership
+        ix.close()
+        # --- inner product (BASELINE configs[3] metric), sharded
+        dim, nlist, n, nq, nprobe, k = 96, 64, 16000, 24, 16, 10
+        ix, db, q, D, I, owners = _case(pkg, sharded, rank, "ip", O.METRIC_IP, dim, nlist, n, nq, nprobe, k, 3000)
+        if rank == 0:
+            ora = O.OracleIndex(dim, nlist, O.METRIC_IP)
+            ora.train(db[:3000])
+            ora.add(db)
+            Dr, Ir = ora.search(q, nprobe, k)
+            check_search(D, I, Dr, Ir, ip_scale(q, db))
+        ix.close()
+        # --- configs[3]-shaped but small: inner product, nlist 16384, nprobe 64 (centroids = data rows; the
+        # oracle's O(nlist^2) seeding is infeasible at this nlist)
+        dim, nlist, n, nq, nprobe, k = 16, 16384, 30000, 16, 64, 10
+        cent = O.gaussian(31 + dim, n + nq, dim)[:nlist].copy()
+        ix, db, q, D, I, owners = _case(pkg, sharded, rank, "c4-shaped", O.METRIC_IP, dim, nlist, n, nq, nprobe, k, 0,
+                                        centroids=cent)
+        if rank == 0:
+            ora = O.OracleIndex(dim, nlist, O.METRIC_IP)
+            ora.centroids = cent
+            ora.add(db)
+            Dr, Ir = ora.search(q, nprobe, k, 8)
+            check_search(D, I, Dr, Ir, ip_scale(q, db))
+        ix.close()
+        if rank == 0:
             ret.put("ok")
-        except AssertionError as e:
-            ret.put(f"FAIL {e}")
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        if rank == 0:
+            ret.put(f"FAIL rank {rank}: {e}\n{traceback.format_exc()}")
+        raise
     dist.barrier()
     dist.destroy_process_group()
 
