@@ -54,7 +54,7 @@ class _Stats(C.Structure):
     _fields_ = [("total_vectors", C.c_uint64), ("local_vectors", C.c_uint64), ("gpu_memory_bytes", C.c_uint64),
                 ("pages", C.c_uint64), ("dimension", C.c_uint32), ("nlist", C.c_uint32),
                 ("row_stride", C.c_uint32), ("page_rows", C.c_uint32), ("trained", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("metric", C.c_int32)]
 
 
 class _SearchStats(C.Structure):
@@ -70,6 +70,7 @@ ABI = {
     "vdb_version": (_i32, []),
     "vdb_config_default": (None, [C.POINTER(_Config)]),
     "vdb_index_create": (_i32, [C.POINTER(_Config), C.POINTER(_vp)]),
+    "vdb_index_create_sharded": (_i32, [C.POINTER(_Config), C.POINTER(_i32), _i32, C.POINTER(_vp)]),
     "vdb_index_destroy": (_i32, [_vp]),
     "vdb_index_train": (_i32, [_vp, _vp, _u64]),
     "vdb_index_add": (_i32, [_vp, _vp, _vp, _u64]),
@@ -89,6 +90,10 @@ ABI = {
     "vdb_index_set_owners": (_i32, [_vp, _vp]),
     "vdb_index_list_sizes": (_i32, [_vp, _vp]),
     "vdb_index_list_ids": (_i32, [_vp, _u32, _vp]),
+    "vdb_index_list_vectors": (_i32, [_vp, _u32, _vp]),
+    "vdb_index_append_list": (_i32, [_vp, _u32, _vp, _vp, _u64]),
+    "vdb_index_finish_load": (_i32, [_vp]),
+    "vdb_index_balance_owners": (_i32, [_vp, _vp]),
     "vdb_index_stats": (_i32, [_vp, C.POINTER(_Stats)]),
     "vdb_index_last_search_stats": (_i32, [_vp, C.POINTER(_SearchStats)]),
     "vdb_index_warmup": (_i32, [_vp, _vp, _u32]),
@@ -186,7 +191,8 @@ class Config:
     dimension: int = 0
     nlist: int = 0
     metric: Metric = Metric.L2
-    use_gpu: bool = True          # kept for source compatibility; False is rejected (no CPU path)
+    use_gpu: bool = True          # accepted either way and without effect: there is no CPU path, the GPU path
+                                  # returns what the reference's CPU path returns (test/simple_test.cpp:114 sets False)
     max_gpu_memory: int = 0       # 0 = uncapped; the reference default of 8 GiB would not hold the headline index
     device: int = 0
     train_mode: TrainMode = TrainMode.AUTO
@@ -194,6 +200,7 @@ class Config:
     page_rows: int = 0
     shard_rank: int = 0
     shard_count: int = 1
+    devices: tuple = ()           # more than one entry: ONE process, one list shard per device (create_sharded)
     pipeline_depth: int = 0       # searches in flight (search_submit), 0 = 4
     reserve_sms: int = 0          # SMs a pipelined scan leaves to the neighbouring batches' small kernels, 0 = 8
 
@@ -208,8 +215,6 @@ class SearchParams:
 
 class IVFFlatIndex:
     def __init__(self, config, tm=None):
-        if not config.use_gpu:
-            raise ValueError("use_gpu=False: this implementation has no CPU path")
         l = lib()
         c = _Config()
         l.vdb_config_default(C.byref(c))
@@ -220,7 +225,13 @@ class IVFFlatIndex:
         self.config = config
         self._tm = tm  # borrowed, like the reference's TransferManager*
         self._h = _vp()
-        _check(l.vdb_index_create(C.byref(c), C.byref(self._h)))
+        if len(config.devices) > 1:
+            devs = (_i32 * len(config.devices))(*config.devices)
+            _check(l.vdb_index_create_sharded(C.byref(c), devs, len(config.devices), C.byref(self._h)))
+        else:
+            if len(config.devices) == 1:
+                c.device = config.devices[0]
+            _check(l.vdb_index_create(C.byref(c), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -402,6 +413,13 @@ class IVFFlatIndex:
         out = np.empty(n, np.uint64)
         if n:
             _check(lib().vdb_index_list_ids(self._h, l, _ptr(out)))
+        return out
+
+    def list_vectors(self, l):
+        n = int(self.list_sizes()[l])
+        out = np.empty((n, self.config.dimension), np.float32)
+        if n:
+            _check(lib().vdb_index_list_vectors(self._h, l, _ptr(out)))
         return out
 
     def select_nprobe(self, queries, nprobe):

@@ -216,7 +216,7 @@ int32_t exchange_begin_publish(vdb_exchange* ex, uint32_t nq, uint32_t k, Publis
     VDB_TRY(check_healthy(ex));
     fill_target(ex, ex->epoch + 1, t);
     ++ex->epoch;  // the caller's launch is what publishes; a failed launch there is fatal for the index anyway
-    ex->pending = true;
+    ex->pending = !(ex->root_only && ex->rank != ex->root);  // only the root of a root-only exchange collects
     ex->pending_nq = nq;
     ex->pending_k = k;
     return VDB_OK;

@@ -348,6 +348,10 @@ int32_t vdb::index_finish_slot(vdb_index* ix, SearchSlot& s) {
 }
 
 int32_t vdb::index_acquire_slot(vdb_index* ix, SearchSlot** out, uint64_t* ticket) {
+    if (ix->tables_dirty) {
+        ix->tables_dirty = false;
+        VDB_TRY(index_upload_list_tables(ix));
+    }
     const uint64_t t = ++ix->next_ticket;
     SearchSlot& s = ix->slots[t % ix->depth];
     VDB_TRY(ensure_slot_events(s));
@@ -443,6 +447,7 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
 
     // ---- back: merge (+ publish into the peers' mailboxes, + collect), results to the caller
     nvtxRangePushA("vdb.search.back");
+    if (st.back_wait) VDB_CUDA_TRY(cudaStreamWaitEvent(st.back, st.back_wait, 0));
     if (prof) cudaEventRecord(s.tm[5], st.back);
     float* od = distances;
     uint64_t* oi = indices;
@@ -490,6 +495,22 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
     return VDB_OK;
 }
 
+// vdb_index_append_list defers the upload of the list tables (one per stored list would be quadratic)
+static int32_t flush_tables(vdb_index* ix) {
+    if (!ix->tables_dirty) return VDB_OK;
+    ix->tables_dirty = false;
+    return index_upload_list_tables(ix);
+}
+
+SearchStreams vdb::index_pipeline_streams(vdb_index* ix, uint64_t ticket) {
+    return SearchStreams{ix->s_front, ix->s_scan[ticket & 1], ix->s_back, true, nullptr};
+}
+
+void vdb::index_choose_ppi(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t k, uint32_t* ppi,
+                           uint32_t* nq_chunk) {
+    choose_ppi(ix, nq, np, k, ppi, nq_chunk);
+}
+
 namespace {
 
 // every slot's buffers for searches of up to (rs_nq, rs_np, rs_k), so that no cudaMalloc (an implicit device
@@ -520,7 +541,7 @@ int32_t reserve_slots(vdb_index* ix) {
 }
 
 SearchStreams pipeline_streams(vdb_index* ix, uint64_t ticket) {
-    return SearchStreams{ix->s_front, ix->s_scan[ticket & 1], ix->s_back, true};
+    return SearchStreams{ix->s_front, ix->s_scan[ticket & 1], ix->s_back, true, nullptr};
 }
 
 // the shapes one pass cannot take (partial-result buffer) are split over query chunks, each a pass of its own
@@ -657,6 +678,7 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
 }
 
 int32_t vdb_index_destroy(vdb_index* ix) {
+    if (ix && ix->composite) return composite_destroy(ix);
     if (!ix) return VDB_OK;
     {
         DeviceGuard g(ix->device);
@@ -668,7 +690,12 @@ int32_t vdb_index_destroy(vdb_index* ix) {
         ix->assign_buf.release(); ix->hist_buf.release(); ix->fill_buf.release(); ix->stage_buf.release();
         ix->ids_stage.release(); ix->d_owner.release();
         ix->tc_assign.release();
-        for (auto& s : ix->slots) {
+        SearchSlot* all_slots[MAX_SEARCH_SLOTS + 1];
+        for (uint32_t i = 0; i < MAX_SEARCH_SLOTS; ++i) all_slots[i] = &ix->slots[i];
+        all_slots[MAX_SEARCH_SLOTS] = &ix->aux_slot;
+        for (SearchSlot* sp : all_slots) {
+            SearchSlot& s = *sp;
+            s.q_raw.release();
             s.ws_scan.release(); s.ws_coarse.release();
             s.q_buf.release(); s.dots.release(); s.coarse_d.release(); s.out_d.release();
             s.coarse_i.release(); s.out_i.release(); s.probes.release(); s.zero_probes.release();
@@ -689,6 +716,10 @@ int32_t vdb_index_destroy(vdb_index* ix) {
 }
 
 int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(vectors && n >= 1, "train: no vectors");
+        return composite_train(ix, vectors, n);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(vectors && n >= 1, "train: no vectors");
     VDB_REQUIRE(n < 0xffffffffull, "train: at most 2^32-2 training vectors");
@@ -745,6 +776,7 @@ int32_t vdb_index_train(vdb_index* ix, const float* vectors, uint64_t n) {
 // add() and add_assigned() share everything but the assignment step
 static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids, const uint32_t* assigned,
                         uint64_t n, uint64_t counted) {
+    ix->tables_dirty = false;  // every chunk below uploads the tables anyway
     const uint64_t chunk_rows = std::max<uint64_t>(1024, ADD_CHUNK_BYTES / (ix->ld * 4ull));
     const bool ids_dev = is_device_ptr(ids);
     for (uint64_t lo = 0; lo < n; lo += chunk_rows) {
@@ -809,6 +841,11 @@ static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids
 }
 
 int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
+    if (ix && ix->composite) {
+        if (n == 0) return VDB_OK;
+        VDB_REQUIRE(vectors, "add: null vectors");
+        return composite_add(ix, vectors, ids, n);
+    }
     VDB_TRY(check_index(ix));
     if (n == 0) return VDB_OK;
     VDB_REQUIRE(vectors, "add: null vectors");
@@ -819,6 +856,7 @@ int32_t vdb_index_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
 
 int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64_t* ids,
                                const uint32_t* assignments_dev, uint64_t n, uint64_t global_n) {
+    VDB_REQUIRE(!(ix && ix->composite), "add_assigned: address the shards of a single-process sharded index through vdb_index_add");
     VDB_TRY(check_index(ix));
     if (n == 0 && global_n == 0) return VDB_OK;
     VDB_REQUIRE(n == 0 || (vectors && ids && assignments_dev), "add_assigned: null buffer");
@@ -830,6 +868,7 @@ int32_t vdb_index_add_assigned(vdb_index* ix, const float* vectors, const uint64
 
 int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t nq, uint32_t nprobe, uint32_t k,
                                float* distances_dev, uint64_t* indices_dev, void* stream) {
+    VDB_REQUIRE(!(ix && ix->composite), "search_async: a single-process sharded index runs on its own streams; use vdb_index_search_submit");
     VDB_TRY(check_index(ix));
     VDB_TRY(check_search_args(ix, queries_dev, distances_dev, indices_dev, nq, nprobe, k));
     VDB_REQUIRE(is_device_ptr(distances_dev) && is_device_ptr(indices_dev), "search_async: outputs must be device arrays");
@@ -843,11 +882,16 @@ int32_t vdb_index_search_async(vdb_index* ix, const float* queries_dev, uint32_t
     VDB_TRY(index_acquire_slot(ix, &s, &t));
     cudaStream_t st = (cudaStream_t)stream;
     return index_enqueue_search(ix, *s, queries_dev, nq, nprobe, k, distances_dev, indices_dev,
-                                SearchStreams{st, st, st, false}, true);
+                                SearchStreams{st, st, st, false, nullptr}, true);
 }
 
 int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
                                 float* distances, uint64_t* indices, uint64_t* ticket) {
+    if (ix && ix->composite) {
+        VDB_TRY(check_search_args(ix, queries, distances, indices, nq, nprobe, k));
+        VDB_REQUIRE(ticket, "search_submit: null ticket");
+        return composite_submit(ix, queries, nq, nprobe, k, distances, indices, ticket);
+    }
     VDB_TRY(check_index(ix));
     VDB_TRY(check_search_args(ix, queries, distances, indices, nq, nprobe, k));
     VDB_REQUIRE(ticket, "search_submit: null ticket");
@@ -866,6 +910,7 @@ int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq
 }
 
 int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket) {
+    if (ix && ix->composite) return composite_wait(ix, ticket);
     VDB_TRY(check_index(ix));
     SearchSlot* s = nullptr;
     {
@@ -884,6 +929,7 @@ int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket) {
 }
 
 int32_t vdb_index_search_wait_stream(vdb_index* ix, uint64_t ticket, void* stream) {
+    if (ix && ix->composite) return composite_wait_stream(ix, ticket, (cudaStream_t)stream);
     VDB_TRY(check_index(ix));
     std::lock_guard<std::mutex> lock(ix->mu);
     VDB_REQUIRE(ticket >= 1 && ticket <= ix->next_ticket, "search_wait_stream: unknown ticket");
@@ -902,6 +948,7 @@ int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint3
 }
 
 int32_t vdb_index_reserve_search(vdb_index* ix, uint32_t max_nq, uint32_t max_nprobe, uint32_t max_k) {
+    if (ix && ix->composite) return composite_reserve_search(ix, max_nq, max_nprobe, max_k);
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(max_nq >= 1 && max_nprobe >= 1 && max_k >= 1 && max_k <= (uint32_t)scan_max_k(), "reserve_search: bad shape");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -911,6 +958,7 @@ int32_t vdb_index_reserve_search(vdb_index* ix, uint32_t max_nq, uint32_t max_np
 }
 
 int32_t vdb_index_attach_exchange(vdb_index* ix, vdb_exchange* ex) {
+    VDB_REQUIRE(!(ix && ix->composite), "attach_exchange: a single-process sharded index owns its exchange");
     VDB_TRY(check_index(ix));
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
@@ -920,14 +968,13 @@ int32_t vdb_index_attach_exchange(vdb_index* ix, vdb_exchange* ex) {
 }
 
 int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t* lists) {
+    if (ix && ix->composite) ix = composite_root(ix);
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(queries && lists && nq >= 1 && nprobe >= 1, "select_nprobe: bad arguments");
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     const uint32_t np = std::min(nprobe, ix->nlist);
-    SearchSlot* s = nullptr;
-    uint64_t t = 0;
-    VDB_TRY(index_acquire_slot(ix, &s, &t));
+    SearchSlot* s = &ix->aux_slot;  // not a slot of the search ring: takes no ticket
     const float* q = nullptr;
     VDB_TRY(stage_rows(ix, queries, nq, s->q_buf, &q, ix->stream));
     VDB_TRY(slot_coarse_select(ix, *s, q, nq, np, ix->stream));
@@ -939,6 +986,7 @@ int32_t vdb_index_select_nprobe(vdb_index* ix, const float* queries, uint32_t nq
 }
 
 int32_t vdb_index_assign(vdb_index* ix, const float* vectors, uint64_t n, uint32_t* lists) {
+    if (ix && ix->composite) ix = composite_root(ix);
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(vectors && lists, "assign: null buffer");
     if (n == 0) return VDB_OK;
@@ -956,6 +1004,7 @@ int32_t vdb_index_assign(vdb_index* ix, const float* vectors, uint64_t n, uint32
 }
 
 int32_t vdb_index_get_centroids(vdb_index* ix, float* out) {
+    if (ix && ix->composite) ix = composite_root(ix);
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out, "get_centroids: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -967,6 +1016,10 @@ int32_t vdb_index_get_centroids(vdb_index* ix, float* out) {
 }
 
 int32_t vdb_index_set_centroids(vdb_index* ix, const float* in) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(in, "set_centroids: null buffer");
+        return composite_set_centroids(ix, in);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(in, "set_centroids: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -981,6 +1034,7 @@ int32_t vdb_index_set_centroids(vdb_index* ix, const float* in) {
 }
 
 int32_t vdb_index_get_owners(vdb_index* ix, uint8_t* out) {
+    if (ix && ix->composite) ix = composite_root(ix);
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out, "get_owners: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -989,6 +1043,10 @@ int32_t vdb_index_get_owners(vdb_index* ix, uint8_t* out) {
 }
 
 int32_t vdb_index_set_owners(vdb_index* ix, const uint8_t* in) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(in, "set_owners: null buffer");
+        return composite_set_owners(ix, in);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(in, "set_owners: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1003,6 +1061,10 @@ int32_t vdb_index_set_owners(vdb_index* ix, const uint8_t* in) {
 }
 
 int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(out, "list_sizes: null buffer");
+        return composite_list_sizes(ix, out);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out, "list_sizes: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1011,6 +1073,10 @@ int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out) {
 }
 
 int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(out, "list_ids: bad arguments");
+        return composite_list_ids(ix, list, out);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out && list < ix->nlist, "list_ids: bad arguments");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1027,7 +1093,116 @@ int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out) {
     return VDB_OK;
 }
 
+int32_t vdb_index_list_vectors(vdb_index* ix, uint32_t list, float* out) {
+    VDB_TRY(check_index(ix));
+    if (ix->composite) {
+        VDB_REQUIRE(out && list < ix->cfg.nlist, "list_vectors: bad arguments");
+        std::vector<uint8_t> owners(ix->cfg.nlist);
+        VDB_TRY(vdb_index_get_owners(composite_root(ix), owners.data()));
+        return vdb_index_list_vectors(composite_shard(ix, owners[list]), list, out);
+    }
+    VDB_REQUIRE(out && list < ix->nlist, "list_vectors: bad arguments");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    uint32_t left = ix->h_rows[list];
+    for (size_t j = 0; j < ix->h_pages[list].size() && left; ++j) {
+        const uint32_t take = std::min(left, ix->page_rows);
+        const void* src = (const void*)(uintptr_t)ix->page_addr[ix->h_pages[list][j]];
+        VDB_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)j * ix->page_rows * ix->dim, (size_t)ix->dim * 4, src,
+                                       (size_t)ix->ld * 4, (size_t)ix->dim * 4, take, cudaMemcpyDefault, ix->stream));
+        left -= take;
+    }
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return VDB_OK;
+}
+
+// Append rows whose list is known (persistence: one stored list file) -- no assignment, and no staging either: the
+// copies go from the caller's memory (e.g. a memory-mapped Arrow values buffer) straight into the list's HBM pages.
+int32_t vdb_index_append_list(vdb_index* ix, uint32_t list, const float* vectors, const uint64_t* ids, uint64_t n) {
+    VDB_TRY(check_index(ix));
+    if (n == 0) return VDB_OK;
+    if (ix->composite) {
+        VDB_REQUIRE(vectors && ids && list < ix->cfg.nlist, "append_list: bad arguments");
+        std::vector<uint8_t> owners(ix->cfg.nlist);
+        VDB_TRY(vdb_index_get_owners(composite_root(ix), owners.data()));
+        // every shard counts the rows (get_total_vectors), the owner stores them
+        for (uint32_t r = 0; r < composite_size(ix); ++r) {
+            vdb_index* s = composite_shard(ix, r);
+            if (r == owners[list]) VDB_TRY(vdb_index_append_list(s, list, vectors, ids, n));
+            else {
+                std::lock_guard<std::mutex> lock(s->mu);
+                s->total_vectors += n;
+            }
+        }
+        return composite_note_added(ix, n);
+    }
+    VDB_REQUIRE(vectors && ids && list < ix->nlist, "append_list: bad arguments");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    ix->total_vectors += n;
+    if (ix->cfg.shard_count > 1 && ix->h_owner[list] != ix->cfg.shard_rank) return VDB_OK;  // another shard's list
+    VDB_REQUIRE((uint64_t)ix->h_rows[list] + n < 0xffffffffull, "append_list: the list would exceed 2^32 rows");
+    const uint32_t old = ix->h_rows[list];
+    const uint32_t need = (uint32_t)((old + n + ix->page_rows - 1) / ix->page_rows);
+    while (ix->h_pages[list].size() < need) {
+        uint32_t pg;
+        VDB_TRY(index_alloc_page(ix, &pg));
+        ix->h_pages[list].push_back(pg);
+    }
+    uint64_t done = 0;
+    while (done < n) {
+        const uint32_t pos = old + (uint32_t)done, pg = pos / ix->page_rows, r = pos % ix->page_rows;
+        const uint64_t take = std::min<uint64_t>(ix->page_rows - r, n - done);
+        uint8_t* page = (uint8_t*)(uintptr_t)ix->page_addr[ix->h_pages[list][pg]];
+        if (ix->dim != ix->ld)
+            VDB_CUDA_TRY(cudaMemsetAsync(page + (size_t)r * ix->ld * 4, 0, take * ix->ld * 4, ix->stream));
+        VDB_CUDA_TRY(cudaMemcpy2DAsync(page + (size_t)r * ix->ld * 4, (size_t)ix->ld * 4, vectors + done * ix->dim,
+                                       (size_t)ix->dim * 4, (size_t)ix->dim * 4, take, cudaMemcpyDefault, ix->stream));
+        VDB_CUDA_TRY(cudaMemcpyAsync(page + ix->ids_off + (size_t)r * 8, ids + done, take * 8, cudaMemcpyDefault,
+                                     ix->stream));
+        done += take;
+    }
+    VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->h_rows[list] = old + (uint32_t)n;
+    ix->local_vectors += n;
+    ix->tables_dirty = true;  // the device tables are refreshed once, by the next search / add / finish_load
+    return VDB_OK;
+}
+
+int32_t vdb_index_finish_load(vdb_index* ix) {
+    VDB_TRY(check_index(ix));
+    if (ix->composite) {
+        for (uint32_t r = 0; r < composite_size(ix); ++r) VDB_TRY(vdb_index_finish_load(composite_shard(ix, r)));
+        return VDB_OK;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    VDB_TRY(flush_tables(ix));
+    return reserve_slots(ix);
+}
+
+int32_t vdb_index_balance_owners(vdb_index* ix, const uint64_t* list_sizes) {
+    VDB_TRY(check_index(ix));
+    VDB_REQUIRE(list_sizes, "balance_owners: null buffer");
+    if (ix->composite) {
+        for (uint32_t r = 0; r < composite_size(ix); ++r) VDB_TRY(vdb_index_balance_owners(composite_shard(ix, r), list_sizes));
+        return VDB_OK;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    VDB_REQUIRE(ix->total_vectors == 0, "balance_owners: list ownership can only change while the index is empty");
+    if (ix->cfg.shard_count <= 1) return VDB_OK;
+    std::vector<uint32_t> counts(ix->nlist);
+    for (uint32_t l = 0; l < ix->nlist; ++l) counts[l] = (uint32_t)std::min<uint64_t>(list_sizes[l], 0xffffffffull);
+    balance_owners(ix, counts);
+    return index_upload_owners(ix);
+}
+
 int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(out, "stats: null buffer");
+        return composite_stats(ix, out);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out, "stats: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1041,10 +1216,15 @@ int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out) {
     out->row_stride = ix->ld;
     out->page_rows = ix->page_rows;
     out->trained = ix->trained ? 1 : 0;
+    out->metric = ix->cfg.metric;
     return VDB_OK;
 }
 
 int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(out, "search stats: null buffer");
+        return composite_last_search_stats(ix, out);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out, "search stats: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1066,6 +1246,7 @@ int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
 }
 
 int32_t vdb_index_set_profiling(vdb_index* ix, int32_t enable) {
+    if (ix && ix->composite) return composite_set_profiling(ix, enable);
     VDB_TRY(check_index(ix));
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
@@ -1078,6 +1259,10 @@ int32_t vdb_index_set_profiling(vdb_index* ix, int32_t enable) {
 }
 
 int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms, uint32_t* searches) {
+    if (ix && ix->composite) {
+        VDB_REQUIRE(out_ms && searches, "read_profile: null buffer");
+        return composite_read_profile(ix, out_ms, searches);
+    }
     VDB_TRY(check_index(ix));
     VDB_REQUIRE(out_ms && searches, "read_profile: null buffer");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1098,6 +1283,7 @@ int32_t vdb_index_read_profile(vdb_index* ix, float* out_ms, uint32_t* searches)
 }
 
 int32_t vdb_index_warmup(vdb_index* ix, const uint32_t* lists, uint32_t n) {
+    if (ix && ix->composite) ix = composite_root(ix);
     VDB_TRY(check_index(ix));
     for (uint32_t i = 0; i < n; ++i) VDB_REQUIRE(lists && lists[i] < ix->nlist, "warmup: list id out of range");
     return VDB_OK;  // every list is HBM-resident from add() on; nothing to load (ivf_flat_index.cpp:387-444)

@@ -75,7 +75,7 @@ constexpr uint32_t SLOT_TIMERS = 8;
 // Each slot owns every buffer one search touches, so `depth` batches are in flight without sharing scratch.
 struct SearchSlot {
     ScanWorkspace ws_scan, ws_coarse;
-    DevBuf<float> q_buf, dots, coarse_d, out_d;
+    DevBuf<float> q_buf, q_raw, dots, coarse_d, out_d;  // q_raw: queries peer-copied from another device
     DevBuf<uint64_t> coarse_i, out_i;
     DevBuf<uint32_t> probes, zero_probes;
     PinnedBuf h_q, h_d, h_i;
@@ -96,18 +96,24 @@ struct SearchSlot {
 
     uint64_t bytes() const {
         return ws_scan.bytes + ws_coarse.bytes + q_buf.bytes() + dots.bytes() + coarse_d.bytes() + out_d.bytes() +
-               coarse_i.bytes() + out_i.bytes() + probes.bytes() + zero_probes.bytes();
+               coarse_i.bytes() + out_i.bytes() + probes.bytes() + zero_probes.bytes() + q_raw.bytes();
     }
 };
 
 struct SearchStreams {
     cudaStream_t front, scan, back;
     bool split;  // the three differ: order them with the slot's events
+    cudaEvent_t back_wait = nullptr;  // the back phase also waits for this (mailbox reuse of a root-only exchange)
 };
+
+struct Composite;  // sharded_index.cu: the shards of a single-process multi-device index
 
 }  // namespace vdb
 
 struct vdb_index {
+    // a single-process multi-device index (vdb_index_create_sharded) is a handle whose work is done by one
+    // vdb_index per device; none of the fields below the config are used on it
+    vdb::Composite* composite = nullptr;
     vdb_config cfg{};
     uint32_t dim = 0, ld = 0, nlist = 0, page_rows = 0;
     uint64_t page_bytes = 0, ids_off = 0;
@@ -133,6 +139,7 @@ struct vdb_index {
     vdb::DevBuf<uint32_t> d_rows, d_page_off;
     vdb::DevBuf<uint64_t> d_page_vec, d_page_ids;
     std::vector<uint32_t> npages_desc;  // page counts, descending (search slot bound)
+    bool tables_dirty = false;          // h_rows / h_pages changed without an upload (vdb_index_append_list)
 
     uint64_t total_vectors = 0, local_vectors = 0, slab_bytes_total = 0;
     // sharding: owner[l] = rank that holds list l (empty on an unsharded index)
@@ -141,6 +148,7 @@ struct vdb_index {
 
     // search pipeline
     vdb::SearchSlot slots[vdb::MAX_SEARCH_SLOTS];
+    vdb::SearchSlot aux_slot;    // vdb_index_select_nprobe (synchronous, outside the ring)
     uint32_t depth = 4;          // slots in use
     uint32_t reserve_sms = 8;    // SMs a pipelined scan leaves to the front / back kernels of its neighbours
     uint32_t ppi_override = 0;   // pages per scan item (0 = heuristic)
@@ -187,5 +195,30 @@ int32_t index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* queries,
                              uint32_t k, float* distances, uint64_t* indices, const SearchStreams& st, bool collect);
 int32_t index_acquire_slot(vdb_index* ix, SearchSlot** out, uint64_t* ticket);
 int32_t index_finish_slot(vdb_index* ix, SearchSlot& s);  // host-wait + deliver + harvest timings
+SearchStreams index_pipeline_streams(vdb_index* ix, uint64_t ticket);
+// sum of the partial-result bytes one query needs (0 chunks => fits): nq_chunk < nq means "split the batch"
+void index_choose_ppi(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t k, uint32_t* ppi, uint32_t* nq_chunk);
+
+// sharded_index.cu: the composite's side of every C-ABI entry point
+int32_t composite_destroy(vdb_index* ix);
+int32_t composite_train(vdb_index* ix, const float* vectors, uint64_t n);
+int32_t composite_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n);
+int32_t composite_submit(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k,
+                         float* distances, uint64_t* indices, uint64_t* ticket);
+int32_t composite_wait(vdb_index* ix, uint64_t ticket);
+int32_t composite_wait_stream(vdb_index* ix, uint64_t ticket, cudaStream_t stream);
+vdb_index* composite_root(vdb_index* ix);
+uint32_t composite_size(vdb_index* ix);
+vdb_index* composite_shard(vdb_index* ix, uint32_t r);
+int32_t composite_set_centroids(vdb_index* ix, const float* in);
+int32_t composite_set_owners(vdb_index* ix, const uint8_t* in);
+int32_t composite_list_sizes(vdb_index* ix, uint64_t* out);
+int32_t composite_list_ids(vdb_index* ix, uint32_t list, uint64_t* out);
+int32_t composite_stats(vdb_index* ix, vdb_stats* out);
+int32_t composite_last_search_stats(vdb_index* ix, vdb_search_stats* out);
+int32_t composite_set_profiling(vdb_index* ix, int32_t enable);
+int32_t composite_read_profile(vdb_index* ix, float* out_ms, uint32_t* searches);
+int32_t composite_reserve_search(vdb_index* ix, uint32_t nq, uint32_t np, uint32_t k);
+int32_t composite_note_added(vdb_index* ix, uint64_t n);
 
 }  // namespace vdb

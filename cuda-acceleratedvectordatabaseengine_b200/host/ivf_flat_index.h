@@ -15,18 +15,34 @@
 // std::invalid_argument on dimension == 0 || nlist == 0 (ivf_flat_index.cpp:17-19);
 // every other failure surfaces as std::runtime_error, which the server's
 // catch (std::exception&) turns into grpc INTERNAL (query_service.cpp:164-167).
-// There is no CPU fallback: Config::use_gpu = false is rejected.
+// There is no CPU path.  Config::use_gpu = false -- which the reference's own smoke test sets
+// (test/simple_test.cpp:114) -- is ACCEPTED and has no effect: the search still runs on the GPU, and returns what
+// the reference's CPU path returns (that equality is the parity contract of this repository).  A missing device
+// or library is an exception, never a silent fallback.
+//
+// The reference's call sites compile against this header unchanged: host/dropin/engine/{ivf_flat_index,
+// transfer_manager}.h forward to it, and tests/test_dropin_compile.py builds /root/reference/test/simple_test.cpp,
+// test/gpu_vs_cpu_test.cpp and bench/benchmark.cpp, unmodified, on top of it.
 #pragma once
+// the standard headers the reference's engine headers bring in (its call sites rely on them transitively)
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <mutex>
+#include <queue>
 #include <shared_mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "vdb_b200.h"
+#include "vdb_b200_storage.h"
 
 #ifndef __CUDA_RUNTIME_H__
 typedef struct CUstream_st* cudaStream_t;
@@ -43,6 +59,12 @@ namespace detail {
 inline void check(int32_t st, const char* what) {
     if (st == VDB_OK) return;
     std::string msg = std::string(what) + ": " + vdb_last_error_string() + " [" + vdb_status_string(st) + "]";
+    if (st == VDB_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+inline void check_storage(int32_t st, const char* what) {
+    if (st == VDB_OK) return;
+    std::string msg = std::string(what) + ": " + vdb_storage_last_error() + " [" + vdb_status_string(st) + "]";
     if (st == VDB_INVALID_ARGUMENT) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);
 }
@@ -145,10 +167,12 @@ public:
         uint32_t dimension;
         uint32_t nlist;
         kernels::Metric metric;
-        bool use_gpu = true;
+        bool use_gpu = true;        // accepted either way, see the header comment
         size_t max_gpu_memory = 0;  // 0 = uncapped (the reference's 8 GiB default cannot hold the headline index)
         int device = 0;
-        uint32_t shard_rank = 0, shard_count = 1;
+        uint32_t shard_rank = 0, shard_count = 1;  // one process per GPU (this process holds shard_rank's lists)
+        std::vector<int> devices;   // more than one entry: ONE process, one list shard per device
+        uint32_t pipeline_depth = 0;  // searches in flight, 0 = 4
     };
     struct SearchParams {
         uint32_t nprobe = 10;
@@ -159,7 +183,6 @@ public:
     IVFFlatIndex(const Config& config, TransferManager* tm) : config_(config), tm_(tm) {
         if (config.dimension == 0 || config.nlist == 0)
             throw std::invalid_argument("Invalid configuration: dimension and nlist must be > 0");
-        if (!config.use_gpu) throw std::invalid_argument("use_gpu = false: this build has no CPU path");
         vdb_config c;
         vdb_config_default(&c);
         c.dimension = config.dimension;
@@ -169,7 +192,15 @@ public:
         c.max_gpu_memory = config.max_gpu_memory;
         c.shard_rank = config.shard_rank;
         c.shard_count = config.shard_count;
-        detail::check(vdb_index_create(&c, &ix_), "IVFFlatIndex");
+        c.pipeline_depth = config.pipeline_depth;
+        if (config.devices.size() > 1) {
+            std::vector<int32_t> devs(config.devices.begin(), config.devices.end());
+            detail::check(vdb_index_create_sharded(&c, devs.data(), static_cast<int32_t>(devs.size()), &ix_),
+                          "IVFFlatIndex");
+        } else {
+            if (config.devices.size() == 1) c.device = config.devices[0];
+            detail::check(vdb_index_create(&c, &ix_), "IVFFlatIndex");
+        }
     }
     ~IVFFlatIndex() { vdb_index_destroy(ix_); }
     IVFFlatIndex(const IVFFlatIndex&) = delete;
@@ -189,6 +220,30 @@ public:
         std::shared_lock<std::shared_mutex> l(mu_);
         detail::check(vdb_index_search(ix_, queries, n_queries, params.nprobe, params.k, distances, indices), "search");
     }
+    // the pipelined form (the reference server's intended batches in flight, query_service.h:26-27)
+    uint64_t search_submit(const float* queries, uint32_t n_queries, const SearchParams& params, float* distances,
+                           uint64_t* indices) {
+        std::shared_lock<std::shared_mutex> l(mu_);
+        uint64_t ticket = 0;
+        detail::check(vdb_index_search_submit(ix_, queries, n_queries, params.nprobe, params.k, distances, indices,
+                                              &ticket), "search_submit");
+        return ticket;
+    }
+    void search_wait(uint64_t ticket) { detail::check(vdb_index_search_wait(ix_, ticket), "search_wait"); }
+    // ivf_flat_index.h:66-67 (declared by the reference, never defined): the epoch directory of format/storage.cpp
+    // -- manifest.json + centroids + one Arrow IPC vector file per non-empty list (libvdb_b200_storage.so)
+    void save(const std::string& path) const {
+        std::shared_lock<std::shared_mutex> l(mu_);
+        detail::check_storage(vdb_index_save(ix_, path.c_str()), "save");
+    }
+    void load(const std::string& path) {
+        std::unique_lock<std::shared_mutex> l(mu_);
+        detail::check_storage(vdb_index_load(ix_, path.c_str()), "load");
+    }
+    // server/query_service.cpp:245 calls index->load_from_epoch(epoch_ptr) with a storage::EpochManager::Epoch;
+    // any type with a std::string base_path member (format/storage.h:175-181) works
+    template <typename EpochPtr>
+    void load_from_epoch(const EpochPtr& epoch) { load(epoch->base_path); }
     void warmup_lists(const std::vector<uint32_t>& list_ids) {
         detail::check(vdb_index_warmup(ix_, list_ids.data(), static_cast<uint32_t>(list_ids.size())), "warmup_lists");
     }

@@ -8,8 +8,60 @@ array and the ``id`` column one contiguous u64 array, so both go to ``vdb_index_
 assignment runs on the GPU and every row lands in the HBM page of its inverted list -- no intermediate host copy,
 no per-row builder loop.  A sharded index (``Config.shard_rank/shard_count``) keeps only the lists it owns.
 """
+import ctypes as C
+import os
+
 import numpy as np
 import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STORAGE_LIB_PATH = os.path.join(_HERE, "libvdb_b200_storage.so")
+_SLIB = None
+
+# every symbol include/vdb_b200_storage.h declares: name -> (restype, argtypes)
+_vp, _u32, _u64, _i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+STORAGE_ABI = {
+    "vdb_index_save_epoch": (_i32, [_vp, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "vdb_index_save": (_i32, [_vp, C.c_char_p]),
+    "vdb_index_load": (_i32, [_vp, C.c_char_p]),
+    "vdb_storage_write_vectors": (_i32, [C.c_char_p, _vp, _vp, _u64, _u32]),
+    "vdb_storage_read_vectors": (_i32, [C.c_char_p, _vp, _vp, C.POINTER(_u64), C.POINTER(_u32)]),
+    "vdb_storage_last_error": (C.c_char_p, []),
+}
+
+
+def storage_lib():
+    """libvdb_b200_storage.so (C++ on Apache Arrow): the epoch directory of format/storage.cpp <-> the HBM index."""
+    global _SLIB
+    if _SLIB is None:
+        if not os.path.exists(STORAGE_LIB_PATH):
+            raise RuntimeError(f"{STORAGE_LIB_PATH} is not built: run __graft_entry__.build()")
+        l = C.CDLL(STORAGE_LIB_PATH)
+        for name, (res, args) in STORAGE_ABI.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _SLIB = l
+    return _SLIB
+
+
+def _scheck(st):
+    if st == 0:
+        return
+    msg = storage_lib().vdb_storage_last_error().decode()
+    if st == 1:
+        raise ValueError(msg)
+    raise RuntimeError(f"{msg} [{st}]")
+
+
+def save_epoch(index, directory, index_name="", epoch=""):
+    """IVFFlatIndex::save (ivf_flat_index.h:66): manifest.json + centroids.arrow + one list_<id>.arrow per list"""
+    _scheck(storage_lib().vdb_index_save_epoch(index._h, os.fsencode(directory), index_name.encode(), epoch.encode()))
+
+
+def load_epoch(index, directory):
+    """IVFFlatIndex::load / load_from_epoch (server/query_service.cpp:245): the list files are memory-mapped and
+    copied straight from the mapping into the owning GPU's HBM pages"""
+    _scheck(storage_lib().vdb_index_load(index._h, os.fsencode(directory)))
 
 
 def vector_schema():

@@ -85,7 +85,7 @@ typedef struct {
     uint64_t pages;              /* inverted-list pages in use */
     uint32_t dimension, nlist, row_stride, page_rows;
     int32_t trained;
-    int32_t reserved;
+    int32_t metric;              /* vdb_metric */
 } vdb_stats;
 
 /* Byte accounting of the most recent search: probed rows summed
@@ -110,6 +110,14 @@ void vdb_config_default(vdb_config* cfg);
 
 /* IVFFlatIndex::IVFFlatIndex(const Config&, TransferManager*), ivf_flat_index.cpp:13-33 */
 int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out);
+/* The same object over several GPUs of ONE process (the reference server constructs one IVFFlatIndex in one
+ * process, server/query_service.cpp:232-245): shard r lives on devices[r] and holds the lists whose owner is r
+ * (vdb_index_get_owners; byte-balanced by train()); every vdb_index_* call below works on the returned handle.
+ * cfg->device / shard_rank / shard_count are ignored.  Searches run on the shards' own pipelines -- submit / wait /
+ * the synchronous vdb_index_search; vdb_index_search_async and vdb_index_add_assigned are refused -- and each
+ * shard's merge kernel stores its top-k into the root shard's mailbox over NVLink peer access, where a collect
+ * kernel merges them.  Results are identical to the unsharded index.  A device may be listed more than once. */
+int32_t vdb_index_create_sharded(const vdb_config* cfg, const int32_t* devices, int32_t ndev, vdb_index** out);
 /* IVFFlatIndex::~IVFFlatIndex, ivf_flat_index.cpp:36-46 */
 int32_t vdb_index_destroy(vdb_index* ix);
 
@@ -177,6 +185,16 @@ int32_t vdb_index_get_owners(vdb_index* ix, uint8_t* out /* [nlist] */);
 int32_t vdb_index_set_owners(vdb_index* ix, const uint8_t* in /* [nlist] */);
 int32_t vdb_index_list_sizes(vdb_index* ix, uint64_t* out /* [nlist] */);
 int32_t vdb_index_list_ids(vdb_index* ix, uint32_t list, uint64_t* out /* [list size] */);
+/* Persistence seam (libvdb_b200_storage.so writes / reads the reference's epoch layout on top of these):
+ * the rows of one list in storage order, [list size][dimension] (host or device memory); append rows to a list
+ * without assignment, copied straight from the caller's memory (e.g. a memory-mapped Arrow values buffer) into the
+ * list's HBM pages -- a sharded index stores them only on the owner; finish_load publishes the appended lists to the
+ * search tables once at the end; balance_owners re-computes the byte-balanced ownership of an EMPTY sharded index
+ * from per-list row counts (what train() does from its sample). */
+int32_t vdb_index_list_vectors(vdb_index* ix, uint32_t list, float* out /* [list size][dimension] */);
+int32_t vdb_index_append_list(vdb_index* ix, uint32_t list, const float* vectors, const uint64_t* ids, uint64_t n);
+int32_t vdb_index_finish_load(vdb_index* ix);
+int32_t vdb_index_balance_owners(vdb_index* ix, const uint64_t* list_sizes /* [nlist] */);
 int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out);
 int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out);
 /* Profiling for the roofline report: when enabled, CUDA events on the launching

@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
 
 
-def header_symbols():
-    src = open(os.path.join(ROOT, "include", "vdb_b200.h")).read()
+def header_symbols(name="vdb_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(vdb_[a-z0-9_]+)\s*\(", src)))
 
@@ -36,8 +36,17 @@ def test_invalid_config_is_invalid_argument():
         pkg.IVFFlatIndex(pkg.Config(dimension=4, nlist=0))
     with pytest.raises(ValueError):
         pkg.IVFFlatIndex(pkg.Config(dimension=4, nlist=4, metric=pkg.Metric.Cosine))
-    with pytest.raises(ValueError):
-        pkg.IVFFlatIndex(pkg.Config(dimension=4, nlist=4, use_gpu=False))
+
+
+def test_storage_library_exports_every_declared_symbol():
+    storage = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200.storage")
+    pkg.build()
+    lib = C.CDLL(storage.STORAGE_LIB_PATH)
+    syms = header_symbols("vdb_b200_storage.h")
+    assert len(syms) >= 6
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in vdb_b200_storage.h but not exported"
+    assert sorted(storage.STORAGE_ABI) == syms, "python binding table and storage header disagree"
 
 
 def test_no_cpu_fallback_without_device():
