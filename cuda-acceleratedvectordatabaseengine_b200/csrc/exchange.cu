@@ -264,6 +264,9 @@ int32_t vdb_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint3
     if ((e = cudaMemset(ex->d_error, 0, 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMallocHost(&ex->h_error, 4)) != cudaSuccess) return fail(e);
     *ex->h_error = 0;
+    // the memsets ran on the legacy default stream, which the callers' non-blocking streams do not wait for: a
+    // publish launched right after create could otherwise have its flags zeroed behind it
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e);
     ex->peer_base.assign(world, nullptr);
     ex->opened.assign(world, false);
     ex->peer_base[rank] = ex->local;

@@ -62,6 +62,8 @@ constexpr uint64_t PARTIAL_BYTES_CAP = 1ull << 30;  // partial-result buffer of 
 
 using namespace vdb;
 
+static void balance_owners_impl(vdb_index* ix, const std::vector<uint32_t>& counts);
+
 namespace {
 
 // assign_to_lists: tensor cores + exact re-check for large centroid tables (bit-identical to the scalar
@@ -73,6 +75,16 @@ int32_t assign_rows(vdb_index* ix, const float* x, uint64_t n, uint32_t* out, cu
     return kmeans_assign_exact(x, n, ix->ld, ix->centroids.p, ix->nlist, ix->ld, ix->dim, ix->cfg.metric, out, nullptr,
                                stream);
 }
+
+}  // namespace
+
+int32_t vdb::index_assign_rows(vdb_index* ix, const float* x, uint64_t n, uint32_t* out, cudaStream_t stream) {
+    return assign_rows(ix, x, n, out, stream);
+}
+
+void vdb::index_balance_owners(vdb_index* ix, const std::vector<uint32_t>& counts) { balance_owners_impl(ix, counts); }
+
+namespace {
 
 ListTable centroid_table(vdb_index* ix) {
     ListTable lt;
@@ -136,7 +148,11 @@ namespace {
 // Greedy (largest first) byte balancing of the lists over the shards from per-list row counts: iid data
 // clusters very unevenly, so `l % world` can leave one GPU with far more to scan than another.
 // Deterministic, so every rank computes the same table from the same counts.
-void balance_owners(vdb_index* ix, const std::vector<uint32_t>& counts) {
+void balance_owners(vdb_index* ix, const std::vector<uint32_t>& counts) { balance_owners_impl(ix, counts); }
+
+}  // namespace
+
+static void balance_owners_impl(vdb_index* ix, const std::vector<uint32_t>& counts) {
     const uint32_t world = ix->cfg.shard_count;
     std::vector<uint32_t> order(ix->nlist);
     std::iota(order.begin(), order.end(), 0u);
@@ -150,6 +166,8 @@ void balance_owners(vdb_index* ix, const std::vector<uint32_t>& counts) {
         load[best] += (uint64_t)counts[l] + 1;  // +1 spreads the empty lists too
     }
 }
+
+namespace {
 
 int32_t refresh_centroid_aux(vdb_index* ix) {
     VDB_TRY(ix->cnorm.reserve(ix->nlist));

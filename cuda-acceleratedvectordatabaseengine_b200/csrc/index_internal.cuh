@@ -189,6 +189,8 @@ int32_t index_upload_list_tables(vdb_index* ix);
 int32_t index_alloc_page(vdb_index* ix, uint32_t* page);
 int32_t index_refresh_centroids(vdb_index* ix);  // norms + flat view after the centroid table changed
 int32_t index_upload_owners(vdb_index* ix);
+int32_t index_assign_rows(vdb_index* ix, const float* x, uint64_t n, uint32_t* out, cudaStream_t stream);
+void index_balance_owners(vdb_index* ix, const std::vector<uint32_t>& counts);  // fills ix->h_owner
 // enqueue one search of `ix` into slot `s` (see SearchSlot); queries may be host or device memory.
 // collect = false: the merged local result is only published (non-root shard of a single-process sharded index)
 int32_t index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* queries, uint32_t nq, uint32_t nprobe,

@@ -200,7 +200,7 @@ __global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
 // the HBM reads stay coalesced), folded into the running minimum (:68-88).
 __global__ void __launch_bounds__(128) seed_dist_kernel(const float* __restrict__ x, uint32_t n, uint32_t ldx,
                                                         uint32_t dim, const float* __restrict__ cnew,
-                                                        float* __restrict__ mind) {
+                                                        const float* mind_in, const PeerF32 mind_out) {
     __shared__ float tile[128][33];
     __shared__ float sc[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(128) seed_dist_kernel(const float* __restrict_
     }
     const uint64_t v = v0 + tid;
     if (v < n) {
-        const float m = mind[v];
-        mind[v] = acc < m ? acc : m;  // std::min(min_dist, dist)
+        const float m = mind_in[v];
+        const float r = acc < m ? acc : m;  // std::min(min_dist, dist)
+        for (uint32_t pr = 0; pr < mind_out.n; ++pr) mind_out.p[pr][v] = r;
     }
 }
 
@@ -240,7 +241,7 @@ constexpr uint32_t SD_SMEM = SD_STAGES * SD_STAGE_BYTES + 2048 * 4 + 2 * SD_STAG
 __global__ void __launch_bounds__(SD_ROWS + 32) seed_dist_tma_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                       uint32_t n, uint32_t ld,
                                                                       const float* __restrict__ cnew,
-                                                                      float* __restrict__ mind) {
+                                                                      const float* mind_in, const PeerF32 mind_out) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t sd_raw[];
     uint8_t* smem = sd_raw + ((1024u - (smem_u32(sd_raw) & 1023u)) & 1023u);
@@ -297,8 +298,11 @@ __global__ void __launch_bounds__(SD_ROWS + 32) seed_dist_tma_kernel(const __gri
         }
         const uint32_t v = row0 + tid;
         if (v < n) {
-            const float m = mind[v];
-            mind[v] = acc < m ? acc : m;  // std::min(min_dist, dist)
+            const float m = mind_in[v];
+            const float r = acc < m ? acc : m;  // std::min(min_dist, dist)
+            // data-parallel training: this rank owns a slice of the rows and stores the slice's new minima
+            // straight into every rank's copy (NVLink peer stores); single GPU: one copy, in place
+            for (uint32_t pr = 0; pr < mind_out.n; ++pr) mind_out.p[pr][v] = r;
         }
     }
 }
@@ -1050,15 +1054,21 @@ int32_t kmeans_assign_exact_rows(const float* x, const uint32_t* row_index, uint
     return VDB_OK;
 }
 
-int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
-                      float* centroids, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream) {
+int32_t kmeanspp_init(const float* x, uint32_t n, uint32_t ldx, uint32_t ld, float* centroids, KMeansScratch& sc,
+                      float* mind, uint64_t n_fill, cudaStream_t stream) {
     seed_init_kernel<<<1, 256, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, centroids, sc.picked);
-    fill_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(sc.mind, n, FLT_MAX);
+    fill_f32_kernel<<<(uint32_t)((n_fill + 255) / 256), 256, 0, stream>>>(mind, n_fill, FLT_MAX);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeanspp_dist_plan(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, SeedDistPlan* plan) {
+    plan->x = x; plan->n = n; plan->ldx = ldx; plan->dim = dim;
     // rows by TMA when the driver offers tensor maps and the rows are 16-byte aligned (always, for staged rows)
-    CUtensorMap mx;
-    const bool tma = tc::encode_tiled() != nullptr && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ldx <= 2048 && ld == ldx;
-    if (tma) {
-        VDB_TRY(tc::make_map(&mx, x, n, ldx, ldx, SD_ROWS));
+    plan->tma = n > 0 && tc::encode_tiled() != nullptr && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ldx <= 2048 && ld == ldx;
+    if (plan->tma) {
+        static_assert(sizeof(plan->map) >= sizeof(CUtensorMap), "tensor map storage");
+        VDB_TRY(tc::make_map(reinterpret_cast<CUtensorMap*>(plan->map), x, n, ldx, ldx, SD_ROWS));
         static bool conf[16] = {false};
         int dev = 0;
         cudaGetDevice(&dev);
@@ -1067,24 +1077,47 @@ int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, ui
             conf[dev] = true;
         }
     }
-    for (uint32_t c = 1; c < nlist; ++c) {
-        if (tma)
-            seed_dist_tma_kernel<<<(n + SD_ROWS - 1) / SD_ROWS, SD_ROWS + 32, SD_SMEM, stream>>>(
-                mx, n, ldx, centroids + (size_t)(c - 1) * ld, sc.mind);
-        else
-            seed_dist_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, n, ldx, dim, centroids + (size_t)(c - 1) * ld,
-                                                                   sc.mind);
-        if (sampler == SeedSampler::Sequential)
-            seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, sc.ckpt, centroids, c,
-                                                     sc.picked);
-        else if (sampler == SeedSampler::ExactParallel)
-            seed_sample_par_kernel<<<PS_CTAS, PS_THREADS, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
-                                                                 sc.picked);
-        else
-            seed_sample_fast_kernel<<<1, 1024, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, sc.mind, centroids, c,
-                                                            sc.picked);
-    }
+    return VDB_OK;
+}
+
+int32_t kmeanspp_dist(const SeedDistPlan& plan, const float* cnew, const float* mind_in, const PeerF32& mind_out,
+                      cudaStream_t stream) {
+    if (plan.n == 0) return VDB_OK;
+    if (plan.tma)
+        seed_dist_tma_kernel<<<(plan.n + SD_ROWS - 1) / SD_ROWS, SD_ROWS + 32, SD_SMEM, stream>>>(
+            *reinterpret_cast<const CUtensorMap*>(plan.map), plan.n, plan.ldx, cnew, mind_in, mind_out);
+    else
+        seed_dist_kernel<<<(plan.n + 127) / 128, 128, 0, stream>>>(plan.x, plan.n, plan.ldx, plan.dim, cnew, mind_in,
+                                                                     mind_out);
     VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeanspp_sample(const float* x, uint32_t n, uint32_t ldx, uint32_t ld, const float* mind, float* centroids,
+                        uint32_t c, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream) {
+    if (sampler == SeedSampler::Sequential)
+        seed_sample_kernel<<<1, 32, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, mind, sc.ckpt, centroids, c, sc.picked);
+    else if (sampler == SeedSampler::ExactParallel)
+        seed_sample_par_kernel<<<PS_CTAS, PS_THREADS, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, mind, centroids, c,
+                                                                     sc.picked);
+    else
+        seed_sample_fast_kernel<<<1, 1024, 0, stream>>>((DevRng*)sc.rng, x, n, ldx, ld, mind, centroids, c, sc.picked);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
+                      float* centroids, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream) {
+    VDB_TRY(kmeanspp_init(x, n, ldx, ld, centroids, sc, sc.mind, n, stream));
+    SeedDistPlan plan;
+    VDB_TRY(kmeanspp_dist_plan(x, n, ldx, dim, ld, &plan));
+    PeerF32 out{};
+    out.p[0] = sc.mind;
+    out.n = 1;
+    for (uint32_t c = 1; c < nlist; ++c) {
+        VDB_TRY(kmeanspp_dist(plan, centroids + (size_t)(c - 1) * ld, sc.mind, out, stream));
+        VDB_TRY(kmeanspp_sample(x, n, ldx, ld, sc.mind, centroids, c, sc, sampler, stream));
+    }
     return VDB_OK;
 }
 
@@ -1106,6 +1139,23 @@ int32_t kmeans_update_exact(const float* x, uint32_t n, uint32_t ldx, const uint
     cluster_sum_kernel<<<grid, 128, 0, stream>>>(x, ldx, sc.members, sc.coff, ld, sc.sums);
     const uint64_t tot = (uint64_t)nc * ld;
     centroid_divide_kernel<<<(uint32_t)((tot + 255) / 256), 256, 0, stream>>>(sc.sums, sc.counts, nc, ld, centroids);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+// data-parallel training: this rank sums and divides only clusters [c_lo, c_hi) -- each cluster's rows are still
+// added in input order by one rank, so the centroids equal the single-GPU ones bit for bit
+int32_t kmeans_update_exact_range(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
+                                  uint32_t ld, float* centroids, KMeansScratch& sc, uint32_t c_lo, uint32_t c_hi,
+                                  cudaStream_t stream) {
+    VDB_TRY(kmeans_members(assign, n, nc, sc, stream));
+    if (c_hi <= c_lo) return VDB_OK;
+    const uint32_t m = c_hi - c_lo;
+    dim3 grid(m, ((ld >> 2) + 127) / 128);
+    cluster_sum_kernel<<<grid, 128, 0, stream>>>(x, ldx, sc.members, sc.coff + c_lo, ld, sc.sums + (size_t)c_lo * ld);
+    const uint64_t tot = (uint64_t)m * ld;
+    centroid_divide_kernel<<<(uint32_t)((tot + 255) / 256), 256, 0, stream>>>(
+        sc.sums + (size_t)c_lo * ld, sc.counts + c_lo, m, ld, centroids + (size_t)c_lo * ld);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
 }
@@ -1135,7 +1185,7 @@ int32_t KMeansScratch::reserve(uint32_t n, uint32_t nc, uint32_t ld) {
     chunk = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
     if (chunk == 0) chunk = 32;
     VDB_CUDA_TRY(cudaMalloc(&rng, rng_state_bytes()));
-    VDB_CUDA_TRY(cudaMalloc(&mind, (size_t)std::max(n, 1u) * 4));
+    VDB_CUDA_TRY(cudaMalloc(&mind, (size_t)std::max(n, 1u) * 4 * mind_copies));
     VDB_CUDA_TRY(cudaMalloc(&ckpt, ((size_t)(n + SEQ_CHUNK - 1) / SEQ_CHUNK + 2) * 4));
     VDB_CUDA_TRY(cudaMalloc(&picked, (size_t)nc * 4));
     VDB_CUDA_TRY(cudaMalloc(&M, (size_t)nchunks * nc * 4));

@@ -5,9 +5,24 @@
 
 namespace vdb {
 
+// the same array on every rank of a data-parallel run (peer-mapped pointers; n = 1 on a single GPU)
+struct PeerF32 {
+    float* p[16];
+    uint32_t n;
+};
+
+// rows [n][ldx] whose distance to the newest seed one rank folds into the running minimum
+struct SeedDistPlan {
+    const float* x = nullptr;
+    uint32_t n = 0, ldx = 0, dim = 0;
+    bool tma = false;
+    alignas(64) unsigned char map[128];  // CUtensorMap
+};
+
 struct KMeansScratch {
     void* rng = nullptr;        // device std::mt19937 state
-    float* mind = nullptr;      // [n] running min squared distance to the chosen seeds
+    uint32_t mind_copies = 1;   // 2 for data-parallel training (the ranks write the next copy while the current is read)
+    float* mind = nullptr;      // [mind_copies][n] running min squared distance to the chosen seeds
     float* ckpt = nullptr;      // sequential-sum checkpoints
     uint32_t* picked = nullptr; // [nlist] training row chosen for each seed
     uint32_t* M = nullptr;      // [nchunks][nlist] counting-sort matrix
@@ -54,6 +69,17 @@ int32_t kmeans_assign_tensor(const float* x, uint64_t n, uint32_t ldx, const flo
 enum class SeedSampler { Fast = 0, ExactParallel = 1, Sequential = 2 };
 int32_t kmeanspp_seed(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, uint32_t nlist,
                       float* centroids, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream);
+// the steps of kmeanspp_seed, for the data-parallel driver (sharded_index.cu)
+int32_t kmeanspp_init(const float* x, uint32_t n, uint32_t ldx, uint32_t ld, float* centroids, KMeansScratch& sc,
+                      float* mind, uint64_t n_fill, cudaStream_t stream);
+int32_t kmeanspp_dist_plan(const float* x, uint32_t n, uint32_t ldx, uint32_t dim, uint32_t ld, SeedDistPlan* plan);
+int32_t kmeanspp_dist(const SeedDistPlan& plan, const float* cnew, const float* mind_in, const PeerF32& mind_out,
+                      cudaStream_t stream);
+int32_t kmeanspp_sample(const float* x, uint32_t n, uint32_t ldx, uint32_t ld, const float* mind, float* centroids,
+                        uint32_t c, KMeansScratch& sc, SeedSampler sampler, cudaStream_t stream);
+int32_t kmeans_update_exact_range(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
+                                  uint32_t ld, float* centroids, KMeansScratch& sc, uint32_t c_lo, uint32_t c_hi,
+                                  cudaStream_t stream);
 int32_t kmeans_update_exact(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,
                             uint32_t ld, float* centroids, KMeansScratch& sc, cudaStream_t stream);
 int32_t kmeans_cluster_sums(const float* x, uint32_t n, uint32_t ldx, const uint32_t* assign, uint32_t nc,

@@ -17,6 +17,7 @@
 
 #include "exchange.cuh"
 #include "index_internal.cuh"
+#include "kmeans.cuh"
 
 namespace vdb {
 
@@ -27,6 +28,8 @@ struct Composite {
     uint32_t max_nq = 0, max_k = 0;  // mailbox shape (grown on demand between searches)
     uint64_t next_ticket = 0;
     uint64_t total_vectors = 0;
+    uint32_t seen_nq = 0, seen_np = 0, seen_k = 0;  // largest search shape so far (scratch is reserved for it)
+    bool peer_all = false;  // every pair of distinct shard devices has peer access (data-parallel training)
 };
 
 namespace {
@@ -100,23 +103,206 @@ int32_t composite_destroy(vdb_index* ix) {
     return VDB_OK;
 }
 
-// train: k-means on the root (bit-exact, ivf_flat_index.cpp:49-145), centroids and the byte-balanced owner table
-// copied to the other shards
-int32_t composite_train(vdb_index* ix, const float* vectors, uint64_t n) {
+// Data-parallel training, bit-identical to the single-GPU trainer (and so to ivf_flat_index.cpp:49-145).
+// Every device holds the whole training sample (3 GB at the largest config) but WORKS on a slice of it:
+//   k-means++   per seed: each rank folds the newest seed into the running minimum of ITS rows
+//               (seed_dist_tma_kernel, HBM-bound) and stores the new minima straight into every rank's copy over
+//               NVLink; then every rank runs the exact D^2 sampler on the full array -- redundantly, since the
+//               reference's sequential fp32 sum does not split -- and so picks the same row without any exchange.
+//               Two copies of the minima alternate by seed, so a rank may write seed c+1 while a peer still samples c.
+//   Lloyd x 10  assignment of the rank's rows (tensor cores), slices copied to all ranks; then the CLUSTERS are
+//               partitioned: a rank sums and divides only its clusters, over all rows in input order -- one rank
+//               per cluster keeps the reference's summation order -- and copies its centroid rows to all ranks.
+// Ranks meet through events recorded after each step and waited for by the other ranks' streams (no host sync
+// inside the loops).  The last assignment also yields the list sizes that balance the list ownership by bytes.
+int32_t composite_train(vdb_index* ix, const float* vectors, uint64_t n64) {
     std::lock_guard<std::mutex> lock(ix->mu);
     Composite* c = ix->composite;
-    vdb_index* root = c->shards[c->root];
-    VDB_TRY(vdb_index_train(root, vectors, n));
-    std::vector<float> cent((size_t)ix->cfg.nlist * ix->cfg.dimension);
-    std::vector<uint8_t> owners(ix->cfg.nlist);
-    VDB_TRY(vdb_index_get_centroids(root, cent.data()));
-    VDB_TRY(vdb_index_get_owners(root, owners.data()));
-    for (uint32_t r = 0; r < c->shards.size(); ++r) {
-        if (r == c->root) continue;
-        VDB_TRY(vdb_index_set_centroids(c->shards[r], cent.data()));
-        if (c->total_vectors == 0) VDB_TRY(vdb_index_set_owners(c->shards[r], owners.data()));
+    const uint32_t R = (uint32_t)c->shards.size();
+    VDB_REQUIRE(n64 < 0xffffffffull, "train: at most 2^32-2 training vectors");
+    const uint32_t n = (uint32_t)n64, dim = ix->cfg.dimension, nlist = ix->cfg.nlist;
+    const uint32_t ld = c->shards[0]->ld;
+    const int vdev = device_of(vectors);
+    if (R == 1 || n < 4096 || !c->peer_all) {  // nothing to split (or no peer access between all devices)
+        vdb_index* root = c->shards[c->root];
+        VDB_TRY(vdb_index_train(root, vectors, n));
+        std::vector<float> cent((size_t)nlist * dim);
+        std::vector<uint8_t> owners(nlist);
+        VDB_TRY(vdb_index_get_centroids(root, cent.data()));
+        VDB_TRY(vdb_index_get_owners(root, owners.data()));
+        for (uint32_t r = 0; r < R; ++r) {
+            if (r == c->root) continue;
+            VDB_TRY(vdb_index_set_centroids(c->shards[r], cent.data()));
+            if (c->total_vectors == 0) VDB_TRY(vdb_index_set_owners(c->shards[r], owners.data()));
+        }
+        return VDB_OK;
     }
-    return VDB_OK;
+
+    struct Rank {
+        vdb_index* ix = nullptr;
+        DevBuf<float> xbuf, xraw;
+        const float* x = nullptr;
+        KMeansScratch sc;
+        SeedDistPlan plan;
+        cudaEvent_t ev = nullptr;
+        uint32_t lo = 0, hi = 0, c_lo = 0, c_hi = 0;
+    };
+    std::vector<Rank> rk(R);
+    auto cleanup = [&] {
+        for (Rank& r : rk) {
+            if (!r.ix) continue;
+            DeviceGuard g(r.ix->device);
+            cudaStreamSynchronize(r.ix->stream);
+            r.sc.release();
+            r.xbuf.release();
+            r.xraw.release();
+            if (r.ev) cudaEventDestroy(r.ev);
+        }
+    };
+    auto run = [&]() -> int32_t {
+        const uint32_t per = ((n + R - 1) / R + 127) / 128 * 128;  // slices start on a TMA box boundary
+        const uint32_t cper = (nlist + R - 1) / R;
+        // ---- the sample on every device, [n][ld] zero padded
+        for (uint32_t r = 0; r < R; ++r) {
+            Rank& k = rk[r];
+            k.ix = c->shards[r];
+            DeviceGuard g(k.ix->device);
+            std::lock_guard<std::mutex> l2(k.ix->mu);
+            cudaStream_t st = k.ix->stream;
+            k.lo = std::min(n, r * per);
+            k.hi = std::min(n, (r + 1) * per);
+            k.c_lo = std::min(nlist, r * cper);
+            k.c_hi = std::min(nlist, (r + 1) * cper);
+            VDB_CUDA_TRY(cudaEventCreateWithFlags(&k.ev, cudaEventDisableTiming));
+            if (vdev == k.ix->device && dim == ld && !((uintptr_t)vectors & 15)) {
+                k.x = vectors;
+            } else {
+                VDB_TRY(k.xbuf.reserve((size_t)n * ld));
+                const float* src = vectors;
+                if (vdev >= 0 && vdev != k.ix->device) {  // another GPU's rows: over NVLink first
+                    VDB_TRY(k.xraw.reserve((size_t)n * dim));
+                    VDB_CUDA_TRY(cudaMemcpyPeerAsync(k.xraw.p, k.ix->device, vectors, vdev, (size_t)n * dim * 4, st));
+                    src = k.xraw.p;
+                }
+                if (vdev >= 0) {
+                    VDB_TRY(launch_pad_rows(src, dim, dim, k.xbuf.p, ld, n, st));
+                } else if (dim == ld) {
+                    VDB_CUDA_TRY(cudaMemcpyAsync(k.xbuf.p, src, (size_t)n * ld * 4, cudaMemcpyHostToDevice, st));
+                } else {
+                    VDB_CUDA_TRY(cudaMemsetAsync(k.xbuf.p, 0, (size_t)n * ld * 4, st));
+                    VDB_CUDA_TRY(cudaMemcpy2DAsync(k.xbuf.p, (size_t)ld * 4, src, (size_t)dim * 4, (size_t)dim * 4, n,
+                                                   cudaMemcpyHostToDevice, st));
+                }
+                k.x = k.xbuf.p;
+            }
+            k.sc.mind_copies = 2;
+            VDB_TRY(k.sc.reserve(n, nlist, ld));
+            VDB_TRY(kmeanspp_dist_plan(k.x + (size_t)k.lo * ld, k.hi - k.lo, ld, dim, ld, &k.plan));
+            // first seed (same generator state on every rank); both copies of the minima start at FLT_MAX
+            VDB_TRY(kmeanspp_init(k.x, n, ld, ld, k.ix->centroids.p, k.sc, k.sc.mind, (uint64_t)2 * n, st));
+        }
+        // every rank's buffers exist and are initialised before any peer writes into them
+        for (Rank& k : rk) {
+            DeviceGuard g(k.ix->device);
+            VDB_CUDA_TRY(cudaStreamSynchronize(k.ix->stream));
+        }
+        auto meet = [&]() -> int32_t {  // every stream continues only when every rank reached this point
+            for (Rank& k : rk) {
+                DeviceGuard g(k.ix->device);
+                VDB_CUDA_TRY(cudaEventRecord(k.ev, k.ix->stream));
+            }
+            for (uint32_t r = 0; r < R; ++r) {
+                DeviceGuard g(rk[r].ix->device);
+                for (uint32_t p = 0; p < R; ++p)
+                    if (p != r) VDB_CUDA_TRY(cudaStreamWaitEvent(rk[r].ix->stream, rk[p].ev, 0));
+            }
+            return VDB_OK;
+        };
+        const vdb_config& cfg = c->shards[0]->cfg;
+        const SeedSampler sampler = cfg.train_mode == VDB_TRAIN_EXACT  ? SeedSampler::Sequential
+                                    : cfg.train_mode == VDB_TRAIN_FAST ? SeedSampler::Fast
+                                                                       : SeedSampler::ExactParallel;
+        // ---- k-means++ (always L2, ivf_flat_index.cpp:63-104)
+        for (uint32_t s = 1; s < nlist; ++s) {
+            const uint32_t cur = s & 1u, prev = cur ^ 1u;
+            for (Rank& k : rk) {
+                DeviceGuard g(k.ix->device);
+                PeerF32 out{};
+                out.n = R;
+                for (uint32_t p = 0; p < R; ++p) out.p[p] = rk[p].sc.mind + (size_t)cur * n + k.lo;
+                VDB_TRY(kmeanspp_dist(k.plan, k.ix->centroids.p + (size_t)(s - 1) * ld,
+                                      k.sc.mind + (size_t)prev * n + k.lo, out, k.ix->stream));
+            }
+            VDB_TRY(meet());
+            for (Rank& k : rk) {
+                DeviceGuard g(k.ix->device);
+                VDB_TRY(kmeanspp_sample(k.x, n, ld, ld, k.sc.mind + (size_t)cur * n, k.ix->centroids.p, s, k.sc, sampler,
+                                        k.ix->stream));
+            }
+        }
+        // ---- slice assignment copied to every rank
+        auto assign_all = [&]() -> int32_t {
+            for (Rank& k : rk) {
+                DeviceGuard g(k.ix->device);
+                if (k.hi > k.lo)
+                    VDB_TRY(index_assign_rows(k.ix, k.x + (size_t)k.lo * ld, k.hi - k.lo, k.sc.assign + k.lo, k.ix->stream));
+                for (Rank& p : rk)
+                    if (&p != &k && k.hi > k.lo)
+                        VDB_CUDA_TRY(cudaMemcpyPeerAsync(p.sc.assign + k.lo, p.ix->device, k.sc.assign + k.lo, k.ix->device,
+                                                         (size_t)(k.hi - k.lo) * 4, k.ix->stream));
+            }
+            return meet();
+        };
+        // ---- exactly 10 Lloyd iterations; assignment honours the index metric (:109-142, :275-285)
+        for (int iter = 0; iter < 10; ++iter) {
+            VDB_TRY(assign_all());
+            for (Rank& k : rk) {
+                DeviceGuard g(k.ix->device);
+                VDB_TRY(kmeans_update_exact_range(k.x, n, ld, k.sc.assign, nlist, ld, k.ix->centroids.p, k.sc, k.c_lo, k.c_hi,
+                                                  k.ix->stream));
+                for (Rank& p : rk)
+                    if (&p != &k && k.c_hi > k.c_lo)
+                        VDB_CUDA_TRY(cudaMemcpyPeerAsync(p.ix->centroids.p + (size_t)k.c_lo * ld, p.ix->device,
+                                                         k.ix->centroids.p + (size_t)k.c_lo * ld, k.ix->device,
+                                                         (size_t)(k.c_hi - k.c_lo) * ld * 4, k.ix->stream));
+            }
+            VDB_TRY(meet());
+        }
+        // ---- list sizes of the sample under the final centroids -> byte-balanced ownership (as vdb_index_train)
+        std::vector<uint32_t> counts(nlist + 1, 0);
+        if (c->total_vectors == 0) {
+            VDB_TRY(assign_all());
+            Rank& k = rk[c->root];
+            DeviceGuard g(k.ix->device);
+            VDB_TRY(k.ix->hist_buf.reserve(nlist + 1));
+            VDB_CUDA_TRY(cudaMemsetAsync(k.ix->hist_buf.p, 0, (size_t)(nlist + 1) * 4, k.ix->stream));
+            VDB_TRY(launch_hist(k.sc.assign, n, nlist, 0, nullptr, k.ix->hist_buf.p, k.ix->stream));
+            VDB_CUDA_TRY(cudaMemcpyAsync(counts.data(), k.ix->hist_buf.p, (size_t)(nlist + 1) * 4, cudaMemcpyDeviceToHost,
+                                         k.ix->stream));
+        }
+        for (Rank& k : rk) {
+            DeviceGuard g(k.ix->device);
+            VDB_CUDA_TRY(cudaStreamSynchronize(k.ix->stream));
+        }
+        counts.resize(nlist);
+        for (Rank& k : rk) {
+            DeviceGuard g(k.ix->device);
+            std::lock_guard<std::mutex> l2(k.ix->mu);
+            VDB_TRY(index_refresh_centroids(k.ix));
+            if (c->total_vectors == 0) {
+                index_balance_owners(k.ix, counts);
+                VDB_TRY(index_upload_owners(k.ix));
+            }
+            VDB_CUDA_TRY(cudaStreamSynchronize(k.ix->stream));
+            k.ix->trained = true;
+        }
+        return VDB_OK;
+    };
+    const int32_t st = run();
+    std::string msg = st == VDB_OK ? std::string() : std::string(vdb_last_error_string());
+    cleanup();
+    if (st != VDB_OK) set_last_error(msg);
+    return st;
 }
 
 int32_t composite_set_centroids(vdb_index* ix, const float* in) {
@@ -195,7 +381,10 @@ int32_t composite_reserve_search(vdb_index* ix, uint32_t nq, uint32_t np, uint32
     std::lock_guard<std::mutex> lock(ix->mu);
     Composite* c = ix->composite;
     if (nq > c->max_nq || k > c->max_k) VDB_TRY(connect_mailboxes(c, std::max(nq, c->max_nq), std::max(k, c->max_k)));
-    for (vdb_index* s : c->shards) VDB_TRY(vdb_index_reserve_search(s, nq, np, k));
+    c->seen_nq = std::max(c->seen_nq, nq);
+    c->seen_np = std::max(c->seen_np, np);
+    c->seen_k = std::max(c->seen_k, k);
+    for (vdb_index* s : c->shards) VDB_TRY(vdb_index_reserve_search(s, c->seen_nq, c->seen_np, c->seen_k));
     return VDB_OK;
 }
 
@@ -208,6 +397,14 @@ int32_t composite_submit(vdb_index* ix, const float* queries, uint32_t nq, uint3
     const uint32_t world = (uint32_t)c->shards.size();
     VDB_REQUIRE((uint64_t)world * k <= 4096, "search: shards * k must be <= 4096");
     if (nq > c->max_nq || k > c->max_k) VDB_TRY(connect_mailboxes(c, std::max(nq, c->max_nq), std::max(k, c->max_k)));
+    // a shape larger than any seen so far: every shard allocates its search scratch NOW, before anything of this
+    // search is enqueued (see below why no allocation may happen in between)
+    if (nq > c->seen_nq || nprobe > c->seen_np || k > c->seen_k) {
+        c->seen_nq = std::max(c->seen_nq, nq);
+        c->seen_np = std::max(c->seen_np, nprobe);
+        c->seen_k = std::max(c->seen_k, k);
+        for (vdb_index* s : c->shards) VDB_TRY(vdb_index_reserve_search(s, c->seen_nq, c->seen_np, c->seen_k));
+    }
     // a batch whose partial results do not fit one pass on some shard is split evenly on all of them
     uint32_t chunk = nq;
     for (vdb_index* s : c->shards) {
@@ -222,10 +419,12 @@ int32_t composite_submit(vdb_index* ix, const float* queries, uint32_t nq, uint3
         const uint32_t m = std::min(chunk, nq - lo);
         const float* q = queries + (size_t)lo * ix->cfg.dimension;
         const uint64_t t = ++c->next_ticket;
-        // root first: recycling its slot waits (on the host) for the collect that used it `depth` tickets ago
+        // The root goes LAST: its collect kernel spins until every shard has published, so nothing that can block
+        // the host (a first-seen shape allocating scratch: cudaFree synchronises the device and, through the
+        // peer mappings, its peers) may sit between enqueuing the collect and enqueuing the publishes it waits for.
         std::vector<SearchSlot*> slot(world, nullptr);
         for (uint32_t i = 0; i < world; ++i) {
-            const uint32_t r = (c->root + i) % world;
+            const uint32_t r = (c->root + 1 + i) % world;
             vdb_index* s = c->shards[r];
             DeviceGuard g(s->device);
             uint64_t ts = 0;
@@ -233,14 +432,14 @@ int32_t composite_submit(vdb_index* ix, const float* queries, uint32_t nq, uint3
             VDB_REQUIRE(ts == t, "sharded search: a shard was searched behind the composite's back");
         }
         // the two mailbox halves alternate by ticket: a non-root shard may overwrite half (t & 1) only after the
-        // root has collected ticket t - 2 from it
+        // root has collected ticket t - 2 from it (with depth <= 2 recycling the root's slot has waited for that)
         cudaEvent_t collected = nullptr;
         if (t > 2 && root->depth > 2) {
             SearchSlot& prev = root->slots[(t - 2) % root->depth];
             if (prev.busy) collected = prev.ev_done;
         }
         for (uint32_t i = 0; i < world; ++i) {
-            const uint32_t r = (c->root + i) % world;
+            const uint32_t r = (c->root + 1 + i) % world;
             vdb_index* s = c->shards[r];
             DeviceGuard g(s->device);
             SearchStreams st = index_pipeline_streams(s, t);
@@ -404,6 +603,21 @@ extern "C" int32_t vdb_index_create_sharded(const vdb_config* cfg, const int32_t
         if (st != VDB_OK) return fail(st);
         c->shards.push_back(s);
     }
+    c->peer_all = true;
+    for (int32_t a = 0; a < ndev; ++a)
+        for (int32_t b = 0; b < ndev; ++b) {
+            if (devices[a] == devices[b]) continue;
+            DeviceGuard g(devices[a]);
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) != cudaSuccess || !can) {
+                cudaGetLastError();
+                c->peer_all = false;
+                continue;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) c->peer_all = false;
+            cudaGetLastError();
+        }
     const int32_t st = connect_mailboxes(c.get(), 256, 64);
     if (st != VDB_OK) {
         for (vdb_exchange* e : c->exchanges) vdb_exchange_destroy(e);
