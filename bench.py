@@ -34,6 +34,12 @@ PKG = "cuda-acceleratedvectordatabaseengine_b200"
 METRIC = "IVF-Flat QPS @10M x 768D nprobe=32 k=10"
 
 
+def metric_name(a):
+    if (a.n, a.dim, a.nprobe, a.k) == (10_000_000, 768, 32, 10):
+        return METRIC
+    return f"IVF-Flat QPS @{a.n / 1e6:g}M x {a.dim}D nprobe={a.nprobe} k={a.k}"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -64,7 +70,8 @@ def parse():
 def workload_name(a):
     shape = (a.n, a.dim, a.metric, a.nlist, a.nprobe, a.k, a.batch)
     tag = {(10_000_000, 768, "l2", 4096, 32, 10, 64): " (BASELINE.json configs[2])",
-           (100_000_000, 768, "ip", 16384, 64, 10, 64): " (BASELINE.json configs[3])"}.get(shape, "")
+           (100_000_000, 768, "ip", 16384, 64, 10, 64): " (BASELINE.json configs[3])",
+           (100_000, 128, "l2", 128, 16, 10, 64): " (BASELINE.json configs[0])"}.get(shape, "")
     return (f"IVF-Flat {a.n / 1e6:g}M x {a.dim}D {'L2' if a.metric == 'l2' else 'inner product'} nlist={a.nlist} "
             f"nprobe={a.nprobe} k={a.k} batch={a.batch}{tag}")
 
@@ -204,7 +211,7 @@ def run_reference(a):
     if rank != 0:
         return
     r = reference_sample(a, a.steps, a.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": a.gpus,
+    line = {"impl": "reference", "metric": metric_name(a), "value": r["value"], "unit": "queries/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a)},
@@ -457,7 +464,7 @@ def run_b200(a):
     headline = (a.n, a.dim, a.metric, a.nlist, a.nprobe, a.k, a.batch) == (10_000_000, 768, "l2", 4096, 32, 10, 64)
     launches_per_step = 5 + (1 if world > 1 else 0)
     line = {
-        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": metric_name(a), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a) + (f" [shard 0 of {a.emulate_shards} only: tuning run]" if shard_count != world else ""),
@@ -499,9 +506,167 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------- configs[1]: brute force
+
+def tensor_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]) / 2.0, "measured bf16 burst / 2 (TF32 operands, MEASURED_PEAKS.json)"
+    except Exception:
+        return 1100.0, "fallback: 2250 / 2 nominal"
+
+
+def run_c2(a):
+    """BASELINE configs[1]: exact top-100 of 1024 queries against a flat 1M x 768 database (vdb_bruteforce_search:
+    TF32 tcgen05 contraction over nested samples + exact fp32 re-scoring).  A step = one batch of 1024 fresh queries."""
+    import numpy as np
+    import torch
+    import oracle_lib as O
+    pkg = importlib.import_module(PKG)
+    pkg.lib()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, dim, nq, k = 1_000_000, 768, 1024, 100
+    gen = torch.Generator(device=dev).manual_seed(12345)
+    db = torch.randn(n, dim, generator=gen, device=dev)
+    nb = a.warmup + a.steps
+    q_all = torch.randn(nb, nq, dim, generator=gen, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    sampler = ClockSampler(0)
+    for s in range(a.warmup):
+        pkg.bruteforce_search(db, q_all[s], k, stream=stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for s in range(a.steps):
+        D, I = pkg.bruteforce_search(db, q_all[a.warmup + s], k, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    q_host = q_all.cpu().pin_memory()
+    Dh = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    Ih = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    lib = pkg.lib()
+
+    def e2e_step(s):
+        pkg._check(lib.vdb_bruteforce_search(db.data_ptr(), q_host[s].data_ptr(), None, n, nq, dim, k, Dh.data_ptr(),
+                                             Ih.data_ptr(), 0, stream))
+    for s in range(min(3, a.warmup)):
+        e2e_step(s)
+    te = time.perf_counter()
+    for s in range(a.steps):
+        e2e_step(a.warmup + s)
+    te = time.perf_counter() - te
+    clocks = sampler.stop(t0, time.time())
+    # untimed check of the last batch's first queries against the oracle's flat search (all host cores)
+    ncores = os.cpu_count() or 1
+    cpu = None
+    if not a.no_cpu_baseline:
+        ora = O.OracleIndex(dim, 1)
+        ora.centroids = np.zeros((1, dim), np.float32)
+        ora.load_assigned(db.cpu().numpy(), np.arange(n, dtype=np.uint64), np.zeros(n, np.uint32))
+        m = min(nq, 2 * ncores)
+        qs = q_all[nb - 1, :m].cpu().numpy()
+        t = time.perf_counter()
+        Dr, Ir = ora.search(qs, 1, k, ncores)
+        dt = time.perf_counter() - t
+        from parity import check_search
+        check_search(D[:m].cpu().numpy(), I[:m].cpu().numpy().view(np.uint64), Dr, Ir)
+        cpu = {"value": m / dt, "unit": "queries/s", "cores": ncores, "kind": "port",
+               "sample": f"{m} of the 1024 queries of one batch against the full 1M x 768 database (oracle search_list_cpu "
+                         f"over one list), results equal to the GPU's"}
+    flops = 2.0 * nq * n * dim
+    peak, src = tensor_peak()
+    ach = flops / (ms / a.steps / 1e3) / 1e12
+    print(json.dumps({
+        "metric": "brute-force flat L2 QPS @1M x 768D, 1024 queries, k=100", "value": nq * a.steps / (ms / 1e3),
+        "unit": "queries/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core screen, fp32 exact re-score)",
+        "data": "synthetic",
+        "config": {"workload": "brute-force flat L2 1M x 768D, query batch 1024, k=100 (BASELINE.json configs[1])",
+                   "cache": "the 3.07 GB database exceeds L2; fresh queries every step"},
+        "roofline": {"bound": "tensor", "kernel": "vdb_bruteforce_search (whole call: row norms, 4 sampled GEMM levels, "
+                     "full GEMM, threshold and select kernels; the full-level rowtile_gemm_kernel is ~half of it)",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": src, "algorithmic_flops_per_launch": flops},
+        "cpu_baseline": cpu,
+        "e2e": {"value": nq * a.steps / te, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+                "d2h_bytes_per_step": nq * k * 12},
+        "gpu_launches": a.steps * 14, "clocks": clocks}), flush=True)
+
+
+# ------------------------------------------- configs[4]: k-means train + add
+
+def run_c5(a):
+    """BASELINE configs[4]: k-means training on the first 1M rows + add() of 10M x 768 rows at nlist 16384, one
+    process over --devices (vdb_index_create_sharded).  A step = one add() batch of 1M rows; training is timed
+    once and reported in config."""
+    import hashlib
+    import numpy as np
+    import torch
+    pkg = importlib.import_module(PKG)
+    pkg.lib()
+    devs = tuple(int(d) for d in a.devices.split(",")) if a.devices else (0,)
+    dev = torch.device("cuda", devs[0])
+    torch.cuda.set_device(devs[0])
+    dim, nlist, ntrain, rows, bs = 768, 16384, 1_000_000, 10_000_000, 1_000_000
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist, devices=devs if len(devs) > 1 else (), device=devs[0]))
+    gen = torch.Generator(device=dev).manual_seed(12345)
+    xt = torch.randn(ntrain, dim, generator=gen, device=dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(devs[0])
+    t0 = time.time()
+    t = time.perf_counter()
+    ix.train(xt)
+    train_s = time.perf_counter() - t
+    del xt
+    sha = hashlib.sha256(np.ascontiguousarray(ix.centroids).tobytes()).hexdigest()
+    nb = rows // bs
+    t_add = 0.0
+    for b in range(nb):
+        x = torch.randn(bs, dim, generator=gen, device=dev)
+        ids = torch.arange(b * bs, (b + 1) * bs, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        ix.add(x, ids)
+        t_add += time.perf_counter() - t
+    # e2e: the same add() from HOST rows (pinned), two more batches
+    xh = torch.randn(bs, dim, generator=gen, device=dev).cpu().pin_memory()
+    idh = torch.arange(rows, rows + bs, dtype=torch.int64).pin_memory()
+    t = time.perf_counter()
+    for b in range(2):
+        ix.add(xh, idh + b * bs)
+    e2e_s = (time.perf_counter() - t) / 2
+    clocks = sampler.stop(t0, time.time())
+    flops = 2.0 * bs * nlist * dim
+    peak, src = tensor_peak()
+    ach = flops / (t_add / nb) / 1e12 / len(devs)  # every shard assigns the whole batch: per-GPU rate
+    print(json.dumps({
+        "metric": "add() rows/s @10M x 768D nlist=16384 (after k-means training on 1M rows)", "value": rows / t_add,
+        "unit": "rows/s", "n_gpus": len(devs), "steps": nb, "warmup": 0, "ms_per_step": t_add / nb * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core screen, fp32 exact re-check)",
+        "data": "synthetic",
+        "config": {"workload": "k-means IVF training + batched add() 10M x 768D nlist=16384 (BASELINE.json configs[4])",
+                   "parallelism": f"one process, {len(devs)} shard(s): data-parallel bit-exact training; every shard assigns "
+                                  f"each batch and keeps the lists it owns",
+                   "train_s": round(train_s, 3), "ntrain": ntrain, "centroid_sha256": sha,
+                   "rows_held_all_shards": int(ix.list_sizes().sum()), "index_gb": round(ix.stats().gpu_memory_bytes / 1e9, 2)},
+        "roofline": {"bound": "tensor", "kernel": "rowtile_gemm_kernel<AssignEpi> inside add() (assignment + staging + scatter timed together)",
+                     "achieved": ach * len(devs) if len(devs) == 1 else ach, "peak": peak, "unit": "TFLOP/s",
+                     "frac": ach / peak, "traffic": None, "peak_source": src, "algorithmic_flops_per_launch": flops},
+        "cpu_baseline": None,
+        "e2e": {"value": bs / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": bs * (dim * 4 + 8) * len(devs), "d2h_bytes_per_step": 0},
+        "gpu_launches": nb * 8 * len(devs), "clocks": clocks}), flush=True)
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c2":
+        run_c2(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_b200(args)

@@ -242,7 +242,10 @@ int32_t composite_train(vdb_index* ix, const float* vectors, uint64_t n64) {
         }
         // ---- slice assignment copied to every rank
         auto assign_all = [&]() -> int32_t {
-            for (Rank& k : rk) {
+            // one host thread per rank: the tensor-core assignment synchronises its stream once (overflow count),
+            // which would otherwise serialise the ranks
+            VDB_TRY(for_each_shard_parallel(c, [&](uint32_t r) -> int32_t {
+                Rank& k = rk[r];
                 DeviceGuard g(k.ix->device);
                 if (k.hi > k.lo)
                     VDB_TRY(index_assign_rows(k.ix, k.x + (size_t)k.lo * ld, k.hi - k.lo, k.sc.assign + k.lo, k.ix->stream));
@@ -250,7 +253,8 @@ int32_t composite_train(vdb_index* ix, const float* vectors, uint64_t n64) {
                     if (&p != &k && k.hi > k.lo)
                         VDB_CUDA_TRY(cudaMemcpyPeerAsync(p.sc.assign + k.lo, p.ix->device, k.sc.assign + k.lo, k.ix->device,
                                                          (size_t)(k.hi - k.lo) * 4, k.ix->stream));
-            }
+                return VDB_OK;
+            }));
             return meet();
         };
         // ---- exactly 10 Lloyd iterations; assignment honours the index metric (:109-142, :275-285)
@@ -347,14 +351,15 @@ int32_t composite_add(vdb_index* ix, const float* vectors, const uint64_t* ids, 
             const float* v = vectors + lo * dim;
             if (v_remote) {
                 if ((st = vb.reserve(m * dim)) != VDB_OK) break;
-                if (cudaMemcpyPeer(vb.p, s->device, v, vdev, m * dim * 4) != cudaSuccess) { st = VDB_CUDA_ERROR; break; }
+                // on the shard's own (non-blocking) stream, so that add()'s kernels are ordered behind the copy
+                if (cudaMemcpyPeerAsync(vb.p, s->device, v, vdev, m * dim * 4, s->stream) != cudaSuccess) { st = VDB_CUDA_ERROR; break; }
                 v = vb.p;
             }
             const uint64_t* id = ids ? ids + lo : nullptr;
             std::vector<uint64_t> seq;
             if (ids && i_remote) {
                 if ((st = ib.reserve(m)) != VDB_OK) break;
-                if (cudaMemcpyPeer(ib.p, s->device, id, idev, m * 8) != cudaSuccess) { st = VDB_CUDA_ERROR; break; }
+                if (cudaMemcpyPeerAsync(ib.p, s->device, id, idev, m * 8, s->stream) != cudaSuccess) { st = VDB_CUDA_ERROR; break; }
                 id = ib.p;
             } else if (!ids) {
                 seq.resize(m);

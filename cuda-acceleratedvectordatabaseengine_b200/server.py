@@ -140,13 +140,22 @@ class RequestCoalescer:
 
 
 class VdbServicer:
-    def __init__(self, pkg, device=0, coalesce=True, batch_size=64, window_ms=2.0):
-        self.pkg, self.device = pkg, device
+    """data_dir: where BuildEpoch persists epochs -- <data_dir>/<index>/<epoch id>/ in the reference's epoch layout
+    (format/storage.cpp:318-348: manifest.json + Arrow IPC files); ActivateEpoch / LoadIndex load such a directory
+    into a fresh HBM index and swap it in (server/query_service.cpp:515-519, 232-257).  devices: more than one entry
+    makes every index a single-process sharded one (one list shard per GPU)."""
+
+    def __init__(self, pkg, device=0, coalesce=True, batch_size=64, window_ms=2.0, data_dir=None, devices=()):
+        self.pkg, self.device, self.devices, self.data_dir = pkg, device, tuple(devices), data_dir
         self.lock = threading.RLock()
         self.specs = {}    # name -> dict(dimension, metric, nlist)
         self.indices = {}  # name -> (IVFFlatIndex, epoch id)
+        self.epochs = {}   # name -> {epoch id: directory or None (not persisted)}
         self.coalescer = RequestCoalescer(self._batched_search, batch_size, window_ms) if coalesce else None
         self.searches = 0
+        self.queries = 0
+        self.per_index = {}  # name -> [search count, latencies]
+        self.started = time.monotonic()
         self.latencies_ms = []
 
     # ---- QueryService --------------------------------------------------------------------------------
@@ -178,8 +187,13 @@ class VdbServicer:
         except Exception as e:  # noqa: BLE001
             ctx.abort(grpc.StatusCode.INTERNAL, "Search failed: " + str(e))
         with self.lock:
+            ms = (time.perf_counter() - t0) * 1e3
             self.searches += 1
-            self.latencies_ms = (self.latencies_ms + [(time.perf_counter() - t0) * 1e3])[-10000:]
+            self.queries += q.shape[0]
+            self.latencies_ms = (self.latencies_ms + [ms])[-10000:]
+            pi = self.per_index.setdefault(req.index, [0, []])
+            pi[0] += 1
+            pi[1] = (pi[1] + [ms])[-10000:]
         resp = SearchResponse()
         for qi in range(q.shape[0]):
             r = resp.results.add()
@@ -207,11 +221,39 @@ class VdbServicer:
                 ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, str(e))
         return Empty()
 
-    def LoadIndex(self, req, ctx):
+    def _new_index(self, spec):
+        return self.pkg.IVFFlatIndex(self.pkg.Config(dimension=spec["dimension"], nlist=spec["nlist"],
+                                                     metric=self.pkg.Metric(spec["metric"]), device=self.device,
+                                                     devices=self.devices))
+
+    def _load_index_internal(self, name, epoch, ctx):
+        """load_index_internal (query_service.cpp:232-257): epoch directory -> new index -> swap under the lock"""
+        from . import storage
         with self.lock:
-            if req.index not in self.specs:
-                ctx.abort(grpc.StatusCode.NOT_FOUND, "Index not found: " + req.index)
-        return Empty()  # epochs live in HBM from BuildEpoch on; nothing to load
+            spec = self.specs.get(name)
+            active = self.indices.get(name)
+            known = self.epochs.get(name, {})
+        if spec is None:
+            ctx.abort(grpc.StatusCode.NOT_FOUND, "Index not found: " + name)
+        if active is not None and (not epoch or active[1] == epoch):
+            return Empty()  # already serving that epoch
+        if epoch not in known:
+            ctx.abort(grpc.StatusCode.NOT_FOUND, "Epoch not found: " + epoch)
+        if known[epoch] is None:
+            ctx.abort(grpc.StatusCode.FAILED_PRECONDITION, "Epoch was not persisted (server has no data_dir): " + epoch)
+        try:
+            ix = self._new_index(spec)
+            storage.load_epoch(ix, known[epoch])
+        except Exception as e:  # noqa: BLE001
+            ctx.abort(grpc.StatusCode.INTERNAL, "Load failed: " + str(e))
+        with self.lock:
+            old = self.indices.get(name)
+            self.indices[name] = (ix, epoch)
+        del old  # the previous epoch's HBM is released once the searches holding it have returned
+        return Empty()
+
+    def LoadIndex(self, req, ctx):
+        return self._load_index_internal(req.index, req.epoch, ctx)
 
     # ---- AdminService --------------------------------------------------------------------------------
     def CreateIndex(self, req, ctx):
@@ -237,8 +279,7 @@ class VdbServicer:
         except Exception as e:  # noqa: BLE001
             ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, f"cannot read {req.source_path}: {e}")
         try:
-            ix = self.pkg.IVFFlatIndex(self.pkg.Config(dimension=spec["dimension"], nlist=spec["nlist"],
-                                                       metric=self.pkg.Metric(spec["metric"]), device=self.device))
+            ix = self._new_index(spec)
             first = parts[0][1]
             if first.shape[1] != spec["dimension"]:
                 ctx.abort(grpc.StatusCode.INVALID_ARGUMENT, "source dimension mismatch")
@@ -249,16 +290,26 @@ class VdbServicer:
             raise
         except Exception as e:  # noqa: BLE001
             ctx.abort(grpc.StatusCode.INTERNAL, "Build failed: " + str(e))
+        # build_index_worker (query_service.cpp:549-584): ... -> save epoch -> activate
         with self.lock:
-            n = len([k for k in self.indices if k == req.index])
-            self.indices[req.index] = (ix, f"epoch_{int(time.time())}_{n}")
+            epoch = f"epoch_{int(time.time())}_{len(self.epochs.get(req.index, {}))}"
+        path = None
+        if self.data_dir:
+            import os
+            path = os.path.join(self.data_dir, req.index, epoch)
+            try:
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                storage.save_epoch(ix, path, req.index, epoch)
+            except Exception as e:  # noqa: BLE001
+                ctx.abort(grpc.StatusCode.INTERNAL, "Build failed while writing the epoch: " + str(e))
+        with self.lock:
+            self.epochs.setdefault(req.index, {})[epoch] = path
+            self.indices[req.index] = (ix, epoch)
         return Empty()
 
     def ActivateEpoch(self, req, ctx):
-        with self.lock:
-            if req.index not in self.specs:
-                ctx.abort(grpc.StatusCode.NOT_FOUND, "Index not found: " + req.index)
-        return Empty()
+        """AdminServiceImpl::ActivateEpoch = load_index_internal(index, epoch) (query_service.cpp:515-519)"""
+        return self._load_index_internal(req.index, req.epoch, ctx)
 
     def GetStats(self, req, ctx):
         with self.lock:
@@ -274,15 +325,47 @@ class VdbServicer:
         return out
 
     def metrics_text(self):
-        """Prometheus text of the four series the reference renders (query_service.cpp:748-780)."""
+        """MetricsCollector::prometheus_format (query_service.cpp:748-780): the reference's four series, same names,
+        HELP / TYPE lines and labels, fed by real counters."""
         with self.lock:
-            lat = sorted(self.latencies_ms)
+            per = {k: (v[0], sorted(v[1])) for k, v in self.per_index.items()}
             mem = sum(e[0].get_gpu_memory_usage() for e in self.indices.values())
-            n = self.searches
-        q = (lambda p: lat[min(len(lat) - 1, int(p * len(lat)))]) if lat else (lambda p: 0.0)
-        lines = [f'vdb_search_duration_milliseconds{{quantile="{p}"}} {q(p):.3f}' for p in (0.5, 0.95, 0.99)]
-        lines += [f"vdb_searches_total {n}", f"vdb_gpu_memory_bytes {mem}"]
-        return "\n".join(lines) + "\n"
+            elapsed = max(time.monotonic() - self.started, 1e-9)
+            total = self.searches
+        q = lambda lat, p: lat[min(len(lat) - 1, int(p * len(lat)))] if lat else 0.0  # noqa: E731
+        out = ["# HELP vdb_search_duration_milliseconds Search latency in milliseconds",
+               "# TYPE vdb_search_duration_milliseconds histogram"]
+        for name, (_n, lat) in sorted(per.items()):
+            out += [f'vdb_search_duration_milliseconds{{index="{name}",quantile="{p}"}} {q(lat, p):.3f}'
+                    for p in (0.5, 0.95, 0.99)]
+        out += ["# HELP vdb_searches_total Total number of searches", "# TYPE vdb_searches_total counter"]
+        out += [f'vdb_searches_total{{index="{name}"}} {n}' for name, (n, _l) in sorted(per.items())]
+        out += ["# HELP vdb_gpu_memory_bytes GPU memory usage in bytes", "# TYPE vdb_gpu_memory_bytes gauge",
+                f"vdb_gpu_memory_bytes {mem}",
+                "# HELP vdb_queries_per_second Current queries per second", "# TYPE vdb_queries_per_second gauge",
+                f"vdb_queries_per_second {total / elapsed:.3f}"]
+        return "\n".join(out) + "\n"
+
+    def serve_metrics(self, port=0, host="127.0.0.1"):
+        """GET /metrics over HTTP (the reference's metrics endpoint); returns (http server, bound port)"""
+        import http.server
+        servicer = self
+
+        class H(http.server.BaseHTTPRequestHandler):
+            def do_GET(self):  # noqa: N802
+                body = servicer.metrics_text().encode() if self.path.startswith("/metrics") else b"not found\n"
+                self.send_response(200 if self.path.startswith("/metrics") else 404)
+                self.send_header("Content-Type", "text/plain; version=0.0.4")
+                self.send_header("Content-Length", str(len(body)))
+                self.end_headers()
+                self.wfile.write(body)
+
+            def log_message(self, *args):
+                pass
+
+        httpd = http.server.ThreadingHTTPServer((host, port), H)
+        threading.Thread(target=httpd.serve_forever, daemon=True).start()
+        return httpd, httpd.server_address[1]
 
 
 def _handlers(servicer):

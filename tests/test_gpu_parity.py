@@ -616,6 +616,17 @@ def test_full_size_config2_bruteforce_against_float64():
     check_search(D[sub].cpu().numpy(), I[sub].cpu().numpy(), ref.values.float().cpu().numpy(),
                  ref.indices.cpu().numpy().astype(np.uint64))
     del d64, vn
+    # the reference's own arithmetic on a 64-query subset -- the oracle as a flat index (nlist = 1,
+    # nprobe = 1: search_list_cpu over all 1M rows, strict left-to-right fp32), every host core on its own queries
+    sub64 = np.arange(0, nq, 16)
+    dbh = db.cpu().numpy()
+    ora = O.OracleIndex(dim, 1)
+    ora.centroids = np.zeros((1, dim), np.float32)
+    ora.load_assigned(dbh, np.arange(n, dtype=np.uint64), np.zeros(n, np.uint32))
+    Dr, Ir = ora.search(q[torch.from_numpy(sub64).cuda()].cpu().numpy(), 1, k, os.cpu_count() or 1)
+    check_search(D[sub64].cpu().numpy(), I[sub64].cpu().numpy(), Dr, Ir)
+    ora.close()
+    del dbh
     D8, I8 = pkg.bruteforce_search(db, q[:8], k)   # < 16 queries: the exact scan kernel
     check_search(D[:8].cpu().numpy(), I[:8].cpu().numpy(), D8.cpu().numpy(), I8.cpu().numpy())
 
@@ -676,3 +687,21 @@ def test_full_size_config3_ivf_equals_bruteforce_and_is_monotone():
     assert (owner[:, :, None] == probes[:, None, :]).any(-1).all()
     d_chk = ((db[I32.reshape(-1)].reshape(nq, k, dim) - q[:, None, :]) ** 2).sum(-1)
     assert torch.allclose(d_chk, D32, rtol=1e-5)
+    # COMPLETENESS of the headline setting, from an independent truth: assign all 10M rows, keep the rows whose list
+    # one of the query's 32 probes names, evaluate their distances in float64 with torch, take the top-k.  No row of
+    # a probed list may have been dropped by the scan's bound pruning (global per-query threshold, item pruning).
+    assign = torch.cat([ix.assign_device(db[lo:lo + 1_000_000]) for lo in range(0, n, 1_000_000)]).long()
+    assert torch.equal(torch.bincount(assign, minlength=nlist).cpu(), torch.from_numpy(sizes))
+    Dt = np.empty((nq, k), np.float32)
+    It = np.empty((nq, k), np.uint64)
+    for qi in range(nq):
+        rows = torch.isin(assign, probes[qi]).nonzero().squeeze(1)
+        d = torch.empty(rows.numel(), dtype=torch.float64, device="cuda")
+        for lo in range(0, rows.numel(), 131072):
+            r = rows[lo:lo + 131072]
+            d[lo:lo + 131072] = ((db[r].double() - q[qi].double()[None, :]) ** 2).sum(1)
+        # top-k by (distance, id): a stable sort of ids-ascending rows by distance
+        order = torch.argsort(d, stable=True)[:k]
+        Dt[qi] = d[order].float().cpu().numpy()
+        It[qi] = rows[order].cpu().numpy().astype(np.uint64)
+    check_search(D32.cpu().numpy(), I32.cpu().numpy().view(np.uint64), Dt, It)

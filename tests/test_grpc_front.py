@@ -130,3 +130,59 @@ def test_build_epoch_and_search_parity(endpoint, tmp_path):
     bad.queries.add().values.extend([0.0] * (dim + 1))
     assert code(c.Search, bad) == grpc.StatusCode.INVALID_ARGUMENT  # dimension mismatch
     assert "vdb_searches_total" in servicer.metrics_text()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", [(), (0, 0)])
+def test_epochs_are_persisted_activated_and_measured(tmp_path, devices):
+    """N3 + N4: BuildEpoch writes the reference's epoch directory, ActivateEpoch / LoadIndex swap a stored epoch
+    back in (query_service.cpp:515-519, 232-257), GetStats names the serving epoch, and /metrics renders the
+    reference's four Prometheus series from real counters (query_service.cpp:748-780)."""
+    import json
+    import urllib.request
+    server, servicer = srv.serve(pkg, address="127.0.0.1:0", data_dir=str(tmp_path / "data"), devices=devices)
+    c = srv.Client(f"127.0.0.1:{server.bound_port}")
+    try:
+        dim, nlist, n = 24, 6, 3000
+        a, b = O.gaussian(1, n, dim), O.gaussian(2, n, dim) + 3.0
+        pa_, pb_ = os.path.join(tmp_path, "a.arrow"), os.path.join(tmp_path, "b.arrow")
+        storage.write_vectors(pa_, a)
+        storage.write_vectors(pb_, b, np.arange(n, dtype=np.uint64) + 10**6)
+        assert code(c.CreateIndex, srv.CreateIndexRequest(name="ix", dimension=dim, metric="L2", nlist=nlist)) == grpc.StatusCode.OK
+        assert code(c.BuildEpoch, srv.BuildEpochRequest(index="ix", source_path=pa_)) == grpc.StatusCode.OK
+        e1 = c.GetStats(srv.StatsRequest(index="ix")).current_epoch
+        assert code(c.BuildEpoch, srv.BuildEpochRequest(index="ix", source_path=pb_)) == grpc.StatusCode.OK
+        e2 = c.GetStats(srv.StatsRequest(index="ix")).current_epoch
+        assert e1 and e2 and e1 != e2
+        for e in (e1, e2):  # both epochs are complete directories in the reference's layout
+            m = json.load(open(os.path.join(tmp_path, "data", "ix", e, "manifest.json")))
+            assert m["index_name"] == "ix" and m["epoch"] == e and m["dimension"] == dim and m["nlist"] == nlist
+            assert sum(s["num_vectors"] for s in m["shards"]) == n
+
+        def nearest(vec):
+            r = srv.SearchRequest(index="ix", topk=1, nprobe=nlist)
+            r.queries.add().values.extend(vec.tolist())
+            return c.Search(r, timeout=60).results[0].neighbors[0]
+
+        assert nearest(b[5]).id == 10**6 + 5 and nearest(b[5]).distance == 0.0  # epoch 2 serves
+        assert code(c.ActivateEpoch, srv.ActivateEpochRequest(index="ix", epoch=e1)) == grpc.StatusCode.OK
+        assert c.GetStats(srv.StatsRequest(index="ix")).current_epoch == e1
+        assert nearest(a[7]).id == 7 and nearest(a[7]).distance == 0.0           # epoch 1 again, loaded from disk
+        assert code(c.LoadIndex, srv.LoadIndexRequest(index="ix", epoch=e2)) == grpc.StatusCode.OK
+        assert nearest(b[9]).id == 10**6 + 9
+        assert code(c.ActivateEpoch, srv.ActivateEpochRequest(index="ix", epoch="epoch_0_none")) == grpc.StatusCode.NOT_FOUND
+        assert code(c.ActivateEpoch, srv.ActivateEpochRequest(index="nope", epoch=e1)) == grpc.StatusCode.NOT_FOUND
+        httpd, port = servicer.serve_metrics()
+        text = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=10).read().decode()
+        httpd.shutdown()
+        for series in ("vdb_search_duration_milliseconds", "vdb_searches_total", "vdb_gpu_memory_bytes",
+                       "vdb_queries_per_second"):
+            assert f"# TYPE {series}" in text
+        vals = dict(line.rsplit(" ", 1) for line in text.splitlines() if line and not line.startswith("#"))
+        assert float(vals['vdb_searches_total{index="ix"}']) == 4
+        assert float(vals["vdb_gpu_memory_bytes"]) > 0 and float(vals["vdb_queries_per_second"]) > 0
+        assert float(vals['vdb_search_duration_milliseconds{index="ix",quantile="0.99"}']) > 0
+    finally:
+        c.close()
+        server.stop(0)
+        servicer.coalescer.close()

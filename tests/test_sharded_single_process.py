@@ -131,3 +131,27 @@ def test_sharded_c4_shaped_inner_product():
     ora.add(db)
     Dr, Ir = ora.search(q, nprobe, k, 8)
     check_search(D, I, Dr, Ir, ip_scale(q, db))
+
+
+def test_sharded_add_of_device_rows_staged_in_chunks():
+    """rows that live on device 0 reach the other shards chunk by chunk over NVLink (more than one 256 MB chunk):
+    every row must land on exactly one shard, in the list the unsharded index puts it in"""
+    import torch
+    dim, nlist, n = 128, 64, 600_000
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    x = torch.randn(n, dim, generator=gen, device="cuda:0")
+    cent = x[:nlist].cpu().numpy()
+    one = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist))
+    one.centroids = cent
+    one.add(x)
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist, devices=device_lists()[-1]))
+    ix.centroids = cent
+    ix.add(x)
+    assert ix.get_total_vectors() == n
+    assert np.array_equal(ix.list_sizes(), one.list_sizes()) and int(ix.list_sizes().sum()) == n
+    l = int(np.argmin(one.list_sizes()))
+    assert sorted(ix.list_ids(l).tolist()) == sorted(one.list_ids(l).tolist())
+    q = x[:9].cpu().numpy()
+    Ds, Is = ix.search(q, nlist, 3)
+    Do, Io = one.search(q, nlist, 3)
+    assert np.array_equal(Ds, Do) and np.array_equal(Is, Io) and Is[:, 0].tolist() == list(range(9))

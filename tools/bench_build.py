@@ -1,6 +1,10 @@
 """BASELINE.json configs[4]: k-means IVF training + batched add() of 10M x 768D at nlist 16384 on N GPUs.
 
     python tools/bench_build.py                                    # 1 GPU
+    python tools/bench_build.py --devices 0,1,2,3,4,5,6,7           # ONE process, one shard per device
+                                                                   # (vdb_index_create_sharded): data-parallel,
+                                                                   # bit-exact training; every shard assigns
+                                                                   # the batch and keeps the lists it owns
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tools/bench_build.py [--mode distributed|replicated]
 
@@ -22,15 +26,58 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
+def single_process(a):
+    """vdb_index_create_sharded over --devices: train() is data-parallel over the devices (rows sliced for the
+    distance updates and the assignment, clusters partitioned for the sums) and bit-identical to one GPU --
+    `centroid_sha256` is the same at every device count; add() runs on all shards concurrently."""
+    import hashlib
+    import numpy as np
+    pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
+    devs = tuple(int(d) for d in a.devices.split(","))
+    torch.cuda.set_device(devs[0])
+    dev = torch.device("cuda", devs[0])
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, devices=devs if len(devs) > 1 else (),
+                                     device=devs[0]))
+    gen = torch.Generator(device=dev).manual_seed(12345)
+    xt = torch.randn(a.ntrain, a.dim, generator=gen, device=dev)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    ix.train(xt)
+    t_train = time.perf_counter() - t
+    del xt
+    sha = hashlib.sha256(np.ascontiguousarray(ix.centroids).tobytes()).hexdigest()
+    gen = torch.Generator(device=dev).manual_seed(777)
+    t_add = 0.0
+    for lo in range(0, a.rows, a.batch_rows):
+        nb = min(a.batch_rows, a.rows - lo)
+        x = torch.randn(nb, a.dim, generator=gen, device=dev)
+        ids = torch.arange(lo, lo + nb, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        ix.add(x, ids)
+        t_add += time.perf_counter() - t
+        del x, ids
+    st = ix.stats()
+    sizes = ix.list_sizes()
+    print(json.dumps({"config": f"configs[4] train({a.ntrain}) + add({a.rows}) {a.dim}D nlist={a.nlist}",
+                      "n_gpus": len(devs), "mode": "single process, one shard per device" if len(devs) > 1 else "single",
+                      "train_s": round(t_train, 3), "add_s": round(t_add, 3), "add_rows_per_s": a.rows / max(t_add, 1e-9),
+                      "rows_held_all_shards": int(sizes.sum()), "centroid_sha256": sha,
+                      "index_gb_all_shards": round(st.gpu_memory_bytes / 2**30, 2)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--nlist", type=int, default=16384)
-    ap.add_argument("--ntrain", type=int, default=262144)
+    ap.add_argument("--ntrain", type=int, default=1_000_000, help="SURVEY 8d: train on the first 1M rows")
+    ap.add_argument("--devices", default="", help="comma-separated device list: single-process sharded index")
     ap.add_argument("--batch-rows", type=int, default=1_000_000)
     ap.add_argument("--mode", default="distributed", choices=["distributed", "replicated"])
     a = ap.parse_args()
+    if a.devices:
+        return single_process(a)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
