@@ -435,6 +435,7 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
     ScanPlan plan;
     VDB_TRY(scan_plan(list_table(ix), q, nq, s.probes.p, np, k, ix->cfg.metric, ppi, slot_bound(ix, nq, np, ppi), true,
                       max_ctas, s.ws_scan, &plan));
+    plan.has_norms = !ix->scan_exact;
     VDB_TRY(scan_enqueue_groups(plan, s.ws_scan, st.front));
     if (prof) cudaEventRecord(s.tm[2], st.front);
     if (st.split) {
@@ -654,7 +655,8 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     VDB_REQUIRE(pr % 16 == 0 && pr <= 65536, "page_rows must be a multiple of 16, <= 65536");
     ix->page_rows = pr;
     ix->ids_off = (uint64_t)pr * ix->ld * 4;
-    ix->page_bytes = (ix->ids_off + (uint64_t)pr * 8 + 255) / 256 * 256;
+    // page = [pr][ld] fp32 rows | [pr] u64 ids | [pr] fp32 |row|^2 (the dot-form screen of the L2 scan)
+    ix->page_bytes = (ix->ids_off + (uint64_t)pr * 12 + 255) / 256 * 256;
     ix->pages_per_slab = (uint32_t)std::max<uint64_t>(1, SLAB_BYTES / ix->page_bytes);
     ix->h_rows.assign(ix->nlist, 0);
     ix->h_pages.resize(ix->nlist);
@@ -678,6 +680,7 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
         if (v == 1 || v == 2 || v == 4 || v == 8) ix->ppi_override = (uint32_t)v;
     }
     if (const char* e = std::getenv("VDB_PIPELINE_DEPTH")) ix->depth = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("VDB_SCAN_EXACT")) ix->scan_exact = std::atoi(e) != 0;  // A/B: no dot-form screen
     if (const char* e = std::getenv("VDB_RESERVE_SMS")) ix->reserve_sms = (uint32_t)std::atoi(e);
     VDB_REQUIRE(ix->depth >= 1 && ix->depth <= MAX_SEARCH_SLOTS, "pipeline_depth must be in [1, 8]");
     VDB_REQUIRE(ix->reserve_sms <= 64, "reserve_sms must be <= 64");
@@ -1178,6 +1181,9 @@ int32_t vdb_index_append_list(vdb_index* ix, uint32_t list, const float* vectors
                                        (size_t)ix->dim * 4, (size_t)ix->dim * 4, take, cudaMemcpyDefault, ix->stream));
         VDB_CUDA_TRY(cudaMemcpyAsync(page + ix->ids_off + (size_t)r * 8, ids + done, take * 8, cudaMemcpyDefault,
                                      ix->stream));
+        VDB_TRY(launch_page_norms(reinterpret_cast<const float*>(page), ix->ld,
+                                  reinterpret_cast<float*>(page + ix->ids_off + (size_t)ix->page_rows * 8), r,
+                                  (uint32_t)take, ix->stream));
         done += take;
     }
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));

@@ -946,8 +946,41 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
     const uint32_t pg = page_off[l] + pos / page_rows, r = pos % page_rows;
     float4* dst = reinterpret_cast<float4*>(page_vec[pg]) + (size_t)r * (ld >> 2);
     const float4* src = reinterpret_cast<const float4*>(x + v * ldx);
-    for (uint32_t c = lane; c < (ld >> 2); c += 32) dst[c] = src[c];
-    if (lane == 0) reinterpret_cast<uint64_t*>(page_ids[pg])[r] = ids ? ids[v] : id_base + v;
+    float nrm = 0.f;  // |row|^2 for the scan's dot-form screen (any fixed order: its rounding is inside the slack)
+    for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+        const float4 t = src[c];
+        dst[c] = t;
+        nrm = fmaf(t.x, t.x, nrm);
+        nrm = fmaf(t.y, t.y, nrm);
+        nrm = fmaf(t.z, t.z, nrm);
+        nrm = fmaf(t.w, t.w, nrm);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) {
+        uint64_t* idp = reinterpret_cast<uint64_t*>(page_ids[pg]);
+        idp[r] = ids ? ids[v] : id_base + v;
+        reinterpret_cast<float*>(idp + page_rows)[r] = nrm;  // the norms follow the page's id block
+    }
+}
+
+// |row|^2 of rows [r0, r0 + count) of one page (rows copied in without the scatter kernel: vdb_index_append_list)
+__global__ void __launch_bounds__(256) page_norms_kernel(const float* __restrict__ rows, uint32_t ld,
+                                                         float* __restrict__ norms, uint32_t r0, uint32_t count) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= count) return;
+    const float4* src = reinterpret_cast<const float4*>(rows + (size_t)(r0 + w) * ld);
+    float nrm = 0.f;
+    for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+        const float4 t = src[c];
+        nrm = fmaf(t.x, t.x, nrm);
+        nrm = fmaf(t.y, t.y, nrm);
+        nrm = fmaf(t.z, t.z, nrm);
+        nrm = fmaf(t.w, t.w, nrm);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) norms[r0 + w] = nrm;
 }
 
 // [n][dim] (any stride) -> [n][ld] zero-padded
@@ -1222,6 +1255,14 @@ int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, u
     scatter_rows_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, ldx, ids, id_base, n, assign, old_rows, fill,
                                                               page_off, page_vec, page_ids, page_rows, ld, nlist,
                                                               shard_rank, owner);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+int32_t launch_page_norms(const float* rows, uint32_t ld, float* norms, uint32_t r0, uint32_t count,
+                          cudaStream_t stream) {
+    if (count == 0) return VDB_OK;
+    page_norms_kernel<<<(count * 32 + 255) / 256, 256, 0, stream>>>(rows, ld, norms, r0, count);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
 }

@@ -363,6 +363,7 @@ struct ScanParams {
     uint32_t* glock;     // [nq] spin locks guarding gtop
     uint32_t* work_counter;
     uint32_t k, P, S, np, check_interval, has_ids;
+    uint32_t dotform;  // L2 over pages that carry row norms: dot-product screen, exact (q-v)^2 for the survivors
     uint32_t stage_rows;  // rows per ring stage: 16, or 8 for rows wider than 4 KB
     uint32_t qt;  // queries per tile at run time (<= the kernel's register tile)
     int metric;
@@ -371,6 +372,8 @@ struct ScanParams {
 struct ScanSmem {
     float* stages;        // [S][STAGE_ROWS][ld]
     uint64_t* stage_ids;  // [S][STAGE_ROWS] ids of the staged rows (lists that carry ids)
+    float* stage_norm;    // [S][STAGE_ROWS] |v|^2 of the staged rows (dotform)
+    float* qn;            // [MAX_QT] |q|^2 of the tile's queries (dotform)
     float* sq;            // [2][QT][ld] the tile's queries, double-buffered across items
     uint64_t* pool_i;     // [QT][P]
     float* pool_d;        // [QT][P]
@@ -395,6 +398,10 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
     q += (size_t)p.S * p.stage_rows * p.lt.ld * 4;
     s.stage_ids = (uint64_t*)q;
     q += (size_t)p.S * STAGE_ROWS * 8;
+    s.stage_norm = (float*)q;
+    q += (size_t)p.S * STAGE_ROWS * 4;
+    s.qn = (float*)q;
+    q += MAX_QT * 4;
     s.sq = (float*)q;
     q += (size_t)2 * QT * p.lt.ld * 4;
     s.pool_i = (uint64_t*)q;
@@ -426,7 +433,7 @@ __device__ __forceinline__ ScanSmem carve(uint8_t* base, const ScanParams& p) {
 }
 
 static uint32_t scan_smem_bytes(uint32_t ld, uint32_t S, uint32_t QT, uint32_t P, uint32_t stage_rows) {
-    return S * stage_rows * ld * 4 + S * STAGE_ROWS * 8 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64 + 4 * MAX_QT * 4;
+    return S * stage_rows * ld * 4 + S * STAGE_ROWS * 12 + MAX_QT * 4 + 2 * QT * ld * 4 + QT * P * 12 + 4 * MAX_QT * 4 + 20 * 8 + 64 + 4 * MAX_QT * 4;
 }
 
 // queries held in registers per tile, by the number of float4 columns a lane owns
@@ -585,10 +592,41 @@ __device__ __forceinline__ float transposed_reduce(float (&x)[V], uint32_t lane)
     return r;
 }
 
+// Relative slack of the dot-form screen.  With u = 2^-24 and chains of at most 2*NJ+6 <= 38 roundings (dot, exact
+// distance) or 4*NJ+5 <= 69 (norms): |screen - exact| <= (69 + 38 + 4 + 80) u (|q|^2 + |v|^2) < 196 u (|q|^2+|v|^2),
+// so lowering the screen by 2e-5 (= 335 u) of |q|^2 + |v|^2 can never reject a pair whose exact distance passes.
+constexpr float DOT_SLACK = 2e-5f;
+
+// this lane's share of the exact (q - v)^2 of one staged row: the arithmetic of the L2 branch of score_batch
+template <int NJ, bool FULLW>
+__device__ __forceinline__ float exact_l2_lane(const float4* __restrict__ st4, uint32_t ld4, uint32_t r, uint32_t nr,
+                                               uint32_t lane, const float4 (&q)[NJ]) {
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+        const uint32_t c4 = lane + 32 * jj;
+        float4 v;
+        if (FULLW) v = st4[min(r, nr - 1) * ld4 + c4];
+        else v = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2 dlo = __ffma2_rn(make_float2(v.x, v.y), neg1, make_float2(q[jj].x, q[jj].y));
+        const float2 dhi = __ffma2_rn(make_float2(v.z, v.w), neg1, make_float2(q[jj].z, q[jj].w));
+        acc = jj == 0 ? __fmul2_rn(dlo, dlo) : __ffma2_rn(dlo, dlo, acc);
+        acc = __ffma2_rn(dhi, dhi, acc);
+    }
+    return acc.x + acc.y;
+}
+
 // Distances of RB staged rows (r_first, r_first + r_stride, ...) to the first QC queries of this warp's
 // group, then ONE transposed reduction for the RB x QC per-lane partials and the pushes of the survivors.
-// Packed fp32x2 FMAs (sm_100): a (row, query) pair costs 2 instructions per float2 of the row --
-// d = v * (-1) + q (exactly q - v), acc += d * d -- instead of 4.
+// Packed fp32x2 FMAs (sm_100): a (row, query) pair costs 2 instructions per float2 of the row for the exact L2
+// form -- d = v * (-1) + q (exactly q - v), acc += d * d -- and 1 for a dot product.
+// L2 over index pages (p.dotform) therefore SCREENS with the dot product: |q|^2 + |v|^2 - 2 q.v, lowered by a
+// proven bound on its rounding error (DOT_SLACK), is compared with the query's running k-th distance; only a pair
+// that passes -- after the first items of a query almost none does -- gets the exact (q - v)^2, computed by the whole
+// warp from the row still sitting in its stage, with the same arithmetic and summation tree as the unscreened
+// path: the distances that reach the pools are bit-identical, at half the FP instructions and less power.  While
+// some query of the tile has no bound yet (every pair would pass) the exact form runs directly.
 // FULLW: the row is exactly 32 * NJ float4 wide (768-D, 128-D, ...), so no column needs masking and rows past
 // the end of a short stage are simply read from the last valid row (their results are discarded)
 template <int NJ, int QT, int QC, int RB, bool FULLW>
@@ -599,81 +637,114 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
                                             bool release) {
     constexpr int QCP = QC <= 1 ? 1 : QC <= 2 ? 2 : QC <= 4 ? 4 : 8;  // reduction width: QC padded to a power of two
     constexpr int V = RB * QCP;
+    // lane's value after the reduction: index = top log2(V) lane bits = (row in batch, query in group)
+    constexpr int COPIES = 32 / V;
+    const uint32_t vidx = lane / COPIES;
+    const uint32_t b = vidx / QCP, jl = vidx % QCP;
+    const uint32_t r = r_first + r_stride * b;
+    const uint32_t j = g + ng * jl;  // the query's slot in the CTA tile
+    const bool mine = (lane % COPIES) == 0 && r < nr && jl < myq;
+    const float thr = jl < myq ? s.thr[j] : -INFINITY;
+    // dot-form screen only once every query of this warp's tile has a finite bound (warp-uniform)
+    const bool screen = p.dotform && !__any_sync(0xffffffffu, jl < myq && thr == INFINITY);
+    const bool exact_l2 = p.metric == VDB_METRIC_L2 && !screen;
     float part[V];
     uint64_t rid[RB];
     const float2 neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
-    for (int b = 0; b < RB; ++b) {
-        const uint32_t r = r_first + r_stride * b;
+    for (int bb = 0; bb < RB; ++bb) {
+        const uint32_t rr = r_first + r_stride * bb;
         float4 v[NJ];
         if (FULLW) {
-            const float4* row4 = st4 + min(r, nr - 1) * ld4 + lane;
+            const float4* row4 = st4 + min(rr, nr - 1) * ld4 + lane;
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) v[jj] = row4[32 * jj];
         } else {
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
                 const uint32_t c4 = lane + 32 * jj;
-                v[jj] = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[jj] = (rr < nr && c4 < ld4) ? st4[rr * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        const uint32_t lr = row0 + r;  // list-relative row
-        rid[b] = lr;
-        if (r < nr) {
-            if (p.has_ids) rid[b] = s.stage_ids[cur * STAGE_ROWS + r];
-            else if (p.lt.ids_flat) rid[b] = __ldg(&p.lt.ids_flat[lr]);
+        const uint32_t lr = row0 + rr;  // list-relative row
+        rid[bb] = lr;
+        if (rr < nr) {
+            if (p.has_ids) rid[bb] = s.stage_ids[cur * STAGE_ROWS + rr];
+            else if (p.lt.ids_flat) rid[bb] = __ldg(&p.lt.ids_flat[lr]);
         }
-        if (release && b == RB - 1) {
+        if (release && bb == RB - 1 && !screen) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.empty[cur]);  // slot free: this warp's last row now lives in registers
         }
         float2 acc2[QC];
-        if (p.metric == VDB_METRIC_L2) {
+        if (exact_l2) {
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
                 const float2 vlo = make_float2(v[jj].x, v[jj].y), vhi = make_float2(v[jj].z, v[jj].w);
 #pragma unroll
-                for (int j = 0; j < QC; ++j) {
-                    const float2 dlo = __ffma2_rn(vlo, neg1, make_float2(qv[j][jj].x, qv[j][jj].y));
-                    const float2 dhi = __ffma2_rn(vhi, neg1, make_float2(qv[j][jj].z, qv[j][jj].w));
-                    acc2[j] = jj == 0 ? __fmul2_rn(dlo, dlo) : __ffma2_rn(dlo, dlo, acc2[j]);
-                    acc2[j] = __ffma2_rn(dhi, dhi, acc2[j]);
+                for (int jq = 0; jq < QC; ++jq) {
+                    const float2 dlo = __ffma2_rn(vlo, neg1, make_float2(qv[jq][jj].x, qv[jq][jj].y));
+                    const float2 dhi = __ffma2_rn(vhi, neg1, make_float2(qv[jq][jj].z, qv[jq][jj].w));
+                    acc2[jq] = jj == 0 ? __fmul2_rn(dlo, dlo) : __ffma2_rn(dlo, dlo, acc2[jq]);
+                    acc2[jq] = __ffma2_rn(dhi, dhi, acc2[jq]);
                 }
             }
-        } else {
+        } else {  // q.v: the inner-product metric, and the screen of the dot-form L2
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
                 const float2 vlo = make_float2(v[jj].x, v[jj].y), vhi = make_float2(v[jj].z, v[jj].w);
 #pragma unroll
-                for (int j = 0; j < QC; ++j) {
-                    const float2 qlo = make_float2(qv[j][jj].x, qv[j][jj].y);
-                    acc2[j] = jj == 0 ? __fmul2_rn(qlo, vlo) : __ffma2_rn(qlo, vlo, acc2[j]);
-                    acc2[j] = __ffma2_rn(make_float2(qv[j][jj].z, qv[j][jj].w), vhi, acc2[j]);
+                for (int jq = 0; jq < QC; ++jq) {
+                    const float2 qlo = make_float2(qv[jq][jj].x, qv[jq][jj].y);
+                    acc2[jq] = jj == 0 ? __fmul2_rn(qlo, vlo) : __ffma2_rn(qlo, vlo, acc2[jq]);
+                    acc2[jq] = __ffma2_rn(make_float2(qv[jq][jj].z, qv[jq][jj].w), vhi, acc2[jq]);
                 }
             }
         }
 #pragma unroll
-        for (int t = 0; t < QCP; ++t) part[b * QCP + t] = t < QC ? acc2[t].x + acc2[t].y : 0.f;
+        for (int t = 0; t < QCP; ++t) part[bb * QCP + t] = t < QC ? acc2[t].x + acc2[t].y : 0.f;
     }
     float tot = transposed_reduce<V>(part, lane);
-    if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
-    // lane's value: index = top log2(V) lane bits = (row in batch, query in group); copies in the other lanes
-    constexpr int COPIES = 32 / V;
-    const uint32_t vidx = lane / COPIES;
-    const uint32_t b = vidx / QCP, jl = vidx % QCP;
-    const uint32_t r = r_first + r_stride * b;
-    const uint32_t j = g + ng * jl;  // the query's slot in the CTA tile
-    if ((lane % COPIES) == 0 && r < nr && jl < myq && tot <= s.thr[j]) {
-        uint64_t id = rid[0];
+    uint64_t id = rid[0];
 #pragma unroll
-        for (int t = 1; t < RB; ++t)
-            if (b == (uint32_t)t) id = rid[t];
+    for (int t = 1; t < RB; ++t)
+        if (b == (uint32_t)t) id = rid[t];
+    auto push = [&](float d) {
         const uint32_t pos = atomicAdd(&s.cnt[j], 1u);
         over |= (pos >= limit);
         if (pos < p.P) {
-            s.pool_d[(size_t)j * p.P + pos] = tot;
+            s.pool_d[(size_t)j * p.P + pos] = d;
             s.pool_i[(size_t)j * p.P + pos] = id;
         }
+    };
+    if (!screen) {
+        if (p.metric != VDB_METRIC_L2) tot = -tot;  // IP distance = -dot, kernels.cuh:59
+        if (mine && tot <= thr) push(tot);
+        return;
+    }
+    // screen: a lower bound of the exact distance from the dot product and the two norms
+    bool pass = false;
+    if (mine) {
+        const float sn = s.qn[j] + s.stage_norm[cur * STAGE_ROWS + r];
+        pass = fmaf(-2.f, tot, sn * (1.f - DOT_SLACK)) <= thr;
+    }
+    uint32_t m = __ballot_sync(0xffffffffu, pass);
+    while (m) {  // warp-uniform: one admitted (row, query) pair at a time, exact distance by all 32 lanes
+        const uint32_t L = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
+        const uint32_t lv = L / COPIES, vb = lv / QCP, vj = lv % QCP;
+        const uint32_t rr = r_first + r_stride * vb;
+        float e = 0.f;
+#pragma unroll
+        for (int t = 0; t < QC; ++t)
+            if (vj == (uint32_t)t) e = exact_l2_lane<NJ, FULLW>(st4, ld4, rr, nr, lane, qv[t]);
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) e += __shfl_xor_sync(0xffffffffu, e, step);  // same tree as above
+        if (lane == L && e <= thr) push(e);
+    }
+    if (release) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[cur]);  // the rows may have been re-read above: slot freed only now
     }
 }
 
@@ -739,6 +810,22 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                     qv[j][jj] = ((uint32_t)j < myq && c4 < ld4) ? q4[(g + ng * j) * ld4 + c4]
                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+        }
+        if (p.dotform) {  // |q|^2 of this group's queries (every warp of the group writes the same values)
+#pragma unroll
+            for (int j = 0; j < QT; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    a = fmaf(qv[j][jj].x, qv[j][jj].x, a);
+                    a = fmaf(qv[j][jj].y, qv[j][jj].y, a);
+                    a = fmaf(qv[j][jj].z, qv[j][jj].z, a);
+                    a = fmaf(qv[j][jj].w, qv[j][jj].w, a);
+                }
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) a += __shfl_xor_sync(0xffffffffu, a, step);
+                if (lane == 0 && (uint32_t)j < myq) s.qn[g + ng * j] = a;
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.qempty[qbuf]);
@@ -891,11 +978,16 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
                     const uint32_t bytes = nr * ld * 4;
                     // bulk copies move multiples of 16 bytes: an odd tail reads one id slot further, inside the page
                     const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
+                    // row norms sit behind the page's ids ([page_rows] u64, then [page_rows] f32)
+                    const uint32_t norm_bytes = (ids && p.dotform) ? ((nr + 3) & ~3u) * 4 : 0;
                     mbar_wait(&s.empty[stage], phase ^ 1);
-                    mbar_expect_tx(&s.full[stage], bytes + id_bytes);
+                    mbar_expect_tx(&s.full[stage], bytes + id_bytes + norm_bytes);
                     tma_bulk_g2s_hint(s.stages + (size_t)stage * p.stage_rows * ld, src + (size_t)r0 * ld, bytes,
                                       &s.full[stage], policy);
                     if (ids) tma_bulk_g2s(s.stage_ids + stage * STAGE_ROWS, ids + r0, id_bytes, &s.full[stage]);
+                    if (norm_bytes)
+                        tma_bulk_g2s(s.stage_norm + stage * STAGE_ROWS,
+                                     reinterpret_cast<const float*>(ids + p.lt.page_rows) + r0, norm_bytes, &s.full[stage]);
                     if (++stage == p.S) {
                         stage = 0;
                         phase ^= 1;
@@ -1289,6 +1381,7 @@ int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, co
     pl.probes = probes_dev;
     pl.nq = nq; pl.np = np; pl.k = k; pl.metric = metric; pl.ppi = ppi;
     pl.has_ids = has_ids;
+    pl.has_norms = false;  // set by the caller for index pages (ids followed by row norms)
     pl.info = ScanLaunchInfo{QT, P, S, NJ, (uint32_t)grid, scan_smem_bytes(lt.ld, S, QT, P, stage_rows),
                              std::max(1u, std::min(64u, (P - k) / STAGE_ROWS))};
     pl.stage_rows = stage_rows;
@@ -1342,6 +1435,7 @@ int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t st
     sp.glock = ws.glock;
     sp.k = pl.k; sp.P = pl.info.P; sp.S = pl.info.S; sp.np = pl.np;
     sp.has_ids = pl.has_ids ? 1u : 0u;
+    sp.dotform = (pl.has_norms && pl.has_ids && pl.metric == VDB_METRIC_L2) ? 1u : 0u;
     sp.qt = pl.info.QT;
     sp.stage_rows = pl.stage_rows;
     sp.work_counter = ws.totals + 2;

@@ -179,7 +179,7 @@ def test_epochs_are_persisted_activated_and_measured(tmp_path, devices):
                        "vdb_queries_per_second"):
             assert f"# TYPE {series}" in text
         vals = dict(line.rsplit(" ", 1) for line in text.splitlines() if line and not line.startswith("#"))
-        assert float(vals['vdb_searches_total{index="ix"}']) == 4
+        assert float(vals['vdb_searches_total{index="ix"}']) == 5
         assert float(vals["vdb_gpu_memory_bytes"]) > 0 and float(vals["vdb_queries_per_second"]) > 0
         assert float(vals['vdb_search_duration_milliseconds{index="ix",quantile="0.99"}']) > 0
     finally:
