@@ -64,7 +64,18 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
     ap.add_argument("--dump-groups", action="store_true", help="stderr: probed-row work by queries-per-list")
-    return ap.parse_args()
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs[0..4]: c1 IVF 100Kx128 (reference's CPU-runnable case), c2 brute force "
+                         "1Mx768 k=100, c3 the headline (default), c4 100Mx768 IP nlist 16384 (8 GPUs), c5 k-means train "
+                         "+ add 10Mx768 nlist 16384 (single process, --devices)")
+    ap.add_argument("--devices", default="", help="c5: comma-separated devices of the single-process sharded index")
+    a = ap.parse_args()
+    presets = {"c1": dict(n=100_000, dim=128, nlist=128, nprobe=16, ntrain=10_000, metric="l2"),
+               "c4": dict(n=100_000_000, dim=768, nlist=16384, nprobe=64, ntrain=1_000_000, metric="ip")}
+    if a.config in presets:
+        for k_, v in presets[a.config].items():
+            setattr(a, k_, v)
+    return a
 
 
 def workload_name(a):

@@ -123,6 +123,7 @@ ABI = {
     "vdb_arena_get_stream": (_vp, [_vp]),
     "vdb_arena_return_stream": (_i32, [_vp, _vp]),
     "vdb_arena_enqueue_transfer": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "vdb_arena_enqueue_transfer_cb": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),
     "vdb_arena_synchronize": (_i32, [_vp]),
     "vdb_arena_synchronize_stream": (_i32, [_vp, _vp]),
     "vdb_arena_stats": (_i32, [_vp, _vp]),

@@ -208,6 +208,29 @@ int32_t vdb_arena_enqueue_transfer(vdb_arena* a, void* dst, const void* src, uin
     return VDB_OK;
 }
 
+// enqueue_transfer with Transfer::callback (transfer_manager.cpp:218-261 passes it to cudaLaunchHostFunc): the copy
+// and then the host function are enqueued on the stream; the caller is not blocked
+int32_t vdb_arena_enqueue_transfer_cb(vdb_arena* a, void* dst, const void* src, uint64_t bytes, int32_t kind,
+                                      void* stream, void (*callback)(void*), void* user) {
+    VDB_REQUIRE(a && dst && src, "arena: null transfer endpoint");
+    VDB_REQUIRE(kind >= 1 && kind <= 4, "arena: kind must be a cudaMemcpyKind in [1,4]");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(a->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    bool borrowed = false;
+    if (!s) {
+        s = (cudaStream_t)vdb_arena_get_stream(a);
+        borrowed = true;
+    }
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, (cudaMemcpyKind)kind, s);
+    if (e == cudaSuccess && callback) e = cudaLaunchHostFunc(s, callback, user);
+    if (borrowed) vdb_arena_return_stream(a, s);
+    cudaSetDevice(prev);
+    VDB_CUDA_TRY(e);
+    return VDB_OK;
+}
+
 int32_t vdb_arena_synchronize(vdb_arena* a) {
     VDB_REQUIRE(a, "arena: null handle");
     for (auto s : a->streams) VDB_CUDA_TRY(cudaStreamSynchronize(s));

@@ -116,7 +116,7 @@ public:
         size_t size;
         cudaMemcpyKind kind;
         cudaStream_t stream;
-        std::function<void()> callback;  // invoked after the copy has been enqueued AND completed
+        std::function<void()> callback;  // runs on a driver thread once the copy has completed (cudaLaunchHostFunc)
     };
     explicit TransferManager(const Config& config) : config_(config) {
         detail::check(vdb_arena_create(config.device, config.device_pool_size, config.pinned_pool_size,
@@ -133,12 +133,23 @@ public:
     cudaStream_t get_stream() { return static_cast<cudaStream_t>(vdb_arena_get_stream(arena_)); }
     void return_stream(cudaStream_t s) { vdb_arena_return_stream(arena_, s); }
     void enqueue_transfer(const Transfer& t) {
-        detail::check(vdb_arena_enqueue_transfer(arena_, t.dst, t.src, t.size, static_cast<int32_t>(t.kind), t.stream),
-                      "enqueue_transfer");
-        if (t.callback) {
-            if (t.stream) synchronize_stream(t.stream); else synchronize();
-            t.callback();
+        if (!t.callback) {
+            detail::check(vdb_arena_enqueue_transfer(arena_, t.dst, t.src, t.size, static_cast<int32_t>(t.kind), t.stream),
+                          "enqueue_transfer");
+            return;
         }
+        // the callback travels with the copy and runs behind it on the stream, as transfer_manager.cpp:250-257 does
+        auto* fn = new std::function<void()>(t.callback);
+        const int32_t st = vdb_arena_enqueue_transfer_cb(
+            arena_, t.dst, t.src, t.size, static_cast<int32_t>(t.kind), t.stream,
+            [](void* u) {
+                auto* f = static_cast<std::function<void()>*>(u);
+                (*f)();
+                delete f;
+            },
+            fn);
+        if (st != VDB_OK) delete fn;
+        detail::check(st, "enqueue_transfer");
     }
     void enqueue_batch(const std::vector<Transfer>& ts) { for (const auto& t : ts) enqueue_transfer(t); }
     void synchronize() { detail::check(vdb_arena_synchronize(arena_), "synchronize"); }

@@ -277,6 +277,9 @@ int32_t vdb_arena_return_stream(vdb_arena* a, void* stream);    /* return_stream
 /* enqueue_transfer: kind 1 = H2D, 2 = D2H, 3 = D2D (cudaMemcpyKind values) */
 int32_t vdb_arena_enqueue_transfer(vdb_arena* a, void* dst, const void* src, uint64_t bytes, int32_t kind,
                                    void* stream);
+/* the same with Transfer::callback: a host function enqueued behind the copy (cudaLaunchHostFunc), caller not blocked */
+int32_t vdb_arena_enqueue_transfer_cb(vdb_arena* a, void* dst, const void* src, uint64_t bytes, int32_t kind,
+                                      void* stream, void (*callback)(void*), void* user);
 int32_t vdb_arena_synchronize(vdb_arena* a);                     /* synchronize */
 int32_t vdb_arena_synchronize_stream(vdb_arena* a, void* stream); /* synchronize_stream */
 /* out[0..3] = device bytes in use, device peak, pinned in use, live allocations */
