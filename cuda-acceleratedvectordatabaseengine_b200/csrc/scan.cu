@@ -363,6 +363,7 @@ struct ScanParams {
     uint32_t* glock;     // [nq] spin locks guarding gtop
     uint32_t* work_counter;
     uint32_t k, P, S, np, check_interval, has_ids;
+    uint32_t dot_min_items;  // the screen is used when the launch has at least this many items per CTA
     uint32_t dotform;  // L2 over pages that carry row norms: dot-product screen, exact (q-v)^2 for the survivors
     uint32_t stage_rows;  // rows per ring stage: 16, or 8 for rows wider than 4 KB
     uint32_t qt;  // queries per tile at run time (<= the kernel's register tile)
@@ -385,7 +386,7 @@ struct ScanSmem {
     uint64_t* empty;   // [S]
     uint64_t* qfull;   // [2]
     uint64_t* qempty;  // [2]
-    uint32_t* tile;    // [2][8] {item | END, first pair, queries, range, pages, row_base, rows_left, -}: producer -> consumers
+    uint32_t* tile;    // [2][8] {item | END, first pair, queries, range, pages, row_base, rows_left, first page}: producer -> consumers
     uint32_t* tq;      // [2][MAX_QT] query index of each tile slot            (written by the producer with the tile)
     uint32_t* tslot;   // [2][MAX_QT] partial-result slot of each (pair, range)
 };
@@ -598,8 +599,10 @@ __device__ __forceinline__ float transposed_reduce(float (&x)[V], uint32_t lane)
 constexpr float DOT_SLACK = 2e-5f;
 
 // this lane's share of the exact (q - v)^2 of one staged row: the arithmetic of the L2 branch of score_batch
+// (rows come from the page in global memory -- just streamed, so normally still in L2 -- because the stage slot
+// has been handed back to the producer by the time a pair is known to pass)
 template <int NJ, bool FULLW>
-__device__ __forceinline__ float exact_l2_lane(const float4* __restrict__ st4, uint32_t ld4, uint32_t r, uint32_t nr,
+__device__ __forceinline__ float exact_l2_lane(const float4* __restrict__ g4, uint32_t ld4, uint32_t r, uint32_t nr,
                                                uint32_t lane, const float4 (&q)[NJ]) {
     const float2 neg1 = make_float2(-1.f, -1.f);
     float2 acc = make_float2(0.f, 0.f);
@@ -607,8 +610,8 @@ __device__ __forceinline__ float exact_l2_lane(const float4* __restrict__ st4, u
     for (int jj = 0; jj < NJ; ++jj) {
         const uint32_t c4 = lane + 32 * jj;
         float4 v;
-        if (FULLW) v = st4[min(r, nr - 1) * ld4 + c4];
-        else v = (r < nr && c4 < ld4) ? st4[r * ld4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FULLW) v = __ldg(&g4[min(r, nr - 1) * ld4 + c4]);
+        else v = (r < nr && c4 < ld4) ? __ldg(&g4[r * ld4 + c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float2 dlo = __ffma2_rn(make_float2(v.x, v.y), neg1, make_float2(q[jj].x, q[jj].y));
         const float2 dhi = __ffma2_rn(make_float2(v.z, v.w), neg1, make_float2(q[jj].z, q[jj].w));
         acc = jj == 0 ? __fmul2_rn(dlo, dlo) : __ffma2_rn(dlo, dlo, acc);
@@ -624,7 +627,7 @@ __device__ __forceinline__ float exact_l2_lane(const float4* __restrict__ st4, u
 // L2 over index pages (p.dotform) therefore SCREENS with the dot product: |q|^2 + |v|^2 - 2 q.v, lowered by a
 // proven bound on its rounding error (DOT_SLACK), is compared with the query's running k-th distance; only a pair
 // that passes -- after the first items of a query almost none does -- gets the exact (q - v)^2, computed by the whole
-// warp from the row still sitting in its stage, with the same arithmetic and summation tree as the unscreened
+// warp from the row's copy in the page (L2), with the same arithmetic and summation tree as the unscreened
 // path: the distances that reach the pools are bit-identical, at half the FP instructions and less power.  While
 // some query of the tile has no bound yet (every pair would pass) the exact form runs directly.
 // FULLW: the row is exactly 32 * NJ float4 wide (768-D, 128-D, ...), so no column needs masking and rows past
@@ -634,7 +637,7 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
                                             uint32_t ld4, uint32_t cur, uint32_t r_first, uint32_t r_stride,
                                             uint32_t nr, uint32_t row0, const float4 (&qv)[QT][NJ], uint32_t myq,
                                             uint32_t g, uint32_t ng, uint32_t lane, uint32_t limit, bool& over,
-                                            bool release) {
+                                            bool release, uint32_t pg, uint32_t prow, bool screen) {
     constexpr int QCP = QC <= 1 ? 1 : QC <= 2 ? 2 : QC <= 4 ? 4 : 8;  // reduction width: QC padded to a power of two
     constexpr int V = RB * QCP;
     // lane's value after the reduction: index = top log2(V) lane bits = (row in batch, query in group)
@@ -644,10 +647,11 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
     const uint32_t r = r_first + r_stride * b;
     const uint32_t j = g + ng * jl;  // the query's slot in the CTA tile
     const bool mine = (lane % COPIES) == 0 && r < nr && jl < myq;
-    const float thr = jl < myq ? s.thr[j] : -INFINITY;
-    // dot-form screen only once every query of this warp's tile has a finite bound (warp-uniform)
-    const bool screen = p.dotform && !__any_sync(0xffffffffu, jl < myq && thr == INFINITY);
+    // `screen` (warp-uniform, decided by the caller once per check interval): every query of the tile has a finite
+    // bound, so the dot-form screen rejects nearly everything; before that the exact form runs directly
     const bool exact_l2 = p.metric == VDB_METRIC_L2 && !screen;
+    // this lane's row norm, read BEFORE the stage slot is handed back (the producer refills ids and norms with it)
+    const float vn = (screen && r < nr) ? s.stage_norm[cur * STAGE_ROWS + r] : 0.f;
     float part[V];
     uint64_t rid[RB];
     const float2 neg1 = make_float2(-1.f, -1.f);
@@ -672,7 +676,7 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
             if (p.has_ids) rid[bb] = s.stage_ids[cur * STAGE_ROWS + rr];
             else if (p.lt.ids_flat) rid[bb] = __ldg(&p.lt.ids_flat[lr]);
         }
-        if (release && bb == RB - 1 && !screen) {
+        if (release && bb == RB - 1) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.empty[cur]);  // slot free: this warp's last row now lives in registers
         }
@@ -705,6 +709,7 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
         for (int t = 0; t < QCP; ++t) part[bb * QCP + t] = t < QC ? acc2[t].x + acc2[t].y : 0.f;
     }
     float tot = transposed_reduce<V>(part, lane);
+    const float thr = mine ? s.thr[j] : -INFINITY;
     uint64_t id = rid[0];
 #pragma unroll
     for (int t = 1; t < RB; ++t)
@@ -725,10 +730,13 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
     // screen: a lower bound of the exact distance from the dot product and the two norms
     bool pass = false;
     if (mine) {
-        const float sn = s.qn[j] + s.stage_norm[cur * STAGE_ROWS + r];
+        const float sn = s.qn[j] + vn;
         pass = fmaf(-2.f, tot, sn * (1.f - DOT_SLACK)) <= thr;
     }
     uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0) return;
+    // rows of this stage in the page: stage row r = page row prow + r
+    const float4* g4 = reinterpret_cast<const float4*>(__ldg(&p.lt.page_vec[pg])) + (size_t)prow * ld4;
     while (m) {  // warp-uniform: one admitted (row, query) pair at a time, exact distance by all 32 lanes
         const uint32_t L = (uint32_t)__ffs((int)m) - 1u;
         m &= m - 1u;
@@ -737,14 +745,10 @@ __device__ __forceinline__ void score_batch(const ScanParams& p, const ScanSmem&
         float e = 0.f;
 #pragma unroll
         for (int t = 0; t < QC; ++t)
-            if (vj == (uint32_t)t) e = exact_l2_lane<NJ, FULLW>(st4, ld4, rr, nr, lane, qv[t]);
+            if (vj == (uint32_t)t) e = exact_l2_lane<NJ, FULLW>(g4, ld4, rr, nr, lane, qv[t]);
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1) e += __shfl_xor_sync(0xffffffffu, e, step);  // same tree as above
         if (lane == L && e <= thr) push(e);
-    }
-    if (release) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[cur]);  // the rows may have been re-read above: slot freed only now
     }
 }
 
@@ -753,21 +757,22 @@ template <int NJ, int QT, int RB, bool FULLW>
 __device__ __forceinline__ void score_dispatch(const ScanParams& p, const ScanSmem& s, const float4* st4, uint32_t ld4,
                                                uint32_t cur, uint32_t r_first, uint32_t r_stride, uint32_t nr,
                                                uint32_t row0, const float4 (&qv)[QT][NJ], uint32_t myq, uint32_t g,
-                                               uint32_t ng, uint32_t lane, uint32_t limit, bool& over, bool release) {
+                                               uint32_t ng, uint32_t lane, uint32_t limit, bool& over, bool release,
+                                               uint32_t pg, uint32_t prow, bool screen) {
     if (QT >= 8 && myq > 4)
-        score_batch<NJ, QT, (QT >= 8 ? 8 : QT), (RB > 4 ? 4 : RB), FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 8 ? 8 : QT), (RB > 4 ? 4 : RB), FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release, pg, prow, screen);
     else if (QT >= 4 && myq > 3)
-        score_batch<NJ, QT, (QT >= 4 ? 4 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 4 ? 4 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release, pg, prow, screen);
     else if (QT >= 4 && myq > 2)  // 3 queries: a quarter less math than the padded 4-wide tile
-        score_batch<NJ, QT, (QT >= 4 ? 3 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 4 ? 3 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release, pg, prow, screen);
     else if (QT >= 2 && myq > 1)
-        score_batch<NJ, QT, (QT >= 2 ? 2 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, (QT >= 2 ? 2 : QT), RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release, pg, prow, screen);
     else
-        score_batch<NJ, QT, 1, RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release);
+        score_batch<NJ, QT, 1, RB, FULLW>(p, s, st4, ld4, cur, r_first, r_stride, nr, row0, qv, myq, g, ng, lane, limit, over, release, pg, prow, screen);
 }
 
 template <int NJ>
-__device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSmem& s) {
+__device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSmem& s, const bool dotform) {
     constexpr int QT = tile_queries(NJ);
     const uint32_t ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
     const uint32_t ld = p.lt.ld, ld4 = ld >> 2;
@@ -783,6 +788,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
         if (tw[0] == END) break;
         const uint32_t qcount = tw[2];
         struct { uint32_t range, npg, row_base, rows_left; } it = {tw[3], tw[4], tw[5], tw[6]};
+        const uint32_t pg0 = tw[7];  // the item's first page in the page tables (exact re-scoring reads rows from there)
         // per-query tile state; the bound is the only global read of the set-up and is issued first so that it
         // overlaps the query loads below
         uint32_t my_q = 0, my_slot = 0;
@@ -811,7 +817,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         }
-        if (p.dotform) {  // |q|^2 of this group's queries (every warp of the group writes the same values)
+        if (dotform) {  // |q|^2 of this group's queries (every warp of the group writes the same values)
 #pragma unroll
             for (int j = 0; j < QT; ++j) {
                 float a = 0.f;
@@ -843,6 +849,9 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
 
         uint32_t since_check = 0;
         bool over = false;  // this thread pushed a candidate at or beyond the compaction mark
+        // dot-form screen only once every query of the tile has a finite bound (re-evaluated at each check; a stale
+        // "not yet" merely keeps the exact form a little longer)
+        bool warm = dotform && !__any_sync(0xffffffffu, lane < qcount && s.thr[lane] == INFINITY);
         for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
             const uint32_t row_base = it.row_base + pgi * p.lt.page_rows;  // list-relative row of the page start
             const uint32_t rows_in_page = min(p.lt.page_rows, it.rows_left - pgi * p.lt.page_rows);
@@ -861,21 +870,23 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                 if (fullw) {
                     if (ng == 1) {
                         score_dispatch<NJ, QT, 2, true>(p, s, st4, ld4, cur, wg, nwg, nr, row_base + r0, qv, myq, g, ng,
-                                                        lane, limit, over, true);
+                                                        lane, limit, over, true, pg0 + pgi, r0, warm);
                     } else {
 #pragma unroll 1
                         for (uint32_t i0 = 0; i0 < rows_per_warp; i0 += 4)
                             score_dispatch<NJ, QT, 4, true>(p, s, st4, ld4, cur, wg + nwg * i0, nwg, nr, row_base + r0,
-                                                            qv, myq, g, ng, lane, limit, over, i0 + 4 >= rows_per_warp);
+                                                            qv, myq, g, ng, lane, limit, over, i0 + 4 >= rows_per_warp,
+                                                            pg0 + pgi, r0, warm);
                     }
                 } else if (ng == 1) {
                     score_dispatch<NJ, QT, 2, false>(p, s, st4, ld4, cur, wg, nwg, nr, row_base + r0, qv, myq, g, ng, lane,
-                                                     limit, over, true);
+                                                     limit, over, true, pg0 + pgi, r0, warm);
                 } else {
 #pragma unroll 1
                     for (uint32_t i0 = 0; i0 < rows_per_warp; i0 += 4)
                         score_dispatch<NJ, QT, 4, false>(p, s, st4, ld4, cur, wg + nwg * i0, nwg, nr, row_base + r0, qv,
-                                                         myq, g, ng, lane, limit, over, i0 + 4 >= rows_per_warp);
+                                                         myq, g, ng, lane, limit, over, i0 + 4 >= rows_per_warp,
+                                                         pg0 + pgi, r0, warm);
                 }
 
                 if (++since_check == p.check_interval) {
@@ -890,6 +901,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
                     }
                     // pick up bounds other CTAs published meanwhile (monotone, so a racy read is still a valid bound)
                     if (ctid < qcount) s.thr[ctid] = fminf(s.thr[ctid], key2f(__ldcg(&p.qthr[s.sqidx[ctid]])));
+                    if (dotform && !warm) warm = !__any_sync(0xffffffffu, lane < qcount && s.thr[lane] == INFINITY);
                 }
             }
         }
@@ -920,7 +932,7 @@ __device__ __forceinline__ void consumer_loop(const ScanParams& p, const ScanSme
     }
 }
 
-__device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSmem& s) {
+__device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSmem& s, const bool dotform) {
     const uint32_t total = *p.totals;
     const uint32_t ld = p.lt.ld;
     constexpr uint32_t END = 0xffffffffu;
@@ -950,6 +962,7 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
             tw[4] = it.npg;
             tw[5] = it.row_base;
             tw[6] = it.rows_left;
+            tw[7] = it.pg0;
             // per query of the tile: its index and the partial-result slot of (pair, range), so that the
             // consumers' tile set-up touches no global memory except the bound
 #pragma unroll 4
@@ -979,7 +992,7 @@ __device__ __forceinline__ void producer_loop(const ScanParams& p, const ScanSme
                     // bulk copies move multiples of 16 bytes: an odd tail reads one id slot further, inside the page
                     const uint32_t id_bytes = ids ? ((nr + 1) & ~1u) * 8 : 0;
                     // row norms sit behind the page's ids ([page_rows] u64, then [page_rows] f32)
-                    const uint32_t norm_bytes = (ids && p.dotform) ? ((nr + 3) & ~3u) * 4 : 0;
+                    const uint32_t norm_bytes = (ids && dotform) ? ((nr + 3) & ~3u) * 4 : 0;
                     mbar_wait(&s.empty[stage], phase ^ 1);
                     mbar_expect_tx(&s.full[stage], bytes + id_bytes + norm_bytes);
                     tma_bulk_g2s_hint(s.stages + (size_t)stage * p.stage_rows * ld, src + (size_t)r0 * ld, bytes,
@@ -1022,12 +1035,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     __syncthreads();
     // register reallocation between warpgroups: the producer's warpgroup (one busy thread) shrinks to 40
     // registers per thread, the two consumer warpgroups grow to 232 = (384 * 168 - 128 * 40) / 256
+    // The dot-form screen pays where the scan is long and runs into the power cap (whole index: +4.7 %, half: +2.3 %);
+    // on a short scan (1/8 shard, ~8 items per CTA, full clocks) its admitted pairs -- k ln(rows/k) per query whatever
+    // the shard size, each an L2 round trip for one warp -- cost more than the halved FP work saves (-2.4 %), so a
+    // launch with fewer than 12 items per CTA keeps the exact form.  Uniform over the grid: both loops read it here.
+    const bool dotform = p.dotform && *p.totals >= p.dot_min_items * gridDim.x;
     if (threadIdx.x < CONSUMER_THREADS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
-        consumer_loop<NJ>(p, s);
+        consumer_loop<NJ>(p, s, dotform);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
-        if (threadIdx.x == CONSUMER_THREADS) producer_loop(p, s);
+        if (threadIdx.x == CONSUMER_THREADS) producer_loop(p, s, dotform);
     }
 }
 
@@ -1381,6 +1399,7 @@ int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, co
     pl.probes = probes_dev;
     pl.nq = nq; pl.np = np; pl.k = k; pl.metric = metric; pl.ppi = ppi;
     pl.has_ids = has_ids;
+    pl.dot_min_items = 12;
     pl.has_norms = false;  // set by the caller for index pages (ids followed by row norms)
     pl.info = ScanLaunchInfo{QT, P, S, NJ, (uint32_t)grid, scan_smem_bytes(lt.ld, S, QT, P, stage_rows),
                              std::max(1u, std::min(64u, (P - k) / STAGE_ROWS))};
@@ -1435,6 +1454,7 @@ int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t st
     sp.glock = ws.glock;
     sp.k = pl.k; sp.P = pl.info.P; sp.S = pl.info.S; sp.np = pl.np;
     sp.has_ids = pl.has_ids ? 1u : 0u;
+    sp.dot_min_items = pl.dot_min_items;
     sp.dotform = (pl.has_norms && pl.has_ids && pl.metric == VDB_METRIC_L2) ? 1u : 0u;
     sp.qt = pl.info.QT;
     sp.stage_rows = pl.stage_rows;

@@ -60,6 +60,7 @@ struct ScanPlan {
     uint32_t nq, np, k, ppi, stage_rows;
     int metric;
     bool has_ids;
+    uint32_t dot_min_items;  // dot-form screen only for launches with >= this many items per CTA (default 12)
     bool has_norms;  // every page's id block is followed by [page_rows] f32 |v|^2 (index pages): L2 may screen by dot product
     ScanLaunchInfo info;
 };

@@ -29,6 +29,13 @@ struct Composite {
     uint64_t next_ticket = 0;
     uint64_t total_vectors = 0;
     uint32_t seen_nq = 0, seen_np = 0, seen_k = 0;  // largest search shape so far (scratch is reserved for it)
+    struct Stage {  // one shard's slice of the batch being added: rows, ids, list assignments (its own HBM)
+        DevBuf<float> x;
+        DevBuf<uint64_t> ids;
+        DevBuf<uint32_t> asg;
+        uint64_t n = 0;
+    };
+    std::vector<Stage> stage;
     bool peer_all = false;  // every pair of distinct shard devices has peer access (data-parallel training)
 };
 
@@ -95,6 +102,10 @@ int32_t composite_destroy(vdb_index* ix) {
             cudaDeviceSynchronize();
             s->exchange = nullptr;
         }
+    for (size_t r = 0; r < c->stage.size(); ++r) {
+        DeviceGuard g(c->shards[r]->device);
+        c->stage[r].x.release(); c->stage[r].ids.release(); c->stage[r].asg.release();
+    }
     for (vdb_exchange* e : c->exchanges) vdb_exchange_destroy(e);
     for (vdb_index* s : c->shards) vdb_index_destroy(s);
     delete c;
@@ -327,11 +338,65 @@ int32_t composite_set_owners(vdb_index* ix, const uint8_t* in) {
     return VDB_OK;
 }
 
-// add: every shard assigns the batch (tensor cores) and keeps the rows of the lists it owns; the shards work
-// concurrently, one host thread each.  Rows that live on another device are staged chunk by chunk over NVLink.
+__global__ void iota_u64_kernel(uint64_t* out, uint64_t base, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = base + i;
+}
+
+// add, data-parallel (the default when every pair of shard devices has peer access):
+//   1. the batch is cut into one slice per shard; shard r stages ITS slice (H2D from the caller's host memory, or a
+//      peer copy from the GPU that holds the rows) and assigns it on its tensor cores -- 1/R of the O(n nlist dim) work;
+//   2. every shard then appends the rows of the lists it OWNS, slice by slice, reading rows, ids and assignments
+//      straight out of the staging buffers of the shard that assigned them (NVLink peer loads inside the histogram
+//      and scatter kernels): each row crosses NVLink once, to the GPU whose list it joins.
+// Both phases run on all shards concurrently, one host thread per shard.
+static int32_t composite_add_distributed(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
+    Composite* c = ix->composite;
+    const uint32_t R = (uint32_t)c->shards.size(), dim = ix->cfg.dimension;
+    const int vdev = device_of(vectors), idev = ids ? device_of(ids) : -1;
+    const uint64_t per = (n + R - 1) / R;
+    const uint64_t id_base = c->total_vectors;
+    if (c->stage.size() != R) c->stage.resize(R);
+    VDB_TRY(for_each_shard_parallel(c, [&](uint32_t r) -> int32_t {
+        vdb_index* s = c->shards[r];
+        Composite::Stage& st = c->stage[r];
+        DeviceGuard g(s->device);
+        const uint64_t lo = std::min(n, r * per), m = std::min(n, (r + 1) * per) - lo;
+        st.n = m;
+        if (m == 0) return VDB_OK;
+        VDB_TRY(st.x.reserve(m * dim));
+        VDB_TRY(st.ids.reserve(m));
+        VDB_TRY(st.asg.reserve(m));
+        const float* src = vectors + lo * dim;
+        if (vdev < 0) VDB_CUDA_TRY(cudaMemcpyAsync(st.x.p, src, m * dim * 4, cudaMemcpyHostToDevice, s->stream));
+        else if (vdev == s->device) VDB_CUDA_TRY(cudaMemcpyAsync(st.x.p, src, m * dim * 4, cudaMemcpyDeviceToDevice, s->stream));
+        else VDB_CUDA_TRY(cudaMemcpyPeerAsync(st.x.p, s->device, src, vdev, m * dim * 4, s->stream));
+        if (!ids) iota_u64_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, s->stream>>>(st.ids.p, id_base + lo, m);
+        else if (idev < 0) VDB_CUDA_TRY(cudaMemcpyAsync(st.ids.p, ids + lo, m * 8, cudaMemcpyHostToDevice, s->stream));
+        else if (idev == s->device) VDB_CUDA_TRY(cudaMemcpyAsync(st.ids.p, ids + lo, m * 8, cudaMemcpyDeviceToDevice, s->stream));
+        else VDB_CUDA_TRY(cudaMemcpyPeerAsync(st.ids.p, s->device, ids + lo, idev, m * 8, s->stream));
+        VDB_CUDA_TRY(cudaStreamSynchronize(s->stream));  // vdb_index_assign works on the same stream; be explicit
+        return vdb_index_assign(s, st.x.p, m, st.asg.p);  // synchronises: the slice's assignments are complete
+    }));
+    VDB_TRY(for_each_shard_parallel(c, [&](uint32_t o) -> int32_t {
+        vdb_index* s = c->shards[o];
+        DeviceGuard g(s->device);
+        for (uint32_t i = 0; i < R; ++i) {
+            const Composite::Stage& st = c->stage[(o + i) % R];  // start with the own slice: spreads the peer reads
+            if (st.n) VDB_TRY(vdb_index_add_assigned(s, st.x.p, st.ids.p, st.asg.p, st.n, st.n));
+        }
+        return VDB_OK;
+    }));
+    c->total_vectors += n;
+    return VDB_OK;
+}
+
+// add, replicated (fallback): every shard assigns the whole batch and keeps the rows of the lists it owns; the shards
+// work concurrently, one host thread each.  Rows that live on another device are staged chunk by chunk over NVLink.
 int32_t composite_add(vdb_index* ix, const float* vectors, const uint64_t* ids, uint64_t n) {
     std::lock_guard<std::mutex> lock(ix->mu);
     Composite* c = ix->composite;
+    if (c->shards.size() > 1 && c->peer_all && n >= 4096) return composite_add_distributed(ix, vectors, ids, n);
     const uint32_t dim = ix->cfg.dimension;
     const int vdev = device_of(vectors), idev = ids ? device_of(ids) : -1;
     const uint64_t chunk = std::max<uint64_t>(1024, (256ull << 20) / (dim * 4ull));
