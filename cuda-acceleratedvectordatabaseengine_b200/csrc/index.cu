@@ -436,7 +436,8 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
     VDB_TRY(scan_plan(list_table(ix), q, nq, s.probes.p, np, k, ix->cfg.metric, ppi, slot_bound(ix, nq, np, ppi), true,
                       max_ctas, s.ws_scan, &plan));
     plan.has_norms = !ix->scan_exact;
-    plan.dot_min_items = ix->dot_min_items;
+    plan.dot_min_rows = ix->dot_min_rows;
+    if (!ix->ppi_override) plan.ppi_max = std::max(ppi, 16u);  // an explicit VDB_SCAN_PPI is taken literally
     VDB_TRY(scan_enqueue_groups(plan, s.ws_scan, st.front));
     if (prof) cudaEventRecord(s.tm[2], st.front);
     if (st.split) {
@@ -678,11 +679,11 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     // tuning knobs, read once: pages per scan item, pipeline depth, SMs left to the side kernels
     if (const char* e = std::getenv("VDB_SCAN_PPI")) {
         const int v = std::atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) ix->ppi_override = (uint32_t)v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32 || v == 64) ix->ppi_override = (uint32_t)v;
     }
     if (const char* e = std::getenv("VDB_PIPELINE_DEPTH")) ix->depth = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("VDB_SCAN_EXACT")) ix->scan_exact = std::atoi(e) != 0;  // A/B: no dot-form screen
-    if (const char* e = std::getenv("VDB_SCAN_DOT_MIN_ITEMS")) ix->dot_min_items = (uint32_t)std::atoi(e);  // tests: 0
+    if (const char* e = std::getenv("VDB_SCAN_DOT_MIN_ROWS")) ix->dot_min_rows = (uint32_t)std::atoi(e);  // tests: 0
     if (const char* e = std::getenv("VDB_RESERVE_SMS")) ix->reserve_sms = (uint32_t)std::atoi(e);
     VDB_REQUIRE(ix->depth >= 1 && ix->depth <= MAX_SEARCH_SLOTS, "pipeline_depth must be in [1, 8]");
     VDB_REQUIRE(ix->reserve_sms <= 64, "reserve_sms must be <= 64");

@@ -152,7 +152,7 @@ struct vdb_index {
     uint32_t depth = 4;          // slots in use
     uint32_t reserve_sms = 8;    // SMs a pipelined scan leaves to the front / back kernels of its neighbours
     uint32_t ppi_override = 0;   // pages per scan item (0 = heuristic)
-    uint32_t dot_min_items = 12; // the L2 scan screens by dot product when a launch has >= this many items per CTA
+    uint32_t dot_min_rows = 20000; // the L2 scan screens by dot product when a launch streams >= this many distinct rows per CTA
     bool scan_exact = false;     // VDB_SCAN_EXACT=1: L2 scan without the dot-form screen (A/B measurements)
     uint64_t next_ticket = 0;
     int last_slot = -1;

@@ -103,9 +103,11 @@ __device__ __forceinline__ uint32_t n_ranges(const ListTable& lt, uint32_t l, ui
 // scratch, which removes most of the kernel's global round trips.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const uint32_t* __restrict__ probes,
-                                                            uint32_t npairs, uint32_t ppi, WorkList wl) {
+                                                            uint32_t npairs, uint32_t ppi, uint32_t ppi_max,
+                                                            uint32_t scan_ctas, WorkList wl) {
     __shared__ uint32_t s_warp[33];
     __shared__ uint32_t s_cls[ITEM_CLASSES];
+    __shared__ uint32_t s_cand[8];
     extern __shared__ uint32_t s_lists[];
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
     const uint32_t nlist = lt.nlist;
@@ -130,7 +132,40 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
         uint32_t l = probes[p];
         if (l < nlist && lt.rows[l] > 0) atomicAdd(&wl.gcount[l], 1u);
     }
+    if (tid < 8) s_cand[tid] = 0;
     __syncthreads();
+
+    // Pages per item, chosen for THIS batch: every item costs a fixed set-up and epilogue (tile announcement, query
+    // registers, final selection, the global-bound update), so items should be as long as the load balance allows.
+    // The caller's `ppi` sizes the partial-result buffer (the smallest value in play); the kernel doubles it while the
+    // batch still yields at least two items per scan CTA, up to ppi_max (16 pages = 12 MB of rows at 768-D: measured
+    // best from a 1/8 shard, 0.579 -> 0.527 ms, to the whole index, 3.97 -> 3.89 ms; 32 starves a short scan and
+    // gains nothing on a long one).
+    if (ppi_max > ppi) {
+        const uint32_t chunk = (nlist + NT - 1) / NT;
+        const uint32_t lo = min(tid * chunk, nlist), hi = min(lo + chunk, nlist);
+        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t l = lo; l < hi; ++l)
+            if (wl.gcount[l]) {
+                const uint32_t npages = lt.page_off[l + 1] - lt.page_off[l];
+#pragma unroll
+                for (int c = 1; c < 8; ++c) {
+                    const uint32_t pc = ppi << c;
+                    if (pc <= ppi_max) cnt[c] += (npages + pc - 1) / pc;
+                }
+            }
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+            if (cnt[c]) atomicAdd(&s_cand[c], cnt[c]);
+        __syncthreads();
+        uint32_t best = ppi;
+#pragma unroll
+        for (int c = 1; c < 8; ++c) {
+            const uint32_t pc = ppi << c;
+            if (pc <= ppi_max && s_cand[c] >= 2u * scan_ctas) best = pc;
+        }
+        ppi = best;  // the same value in every thread
+    }
 
     // exclusive scans over lists: grouped-pair offsets and item offsets
     {
@@ -363,7 +398,8 @@ struct ScanParams {
     uint32_t* glock;     // [nq] spin locks guarding gtop
     uint32_t* work_counter;
     uint32_t k, P, S, np, check_interval, has_ids;
-    uint32_t dot_min_items;  // the screen is used when the launch has at least this many items per CTA
+    uint32_t dot_min_rows;  // the screen is used when the launch streams at least this many distinct rows per CTA
+    const unsigned long long* stats;  // [1] = distinct probed rows of this launch (build_groups_kernel)
     uint32_t dotform;  // L2 over pages that carry row norms: dot-product screen, exact (q-v)^2 for the survivors
     uint32_t stage_rows;  // rows per ring stage: 16, or 8 for rows wider than 4 KB
     uint32_t qt;  // queries per tile at run time (<= the kernel's register tile)
@@ -1036,10 +1072,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     // register reallocation between warpgroups: the producer's warpgroup (one busy thread) shrinks to 40
     // registers per thread, the two consumer warpgroups grow to 232 = (384 * 168 - 128 * 40) / 256
     // The dot-form screen pays where the scan is long and runs into the power cap (whole index: +4.7 %, half: +2.3 %);
-    // on a short scan (1/8 shard, ~8 items per CTA, full clocks) its admitted pairs -- k ln(rows/k) per query whatever
-    // the shard size, each an L2 round trip for one warp -- cost more than the halved FP work saves (-2.4 %), so a
-    // launch with fewer than 12 items per CTA keeps the exact form.  Uniform over the grid: both loops read it here.
-    const bool dotform = p.dotform && *p.totals >= p.dot_min_items * gridDim.x;
+    // on a short scan (1/8 shard, full clocks) its admitted pairs -- k ln(rows/k) per query whatever the shard size,
+    // each an L2 round trip for one warp -- cost more than the halved FP work saves (-2.4 %), so a launch that streams
+    // fewer than 20 000 distinct rows per CTA (between the 1/2 and the 1/4 shard of the headline index) keeps the
+    // exact form.  Uniform over the grid: both loops read it here.
+    const bool dotform = p.dotform && p.stats[1] >= (unsigned long long)p.dot_min_rows * gridDim.x;
     if (threadIdx.x < CONSUMER_THREADS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
         consumer_loop<NJ>(p, s, dotform);
@@ -1399,7 +1436,8 @@ int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, co
     pl.probes = probes_dev;
     pl.nq = nq; pl.np = np; pl.k = k; pl.metric = metric; pl.ppi = ppi;
     pl.has_ids = has_ids;
-    pl.dot_min_items = 12;
+    pl.dot_min_rows = 20000;
+    pl.ppi_max = ppi;  // the caller may allow the grouping kernel to lengthen the items (index scans)
     pl.has_norms = false;  // set by the caller for index pages (ids followed by row norms)
     pl.info = ScanLaunchInfo{QT, P, S, NJ, (uint32_t)grid, scan_smem_bytes(lt.ld, S, QT, P, stage_rows),
                              std::max(1u, std::min(64u, (P - k) / STAGE_ROWS))};
@@ -1429,9 +1467,9 @@ int32_t scan_enqueue_groups(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t 
                                               cudaSharedmemCarveoutMaxShared));
             gconf[gdev] = true;
         }
-        build_groups_kernel<true><<<1, 1024, gsm, stream>>>(lt, pl.probes, npairs, pl.ppi, wl);
+        build_groups_kernel<true><<<1, 1024, gsm, stream>>>(lt, pl.probes, npairs, pl.ppi, pl.ppi_max, pl.info.grid, wl);
     } else {
-        build_groups_kernel<false><<<1, 1024, 0, stream>>>(lt, pl.probes, npairs, pl.ppi, wl);
+        build_groups_kernel<false><<<1, 1024, 0, stream>>>(lt, pl.probes, npairs, pl.ppi, pl.ppi_max, pl.info.grid, wl);
     }
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
@@ -1454,7 +1492,8 @@ int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t st
     sp.glock = ws.glock;
     sp.k = pl.k; sp.P = pl.info.P; sp.S = pl.info.S; sp.np = pl.np;
     sp.has_ids = pl.has_ids ? 1u : 0u;
-    sp.dot_min_items = pl.dot_min_items;
+    sp.dot_min_rows = pl.dot_min_rows;
+    sp.stats = ws.stats;
     sp.dotform = (pl.has_norms && pl.has_ids && pl.metric == VDB_METRIC_L2) ? 1u : 0u;
     sp.qt = pl.info.QT;
     sp.stage_rows = pl.stage_rows;

@@ -58,9 +58,10 @@ struct ScanPlan {
     const float* queries;
     const uint32_t* probes;
     uint32_t nq, np, k, ppi, stage_rows;
+    uint32_t ppi_max;  // build_groups may lengthen the items up to this many pages (>= ppi), see scan.cu
     int metric;
     bool has_ids;
-    uint32_t dot_min_items;  // dot-form screen only for launches with >= this many items per CTA (default 12)
+    uint32_t dot_min_rows;  // dot-form screen only for launches with >= this many distinct rows per CTA (default 20000)
     bool has_norms;  // every page's id block is followed by [page_rows] f32 |v|^2 (index pages): L2 may screen by dot product
     ScanLaunchInfo info;
 };

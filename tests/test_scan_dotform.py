@@ -18,9 +18,9 @@ pytestmark = pytest.mark.gpu
 def build(dim, nlist, cent, db, exact):
     # both knobs are read when an index is created.  The screen is normally reserved for long scans (>= 12 items per
     # CTA); the small cases here force it on.
-    old = {k_: os.environ.get(k_) for k_ in ("VDB_SCAN_EXACT", "VDB_SCAN_DOT_MIN_ITEMS")}
+    old = {k_: os.environ.get(k_) for k_ in ("VDB_SCAN_EXACT", "VDB_SCAN_DOT_MIN_ROWS")}
     os.environ["VDB_SCAN_EXACT"] = "1" if exact else "0"
-    os.environ["VDB_SCAN_DOT_MIN_ITEMS"] = "0"
+    os.environ["VDB_SCAN_DOT_MIN_ROWS"] = "0"
     try:
         ix = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist))
     finally:
@@ -90,11 +90,11 @@ def test_loaded_epoch_has_norms_too(tmp_path):
     src = build(dim, nlist, cent, db, exact=True)
     d = os.path.join(tmp_path, "ep")
     storage.save_epoch(src, d)
-    os.environ["VDB_SCAN_DOT_MIN_ITEMS"] = "0"
+    os.environ["VDB_SCAN_DOT_MIN_ROWS"] = "0"
     try:
         scr = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist))  # screened
     finally:
-        os.environ.pop("VDB_SCAN_DOT_MIN_ITEMS", None)
+        os.environ.pop("VDB_SCAN_DOT_MIN_ROWS", None)
     storage.load_epoch(scr, d)
     D0, I0 = src.search(q, 6, 10)
     D1, I1 = scr.search(q, 6, 10)
