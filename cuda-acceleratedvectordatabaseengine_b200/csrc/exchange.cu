@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Exc
                     s_fail = 1;
                     break;
                 }
-                __nanosleep(64);
+                __nanosleep(256);  // the flags live in local HBM: keep the pollers off the L2 the scan streams through
             }
         }
         __syncthreads();

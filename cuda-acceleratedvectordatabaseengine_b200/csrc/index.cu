@@ -348,11 +348,41 @@ void harvest_timers(vdb_index* ix, SearchSlot& s) {
 
 }  // namespace
 
+// results of slot `s` (device) -> the caller's host arrays or the slot's pinned staging, behind everything on `st`
+static int32_t enqueue_delivery(SearchSlot& s, cudaStream_t st) {
+    if (s.host_d) {
+        VDB_CUDA_TRY(cudaMemcpyAsync(s.host_d, s.dev_d, s.out_elems * 4, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA_TRY(cudaMemcpyAsync(s.host_i, s.dev_i, s.out_elems * 8, cudaMemcpyDeviceToHost, st));
+    }
+    return VDB_OK;
+}
+
+// enqueue the collect of the batch whose publish went out last (if it is still owed), its delivery and its
+// completion event
+static int32_t flush_deferred_collect(vdb_index* ix, cudaStream_t st) {
+    SearchSlot* d = ix->deferred;
+    if (!d) return VDB_OK;
+    ix->deferred = nullptr;
+    d->collect_deferred = false;
+    VDB_TRY(exchange_collect(ix->exchange, d->dev_d, d->dev_i, st));
+    if (d->timed) cudaEventRecord(d->tm[7], st);
+    VDB_TRY(enqueue_delivery(*d, st));
+    VDB_CUDA_TRY(cudaEventRecord(d->ev_done, st));
+    return VDB_OK;
+}
+
+int32_t vdb::index_flush_deferred(vdb_index* ix, SearchSlot& s) {
+    if (!s.collect_deferred) return VDB_OK;
+    DeviceGuard g(ix->device);
+    return flush_deferred_collect(ix, s.collect_stream);
+}
+
 // Block the host until the search in slot `s` is complete, hand host results to the caller's arrays, report a
 // peer-exchange timeout of this search, and make the slot reusable.  Caller holds ix->mu or owns the ticket.
 int32_t vdb::index_finish_slot(vdb_index* ix, SearchSlot& s) {
     if (!s.busy) return VDB_OK;
     DeviceGuard g(ix->device);
+    if (s.collect_deferred) VDB_TRY(flush_deferred_collect(ix, s.collect_stream));  // nobody submitted after it
     VDB_CUDA_TRY(cudaEventSynchronize(s.ev_done));
     s.busy = false;
     harvest_timers(ix, s);
@@ -479,35 +509,58 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
         oi = s.out_i.p;
     }
     s.used_exchange = ex != nullptr;
+    s.deliver = false;
+    s.dev_d = od;
+    s.dev_i = oi;
+    s.host_d = nullptr;
+    s.host_i = nullptr;
+    s.out_elems = (size_t)nq * k;
+    if (collect && !out_dev) {
+        s.host_d = distances;
+        s.host_i = indices;
+        if (!is_pinned_ptr(distances) || !is_pinned_ptr(indices)) {
+            VDB_TRY(s.h_d.reserve(s.out_elems * 4));
+            VDB_TRY(s.h_i.reserve(s.out_elems * 8));
+            s.host_d = static_cast<float*>(s.h_d.p);
+            s.host_i = static_cast<uint64_t*>(s.h_i.p);
+            s.user_d = distances;
+            s.user_i = indices;
+            s.deliver = true;
+        }
+    }
+    s.collect_deferred = false;
     if (ex) {
+        // The previous batch's collect goes HERE, behind this batch's scan: by now every peer has long published it,
+        // so the collect kernel finds its flags set instead of spinning on the SMs the front / back kernels need
+        // (measured at 8 GPUs: collecting right behind the publish kept 16 CTAs polling for 0.3 ms of every 0.57 ms
+        // step).  It still precedes this batch's publish on every rank, which is what keeps two mailbox halves enough.
+        VDB_TRY(flush_deferred_collect(ix, st.back));
         PublishTarget pub;
         VDB_TRY(exchange_begin_publish(ex, nq, k, &pub));
         VDB_TRY(scan_enqueue_merge(plan, s.ws_scan, nullptr, nullptr, nullptr, &pub, st.back));
         if (prof) cudaEventRecord(s.tm[6], st.back);
-        if (collect) VDB_TRY(exchange_collect(ex, od, oi, st.back));
-    } else {
-        VDB_TRY(scan_enqueue_merge(plan, s.ws_scan, od, oi, nullptr, nullptr, st.back));
-        if (prof) cudaEventRecord(s.tm[6], st.back);
-    }
-    if (prof) cudaEventRecord(s.tm[7], st.back);
-    s.deliver = false;
-    if (collect && !out_dev) {
-        const size_t ne = (size_t)nq * k;
-        float* hd = distances;
-        uint64_t* hi = indices;
-        if (!is_pinned_ptr(distances) || !is_pinned_ptr(indices)) {
-            VDB_TRY(s.h_d.reserve(ne * 4));
-            VDB_TRY(s.h_i.reserve(ne * 8));
-            hd = static_cast<float*>(s.h_d.p);
-            hi = static_cast<uint64_t*>(s.h_i.p);
-            s.user_d = distances;
-            s.user_i = indices;
-            s.out_elems = ne;
-            s.deliver = true;
+        s.busy = true;
+        s.timed = prof;
+        s.info = plan.info;
+        nvtxRangePop();
+        if (!collect) {  // a non-root shard of a single-process index: published, nothing to collect
+            if (prof) cudaEventRecord(s.tm[7], st.back);
+            VDB_CUDA_TRY(cudaEventRecord(s.ev_done, st.back));
+            return VDB_OK;
         }
-        VDB_CUDA_TRY(cudaMemcpyAsync(hd, od, ne * 4, cudaMemcpyDeviceToHost, st.back));
-        VDB_CUDA_TRY(cudaMemcpyAsync(hi, oi, ne * 8, cudaMemcpyDeviceToHost, st.back));
+        s.collect_deferred = true;
+        s.collect_stream = st.back;
+        ix->deferred = &s;
+        // stream-ordered callers (vdb_index_search_async) get their result in stream order: no deferral
+        if (!st.split) VDB_TRY(flush_deferred_collect(ix, st.back));
+        return VDB_OK;
     }
+    VDB_TRY(scan_enqueue_merge(plan, s.ws_scan, od, oi, nullptr, nullptr, st.back));
+    if (prof) {
+        cudaEventRecord(s.tm[6], st.back);
+        cudaEventRecord(s.tm[7], st.back);
+    }
+    VDB_TRY(enqueue_delivery(s, st.back));
     VDB_CUDA_TRY(cudaEventRecord(s.ev_done, st.back));
     nvtxRangePop();
     s.busy = true;
@@ -942,6 +995,7 @@ int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket) {
         VDB_REQUIRE(ticket >= 1 && ticket <= ix->next_ticket, "search_wait: unknown ticket");
         s = &ix->slots[ticket % ix->depth];
         if (s->ticket != ticket || !s->busy) return VDB_OK;  // finished (and delivered) when its slot was recycled
+        if (s->collect_deferred) VDB_TRY(flush_deferred_collect(ix, s->collect_stream));
     }
     {
         DeviceGuard g(ix->device);
@@ -960,6 +1014,7 @@ int32_t vdb_index_search_wait_stream(vdb_index* ix, uint64_t ticket, void* strea
     SearchSlot& s = ix->slots[ticket % ix->depth];
     if (s.ticket != ticket || !s.busy) return VDB_OK;
     DeviceGuard g(ix->device);
+    if (s.collect_deferred) VDB_TRY(flush_deferred_collect(ix, s.collect_stream));
     VDB_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s.ev_done, 0));
     return VDB_OK;
 }

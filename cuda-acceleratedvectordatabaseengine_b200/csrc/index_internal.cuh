@@ -92,6 +92,14 @@ struct SearchSlot {
     size_t out_elems = 0;
     bool deliver = false;
     bool used_exchange = false;
+    // where the merged result goes: device arrays, and (host callers) the pinned or staged host arrays behind them
+    float* dev_d = nullptr;
+    uint64_t* dev_i = nullptr;
+    float* host_d = nullptr;
+    uint64_t* host_i = nullptr;
+    // sharded search: the publish went out, the collect is enqueued behind the NEXT batch's scan (or on demand)
+    bool collect_deferred = false;
+    cudaStream_t collect_stream = nullptr;
     ScanLaunchInfo info{};
 
     uint64_t bytes() const {
@@ -158,6 +166,7 @@ struct vdb_index {
     int last_slot = -1;
     cudaStream_t s_front = nullptr, s_scan[2] = {nullptr, nullptr}, s_back = nullptr;
     vdb_exchange* exchange = nullptr;  // borrowed: attached => searches return the merged result of all shards
+    vdb::SearchSlot* deferred = nullptr;  // the slot whose collect is still owed (at most one)
     uint32_t rs_nq = 0, rs_np = 0, rs_k = 0;  // shape the slots were pre-reserved for (0 = none)
 
     vdb::DevBuf<uint32_t> assign_buf, hist_buf, fill_buf;
@@ -199,6 +208,7 @@ int32_t index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* queries,
                              uint32_t k, float* distances, uint64_t* indices, const SearchStreams& st, bool collect);
 int32_t index_acquire_slot(vdb_index* ix, SearchSlot** out, uint64_t* ticket);
 int32_t index_finish_slot(vdb_index* ix, SearchSlot& s);  // host-wait + deliver + harvest timings
+int32_t index_flush_deferred(vdb_index* ix, SearchSlot& s);  // enqueue the slot's owed collect (no-op otherwise)
 SearchStreams index_pipeline_streams(vdb_index* ix, uint64_t ticket);
 // sum of the partial-result bytes one query needs (0 chunks => fits): nq_chunk < nq means "split the batch"
 void index_choose_ppi(const vdb_index* ix, uint32_t nq, uint32_t np, uint32_t k, uint32_t* ppi, uint32_t* nq_chunk);

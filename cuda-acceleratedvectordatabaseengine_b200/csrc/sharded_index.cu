@@ -546,6 +546,7 @@ int32_t composite_wait(vdb_index* ix, uint64_t ticket) {
         VDB_REQUIRE(ticket >= 1 && ticket <= c->next_ticket, "search_wait: unknown ticket");
         rs = &root->slots[ticket % root->depth];
         if (rs->ticket != ticket || !rs->busy) rs = nullptr;  // finished (and delivered) when its slot was recycled
+        else VDB_TRY(index_flush_deferred(root, *rs));        // nobody submitted after it: its collect goes out now
     }
     if (rs) {
         DeviceGuard g(root->device);
@@ -570,6 +571,7 @@ int32_t composite_wait_stream(vdb_index* ix, uint64_t ticket, cudaStream_t strea
     vdb_index* root = c->shards[c->root];
     SearchSlot& sl = root->slots[ticket % root->depth];
     if (sl.ticket != ticket || !sl.busy) return VDB_OK;
+    VDB_TRY(index_flush_deferred(root, sl));
     VDB_CUDA_TRY(cudaStreamWaitEvent(stream, sl.ev_done, 0));
     return VDB_OK;
 }
