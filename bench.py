@@ -248,7 +248,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's init lines (ranks, transports) go to stderr, not stdout: rank 0 prints exactly one JSON line there
+        # NCCL's init lines (ranks, transports) are wanted, but on stderr: stdout carries exactly one JSON line.
+        # (An inherited NCCL_DEBUG is respected; whatever NCCL still writes to fd 1 is diverted below.)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -671,8 +672,18 @@ def run_c5(a):
         "gpu_launches": nb * 8 * len(devs), "clocks": clocks}), flush=True)
 
 
+def _divert_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    fd 1 is pointed at stderr for the whole run and print() is given the real stdout back."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
     args = parse()
+    _divert_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "c2":
