@@ -248,11 +248,12 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's init lines (ranks, transports) are wanted, but on stderr: stdout carries exactly one JSON line.
-        # (An inherited NCCL_DEBUG is respected; whatever NCCL still writes to fd 1 is diverted below.)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's init lines (ranks, transports) are wanted -- on stderr: stdout carries exactly one JSON line (fd 1 is
+        # diverted to stderr for the whole run, see _divert_stdout).  A weaker inherited level (the image exports
+        # NCCL_DEBUG=VERSION) is raised to INFO / INIT; an inherited INFO or TRACE is left alone.
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module(PKG)
     pkg.lib()
