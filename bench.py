@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--emulate-shards", type=int, default=1,
                     help="tuning aid, 1 GPU: hold only shard 0 of W (what one rank of a W-GPU run scans), no exchange")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-mode", default="auto", choices=["auto", "unsharded", "truth"],
+                    help="N > 1, untimed: compare the sharded answer with an unsharded index on rank 0 (auto: when it "
+                         "fits) or with a torch truth kept on rank 0 (auto: otherwise)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=1_000_000)
     ap.add_argument("--dump-groups", action="store_true", help="stderr: probed-row work by queries-per-list")
@@ -269,10 +272,22 @@ def run_b200(a):
     # N > 1: rank 0 also holds an UNSHARDED index of the same rows (if it fits next to its shard) -- the untimed
     # parity check below compares the sharded answer with it
     ref = None
-    if world > 1 and rank == 0 and not a.no_parity_check and a.n * (a.dim * 4 + 8) * 1.2 < 120e9:
+    fits = a.n * (a.dim * 4 + 8) * 1.2 < 120e9
+    use_truth = world > 1 and not a.no_parity_check and (a.parity_mode == "truth" or (a.parity_mode == "auto" and not fits))
+    if world > 1 and rank == 0 and not a.no_parity_check and not use_truth:
         ref = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, device=local, metric=pkg.Metric.L2 if a.metric == "l2" else pkg.Metric.InnerProduct))
+    # ... and where that copy does not fit (configs[3]: 307 GB), rank 0 keeps an independent TRUTH for a few check
+    # queries instead: their distance to every row, evaluated by torch while the rows stream past, and every row's
+    # list (4 bytes per row each) -- enough to state exactly what an nprobe search and an exhaustive search must return
+    truth = None
+    nchk = 8
+    qchk = torch.randn(nchk, a.dim, generator=torch.Generator(device=dev).manual_seed(999), device=dev)
+    if use_truth and rank == 0:
+        truth = {"dist": torch.empty((nchk, a.n), dtype=torch.float32, device=dev),
+                 "asg": torch.empty(a.n, dtype=torch.int32, device=dev), "vmax": 0.0}
     for lo in range(0, a.n, chunk):
         x = torch.randn(min(chunk, a.n - lo), a.dim, generator=gen, device=dev)
+        torch.cuda.current_stream().synchronize()  # the library works on its own streams: hand it finished rows
         if lo == 0:
             t = time.perf_counter()
             ix.train(x[: min(a.ntrain, x.shape[0])])  # every rank trains on the same rows: identical centroids
@@ -284,6 +299,16 @@ def run_b200(a):
         t_add += time.perf_counter() - t
         if ref is not None:
             ref.add(x)
+        if truth is not None:
+            m = x.shape[0]
+            if a.metric == "ip":
+                truth["dist"][:, lo:lo + m] = -(qchk @ x.T)
+            else:
+                for c0 in range(0, m, 131072):
+                    xc = x[c0:c0 + 131072]
+                    truth["dist"][:, lo + c0:lo + c0 + xc.shape[0]] = ((xc[None, :, :] - qchk[:, None, :]) ** 2).sum(-1)
+            truth["asg"][lo:lo + m] = ix.assign_device(x)
+            truth["vmax"] = max(truth["vmax"], float(x.norm(dim=1).max()))
         del x
     nb = a.warmup + a.steps
     q_all = torch.randn(nb, a.batch, a.dim, generator=gen, device=dev)
@@ -366,6 +391,41 @@ def run_b200(a):
             ix.attach_exchange(exch._h)
             if not (torch.equal(Ds, Dn) and torch.equal(Is, In)):
                 raise SystemExit(f"rank {rank}: peer-memory exchange and NCCL all-gather merge disagree")
+        if use_truth:
+            # (all ranks search; rank 0 judges) the check queries at the run's nprobe and exhaustively, against the
+            # torch truth: top-k by (distance, id) over the rows of the probed lists / over all rows
+            from parity import check_search
+            Dc = torch.empty((nchk, a.k), dtype=torch.float32, device=dev)
+            Ic = torch.empty((nchk, a.k), dtype=torch.int64, device=dev)
+            verdict = torch.zeros(1, dtype=torch.int32, device=dev)
+            checked = []
+            for npr in (a.nprobe, a.nlist):
+                ix.search_wait(ix.search_submit(qchk, npr, a.k, Dc, Ic))
+                if rank == 0:
+                    probes = torch.from_numpy(ix.select_nprobe(qchk, npr).astype(np.int64)).to(dev)
+                    Dt = np.empty((nchk, a.k), np.float32)
+                    It = np.empty((nchk, a.k), np.uint64)
+                    for qi in range(nchk):
+                        rows = torch.isin(truth["asg"], probes[qi].to(torch.int32)).nonzero().squeeze(1) if npr < a.nlist \
+                            else torch.arange(a.n, device=dev)
+                        d = truth["dist"][qi][rows]
+                        order = torch.argsort(d, stable=True)[:a.k]
+                        Dt[qi] = d[order].cpu().numpy()
+                        It[qi] = rows[order].cpu().numpy().astype(np.uint64)
+                    scale = (qchk.norm(dim=1) * truth["vmax"]).cpu().numpy() if a.metric == "ip" else None
+                    try:
+                        ties = check_search(Dc.cpu().numpy(), Ic.cpu().numpy().view(np.uint64), Dt, It, scale)
+                        checked.append(f"nprobe={npr}: {nchk} queries equal the torch truth ({ties} tie-explained swaps)")
+                    except AssertionError as e:
+                        print(f"rank 0: sharded search at nprobe={npr} differs from the torch truth: {e}", file=sys.stderr)
+                        verdict += 1
+            dist.broadcast(verdict, 0)
+            if int(verdict.item()):
+                raise SystemExit("sharded search differs from the independent truth")
+            if rank == 0:
+                parity = {"sharded_equals_truth": True, "checked_on": "; ".join(checked),
+                          "truth": f"torch distances of {nchk} check queries to all {a.n} rows + every row's list, kept on rank 0"}
+                truth = None
         if rank == 0 and ref is not None:
             Dr = torch.empty_like(Ds)
             Ir = torch.empty_like(Is)

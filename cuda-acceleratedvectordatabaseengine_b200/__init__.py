@@ -441,7 +441,12 @@ class IVFFlatIndex:
         if _is_torch(x):
             import torch
             assert x.dtype == torch.float32
-            return x.reshape(-1, d).contiguous()
+            x = x.reshape(-1, d).contiguous()
+            if x.is_cuda:
+                # the library works on its own (non-blocking) streams, which do not wait for torch's: hand it rows
+                # whose producing kernels have finished
+                torch.cuda.current_stream(x.device).synchronize()
+            return x
         return np.ascontiguousarray(x, np.float32).reshape(-1, d)
 
 
