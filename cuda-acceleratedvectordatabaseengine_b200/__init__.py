@@ -54,7 +54,7 @@ class _Stats(C.Structure):
     _fields_ = [("total_vectors", C.c_uint64), ("local_vectors", C.c_uint64), ("gpu_memory_bytes", C.c_uint64),
                 ("pages", C.c_uint64), ("dimension", C.c_uint32), ("nlist", C.c_uint32),
                 ("row_stride", C.c_uint32), ("page_rows", C.c_uint32), ("trained", C.c_int32),
-                ("metric", C.c_int32)]
+                ("metric", C.c_int32), ("scanned_bytes", C.c_uint64)]
 
 
 class _SearchStats(C.Structure):
@@ -80,6 +80,7 @@ ABI = {
     "vdb_index_search_submit": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, C.POINTER(_u64)]),
     "vdb_index_search_wait": (_i32, [_vp, _u64]),
     "vdb_index_search_wait_stream": (_i32, [_vp, _u64, _vp]),
+    "vdb_index_set_arena": (_i32, [_vp, _vp, _i32]),
     "vdb_index_reserve_search": (_i32, [_vp, _u32, _u32, _u32]),
     "vdb_index_attach_exchange": (_i32, [_vp, _vp]),
     "vdb_index_select_nprobe": (_i32, [_vp, _vp, _u32, _u32, _vp]),

@@ -197,9 +197,18 @@ int32_t vdb::index_alloc_page(vdb_index* ix, uint32_t* page) {
             set_last_error("max_gpu_memory exceeded while growing the inverted lists");
             return VDB_OUT_OF_MEMORY;
         }
+        // TransferManager::allocate_device first (the reference's index takes its device memory from the pool it is
+        // given, ivf_flat_index.cpp:424-433); a pool that cannot hold the slab -- the reference then skips the GPU and
+        // searches on the CPU -- is bypassed with a plain allocation
         void* p = nullptr;
-        VDB_CUDA_TRY(cudaMalloc(&p, slab));
+        bool pooled = false;
+        if (ix->arena && ix->arena_device == ix->device) {
+            p = vdb_arena_allocate_device(ix->arena, slab);
+            pooled = p != nullptr;
+        }
+        if (!p) VDB_CUDA_TRY(cudaMalloc(&p, slab));
         ix->slabs.push_back(p);
+        ix->slab_pooled.push_back(pooled);
         ix->slab_bytes_total += slab;
         for (uint32_t i = 0; i < slab_pages; ++i)
             ix->page_addr.push_back((uint64_t)(uintptr_t)p + (uint64_t)i * ix->page_bytes);
@@ -466,6 +475,7 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
     VDB_TRY(scan_plan(list_table(ix), q, nq, s.probes.p, np, k, ix->cfg.metric, ppi, slot_bound(ix, nq, np, ppi), true,
                       max_ctas, s.ws_scan, &plan));
     plan.has_norms = !ix->scan_exact;
+    plan.lifetime_rows = ix->d_scanned;
     plan.dot_min_rows = ix->dot_min_rows;
     if (!ix->ppi_override) plan.ppi_max = std::max(ppi, 16u);  // an explicit VDB_SCAN_PPI is taken literally
     VDB_TRY(scan_enqueue_groups(plan, s.ws_scan, st.front));
@@ -725,6 +735,8 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_back, cudaStreamNonBlocking, prio_hi));
     VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_scan[0], cudaStreamNonBlocking, prio_lo));
     VDB_CUDA_TRY(cudaStreamCreateWithPriority(&ix->s_scan[1], cudaStreamNonBlocking, prio_lo));
+    VDB_CUDA_TRY(cudaMalloc(&ix->d_scanned, 8));
+    VDB_CUDA_TRY(cudaMemset(ix->d_scanned, 0, 8));
     VDB_CUDA_TRY(cudaEventCreate(&ix->span_start));
     VDB_CUDA_TRY(cudaEventCreate(&ix->span_end));
     ix->depth = cfg->pipeline_depth ? cfg->pipeline_depth : 4;
@@ -760,7 +772,10 @@ int32_t vdb_index_destroy(vdb_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        for (void* sl : ix->slabs) cudaFree(sl);
+        for (size_t i = 0; i < ix->slabs.size(); ++i) {
+            if (ix->slab_pooled[i]) vdb_arena_free_device(ix->arena, ix->slabs[i]);
+            else cudaFree(ix->slabs[i]);
+        }
         ix->centroids.release(); ix->cnorm.release(); ix->cmax_bits.release(); ix->c_rows.release();
         ix->c_page_off.release(); ix->c_page_vec.release(); ix->c_page_ids.release(); ix->d_rows.release();
         ix->d_page_off.release(); ix->d_page_vec.release(); ix->d_page_ids.release();
@@ -783,6 +798,7 @@ int32_t vdb_index_destroy(vdb_index* ix) {
             for (auto e : s.tm)
                 if (e) cudaEventDestroy(e);
         }
+        cudaFree(ix->d_scanned);
         if (ix->span_start) cudaEventDestroy(ix->span_start);
         if (ix->span_end) cudaEventDestroy(ix->span_end);
         for (cudaStream_t st : {ix->stream, ix->s_front, ix->s_back, ix->s_scan[0], ix->s_scan[1]})
@@ -1024,6 +1040,19 @@ int32_t vdb_index_search(vdb_index* ix, const float* queries, uint32_t nq, uint3
     uint64_t ticket = 0;
     VDB_TRY(vdb_index_search_submit(ix, queries, nq, nprobe, k, distances, indices, &ticket));
     return vdb_index_search_wait(ix, ticket);
+}
+
+int32_t vdb_index_set_arena(vdb_index* ix, vdb_arena* arena, int32_t arena_device) {
+    VDB_TRY(check_index(ix));
+    if (ix->composite) {
+        for (uint32_t r = 0; r < composite_size(ix); ++r) VDB_TRY(vdb_index_set_arena(composite_shard(ix, r), arena, arena_device));
+        return VDB_OK;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    VDB_REQUIRE(ix->slabs.empty() || arena == ix->arena, "set_arena: the index already holds list pages");
+    ix->arena = arena;
+    ix->arena_device = arena_device;
+    return VDB_OK;
 }
 
 int32_t vdb_index_reserve_search(vdb_index* ix, uint32_t max_nq, uint32_t max_nprobe, uint32_t max_k) {
@@ -1299,6 +1328,12 @@ int32_t vdb_index_stats(vdb_index* ix, vdb_stats* out) {
     out->page_rows = ix->page_rows;
     out->trained = ix->trained ? 1 : 0;
     out->metric = ix->cfg.metric;
+    if (ix->d_scanned) {  // distinct list rows streamed by every search so far (counted by the grouping kernel)
+        DeviceGuard g(ix->device);
+        unsigned long long rows = 0;
+        VDB_CUDA_TRY(cudaMemcpy(&rows, ix->d_scanned, 8, cudaMemcpyDeviceToHost));
+        out->scanned_bytes = rows * (4ull * ix->dim + 8);
+    }
     return VDB_OK;
 }
 

@@ -142,6 +142,10 @@ struct vdb_index {
     std::vector<uint32_t> h_rows;
     std::vector<std::vector<uint32_t>> h_pages;
     std::vector<void*> slabs;
+    std::vector<bool> slab_pooled;     // slab i came from the arena (TransferManager pool), not from cudaMalloc
+    vdb_arena* arena = nullptr;        // borrowed (vdb_index_set_arena): must outlive the index, like the reference's tm_
+    int arena_device = 0;
+    unsigned long long* d_scanned = nullptr;  // device counter: distinct list rows streamed by all searches
     std::vector<uint64_t> page_addr;
     uint32_t pages_per_slab = 0, pages_used = 0;
     vdb::DevBuf<uint32_t> d_rows, d_page_off;

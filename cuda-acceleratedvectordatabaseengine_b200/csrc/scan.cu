@@ -50,6 +50,7 @@ struct WorkList {
     unsigned long long* stats;
     uint32_t* qthr;  // [nq] running upper bound of each query's k-th distance, as an ordered key
     uint32_t nq;
+    unsigned long long* lifetime_rows;  // optional: the index's running total of distinct rows streamed
 };
 
 // order-preserving float <-> uint32 so that atomicMin works on distances of either sign
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
         }
         if (alg) atomicAdd(&wl.stats[0], alg);
         if (uniq) atomicAdd(&wl.stats[1], uniq);
+        if (uniq && wl.lifetime_rows) atomicAdd(wl.lifetime_rows, uniq);
     }
     // exclusive scan over pairs: first partial-result slot of each pair
     {
@@ -1450,7 +1452,7 @@ int32_t scan_enqueue_groups(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t 
     const ListTable& lt = pl.lt;
     const uint32_t npairs = pl.nq * pl.np;
     WorkList wl{ws.gcount, ws.gfill, ws.goff, ws.ioff, ws.gpairs, ws.pair_slot, ws.items, ws.totals, ws.stats,
-                ws.qthr, pl.nq};
+                ws.qthr, pl.nq, pl.lifetime_rows};
     // running top-k of every query: "empty" = (3.39e38, UINT64_MAX), i.e. bytes 0x7f / 0xff; locks open
     VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_d, 0x7f, (size_t)pl.nq * pl.k * 4, stream));
     VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_i, 0xff, (size_t)pl.nq * pl.k * 8, stream));

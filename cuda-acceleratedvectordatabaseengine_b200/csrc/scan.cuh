@@ -61,6 +61,7 @@ struct ScanPlan {
     uint32_t ppi_max;  // build_groups may lengthen the items up to this many pages (>= ppi), see scan.cu
     int metric;
     bool has_ids;
+    unsigned long long* lifetime_rows = nullptr;  // optional device counter: += distinct probed rows of every search
     uint32_t dot_min_rows;  // dot-form screen only for launches with >= this many distinct rows per CTA (default 20000)
     bool has_norms;  // every page's id block is followed by [page_rows] f32 |v|^2 (index pages): L2 may screen by dot product
     ScanLaunchInfo info;

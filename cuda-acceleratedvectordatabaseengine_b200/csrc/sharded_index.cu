@@ -602,6 +602,7 @@ int32_t composite_stats(vdb_index* ix, vdb_stats* out) {
         out->local_vectors += st.local_vectors;
         out->gpu_memory_bytes += st.gpu_memory_bytes;
         out->pages += st.pages;
+        out->scanned_bytes += st.scanned_bytes;
         out->dimension = st.dimension; out->nlist = st.nlist; out->row_stride = st.row_stride;
         out->page_rows = st.page_rows;
         out->trained = st.trained;

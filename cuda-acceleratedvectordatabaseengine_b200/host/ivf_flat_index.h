@@ -167,6 +167,9 @@ public:
         return m;
     }
 
+    vdb_arena* handle() const { return arena_; }
+    int device() const { return config_.device; }
+
 private:
     Config config_;
     vdb_arena* arena_ = nullptr;
@@ -212,6 +215,8 @@ public:
             if (config.devices.size() == 1) c.device = config.devices[0];
             detail::check(vdb_index_create(&c, &ix_), "IVFFlatIndex");
         }
+        // device memory for the lists comes from the TransferManager's pool, as in the reference (:424-433)
+        if (tm_) detail::check(vdb_index_set_arena(ix_, tm_->handle(), tm_->device()), "IVFFlatIndex");
     }
     ~IVFFlatIndex() { vdb_index_destroy(ix_); }
     IVFFlatIndex(const IVFFlatIndex&) = delete;

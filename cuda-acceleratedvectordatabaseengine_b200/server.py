@@ -329,7 +329,8 @@ class VdbServicer:
         HELP / TYPE lines and labels, fed by real counters."""
         with self.lock:
             per = {k: (v[0], sorted(v[1])) for k, v in self.per_index.items()}
-            mem = sum(e[0].get_gpu_memory_usage() for e in self.indices.values())
+            stats = {name: e[0].stats() for name, e in self.indices.items()}
+            mem = sum(st.gpu_memory_bytes for st in stats.values())
             elapsed = max(time.monotonic() - self.started, 1e-9)
             total = self.searches
         q = lambda lat, p: lat[min(len(lat) - 1, int(p * len(lat)))] if lat else 0.0  # noqa: E731
@@ -343,7 +344,11 @@ class VdbServicer:
         out += ["# HELP vdb_gpu_memory_bytes GPU memory usage in bytes", "# TYPE vdb_gpu_memory_bytes gauge",
                 f"vdb_gpu_memory_bytes {mem}",
                 "# HELP vdb_queries_per_second Current queries per second", "# TYPE vdb_queries_per_second gauge",
-                f"vdb_queries_per_second {total / elapsed:.3f}"]
+                f"vdb_queries_per_second {total / elapsed:.3f}",
+                # (not in the reference) what the hot path is bound by: distinct list bytes streamed from HBM
+                "# HELP vdb_hbm_bytes_scanned_total Inverted-list bytes streamed from HBM by searches",
+                "# TYPE vdb_hbm_bytes_scanned_total counter"]
+        out += [f'vdb_hbm_bytes_scanned_total{{index="{name}"}} {st.scanned_bytes}' for name, st in sorted(stats.items())]
         return "\n".join(out) + "\n"
 
     def serve_metrics(self, port=0, host="127.0.0.1"):

@@ -86,6 +86,7 @@ typedef struct {
     uint32_t dimension, nlist, row_stride, page_rows;
     int32_t trained;
     int32_t metric;              /* vdb_metric */
+    uint64_t scanned_bytes;      /* distinct inverted-list bytes streamed from HBM by all searches so far */
 } vdb_stats;
 
 /* Byte accounting of the most recent search: probed rows summed
@@ -160,6 +161,12 @@ int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq
                                 float* distances, uint64_t* indices, uint64_t* ticket);
 int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket);
 int32_t vdb_index_search_wait_stream(vdb_index* ix, uint64_t ticket, void* stream);
+/* The reference's index takes its device memory from the TransferManager it is constructed with
+ * (ivf_flat_index.cpp:13, :424-433).  Same here: with an arena attached (before the first add), list slabs come from
+ * vdb_arena_allocate_device on `arena_device`; a slab the pool cannot hold is allocated directly instead (the
+ * reference would leave the list on the host and search it on the CPU).  The arena is borrowed and must outlive
+ * the index. */
+int32_t vdb_index_set_arena(vdb_index* ix, vdb_arena* arena, int32_t arena_device);
 /* Allocate every search buffer for batches of up to (max_nq, max_nprobe, max_k)
  * now (and again after each add()), so that no allocation happens inside a search. */
 int32_t vdb_index_reserve_search(vdb_index* ix, uint32_t max_nq, uint32_t max_nprobe, uint32_t max_k);

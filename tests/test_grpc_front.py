@@ -182,6 +182,7 @@ def test_epochs_are_persisted_activated_and_measured(tmp_path, devices):
         assert float(vals['vdb_searches_total{index="ix"}']) == 5
         assert float(vals["vdb_gpu_memory_bytes"]) > 0 and float(vals["vdb_queries_per_second"]) > 0
         assert float(vals['vdb_search_duration_milliseconds{index="ix",quantile="0.99"}']) > 0
+        assert float(vals['vdb_hbm_bytes_scanned_total{index="ix"}']) > 0
     finally:
         c.close()
         server.stop(0)

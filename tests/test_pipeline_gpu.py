@@ -199,3 +199,61 @@ def test_float64_and_strided_queries_are_coerced_not_reinterpreted():
         ix.search_async(torch.from_numpy(q64).cuda(), p["nprobe"], p["k"],
                         torch.empty((q.shape[0], p["k"]), device="cuda"),
                         torch.empty((q.shape[0], p["k"]), dtype=torch.int64, device="cuda"), 0)
+
+
+def test_index_takes_its_list_memory_from_the_transfer_manager_pool():
+    """the reference's index allocates through the TransferManager it is given (ivf_flat_index.cpp:424-433): with an
+    arena attached the list slabs come out of the pool; what the pool cannot hold is allocated directly"""
+    import ctypes as C
+    l = pkg.lib()
+    a = C.c_void_p()
+    assert l.vdb_arena_create(0, 200 << 20, 1 << 20, 2, C.byref(a)) == 0
+    st = (C.c_uint64 * 4)()
+    g, db, q, p = load_case("config1")
+    ix = pkg.IVFFlatIndex(pkg.Config(dimension=p["dim"], nlist=p["nlist"]))
+    pkg._check(l.vdb_index_set_arena(ix._h, a, 0))
+    ix.centroids = g["centroids"]
+    ix.add(db)  # 51 MB of rows: the first 64 MiB slab
+    l.vdb_arena_stats(a, st)
+    assert st[0] >= 64 << 20 and st[3] >= 1, list(st)
+    D, I = ix.search(q, p["nprobe"], p["k"])
+    check_search(D, I, g["D"], g["I"])
+    big = O.gaussian(8, 400_000, p["dim"])  # 205 MB more: beyond the pool -> direct allocations, still one index
+    ix.add(big, np.arange(400_000, dtype=np.uint64) + 10**7)
+    assert ix.get_total_vectors() == db.shape[0] + 400_000
+    D2, I2 = ix.search(big[:3], p["nlist"], 1)
+    assert I2[:, 0].tolist() == [10**7, 10**7 + 1, 10**7 + 2] and np.all(D2[:, 0] == 0)
+    ix.close()  # pooled slabs go back to the arena
+    l.vdb_arena_stats(a, st)
+    assert st[0] == 0 and st[3] == 0, list(st)
+    assert l.vdb_arena_destroy(a) == 0
+
+
+def test_transfer_callback_runs_behind_the_copy_without_blocking_the_caller():
+    """TransferManager::enqueue_transfer with a callback (transfer_manager.cpp:218-261: cudaLaunchHostFunc)"""
+    import ctypes as C
+    import threading
+    l = pkg.lib()
+    a = C.c_void_p()
+    assert l.vdb_arena_create(0, 64 << 20, 32 << 20, 2, C.byref(a)) == 0
+    n = 4 << 20
+    h = l.vdb_arena_allocate_pinned(a, n)
+    d = l.vdb_arena_allocate_device(a, n)
+    back = l.vdb_arena_allocate_pinned(a, n)
+    C.memset(h, 7, n)
+    done = threading.Event()
+    seen = []
+    CB = C.CFUNCTYPE(None, C.c_void_p)
+
+    def fn(user):
+        seen.append((C.c_ubyte * 4).from_address(back)[:])  # the D2H copy in front of the callback has landed
+        done.set()
+
+    cb = CB(fn)
+    s = l.vdb_arena_get_stream(a)
+    assert l.vdb_arena_enqueue_transfer(a, d, h, n, 1, s) == 0
+    assert l.vdb_arena_enqueue_transfer_cb(a, back, d, n, 2, s, cb, None) == 0
+    assert done.wait(30)
+    assert seen == [[7, 7, 7, 7]]
+    l.vdb_arena_return_stream(a, s)
+    assert l.vdb_arena_destroy(a) == 0
