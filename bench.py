@@ -426,18 +426,25 @@ def run_b200(a):
                 parity = {"sharded_equals_truth": True, "checked_on": "; ".join(checked),
                           "truth": f"torch distances of {nchk} check queries to all {a.n} rows + every row's list, kept on rank 0"}
                 truth = None
+        if not use_truth and not a.no_parity_check:
+            verdict = torch.zeros(1, dtype=torch.int32, device=dev)
+            if rank == 0 and ref is not None:
+                Dr = torch.empty_like(Ds)
+                Ir = torch.empty_like(Is)
+                ref.search_async(q_all[0], a.nprobe, a.k, Dr, Ir, stream)
+                torch.cuda.synchronize()
+                same = bool(torch.equal(Is, Ir)) and bool(torch.equal(Ds, Dr))
+                parity = {"sharded_equals_unsharded": same, "queries": a.batch,
+                          "checked_on": f"batch 0 against an unsharded {a.n}-row index on rank 0"}
+                if not same:
+                    bad = int(((Is != Ir) | (Ds != Dr)).any(dim=1).sum())
+                    print(f"rank 0: sharded search differs from the unsharded index on {bad} of {a.batch} queries",
+                          file=sys.stderr)
+                    verdict += 1
+            dist.broadcast(verdict, 0)  # every rank leaves together: a parity failure must fail the run, not hang it
+            if int(verdict.item()):
+                raise SystemExit("sharded search differs from the unsharded index")
         if rank == 0 and ref is not None:
-            Dr = torch.empty_like(Ds)
-            Ir = torch.empty_like(Is)
-            ref.search_async(q_all[0], a.nprobe, a.k, Dr, Ir, stream)
-            torch.cuda.synchronize()
-            same_ids = bool(torch.equal(Is, Ir))
-            same_d = bool(torch.equal(Ds, Dr))
-            parity = {"sharded_equals_unsharded": same_ids and same_d, "queries": a.batch,
-                      "checked_on": f"batch 0 against an unsharded {a.n}-row index on rank 0"}
-            if not (same_ids and same_d):
-                bad = int((Is != Ir).any(dim=1).sum())
-                raise SystemExit(f"rank 0: sharded search differs from the unsharded index on {bad} of {a.batch} queries")
             ref.close()
         sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
