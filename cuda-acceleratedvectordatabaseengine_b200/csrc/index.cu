@@ -624,10 +624,6 @@ int32_t reserve_slots(vdb_index* ix) {
     return VDB_OK;
 }
 
-SearchStreams pipeline_streams(vdb_index* ix, uint64_t ticket) {
-    return SearchStreams{ix->s_front, ix->s_scan[ticket & 1], ix->s_back, true, nullptr};
-}
-
 // the shapes one pass cannot take (partial-result buffer) are split over query chunks, each a pass of its own
 int32_t search_chunked(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k, float* distances,
                        uint64_t* indices, uint32_t nq_chunk) {
@@ -637,7 +633,7 @@ int32_t search_chunked(vdb_index* ix, const float* queries, uint32_t nq, uint32_
         uint64_t t = 0;
         VDB_TRY(index_acquire_slot(ix, &s, &t));
         VDB_TRY(index_enqueue_search(ix, *s, queries + (size_t)lo * ix->dim, m, nprobe, k, distances + (size_t)lo * k,
-                                     indices + (size_t)lo * k, pipeline_streams(ix, t), true));
+                                     indices + (size_t)lo * k, index_pipeline_streams(ix, t), true));
         VDB_TRY(index_finish_slot(ix, *s));
     }
     return VDB_OK;
@@ -999,7 +995,7 @@ int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq
     }
     SearchSlot* s = nullptr;
     VDB_TRY(index_acquire_slot(ix, &s, ticket));
-    return index_enqueue_search(ix, *s, queries, nq, nprobe, k, distances, indices, pipeline_streams(ix, *ticket), true);
+    return index_enqueue_search(ix, *s, queries, nq, nprobe, k, distances, indices, index_pipeline_streams(ix, *ticket), true);
 }
 
 int32_t vdb_index_search_wait(vdb_index* ix, uint64_t ticket) {
