@@ -155,3 +155,22 @@ def test_sharded_add_of_device_rows_staged_in_chunks():
     Ds, Is = ix.search(q, nlist, 3)
     Do, Io = one.search(q, nlist, 3)
     assert np.array_equal(Ds, Do) and np.array_equal(Is, Io) and Is[:, 0].tolist() == list(range(9))
+
+
+def test_cpp_mirror_spans_several_gpus_and_matches_the_golden_fixture(tmp_path):
+    """the C++ vdb::IVFFlatIndex mirror with Config::devices (host/sharded_test.cpp): train / add / search / pipelined
+    submit / save / load_from_epoch on a multi-device index, results == tests/golden/config1.npz (the reference's own
+    CPU results on the same std::mt19937 data)"""
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "host", "sharded_test")
+    if not os.path.exists(exe):
+        pkg.build()
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    out = subprocess.run([exe, devs, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "PASSED" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    g = np.load(os.path.join(GOLD, "config1.npz"))
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("R ")]
+    I = np.array([int(r[2]) for r in rows], np.uint64).reshape(g["I"].shape)
+    D = np.array([float(r[3]) for r in rows], np.float32).reshape(g["D"].shape)
+    check_search(D, I, g["D"], g["I"])
