@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=4, help="batches in flight (vdb_index_search_submit)")
     ap.add_argument("--emulate-shards", type=int, default=1,
                     help="tuning aid, 1 GPU: hold only shard 0 of W (what one rank of a W-GPU run scans), no exchange")
+    ap.add_argument("--emulate-rank", type=int, default=0, help="with --emulate-shards: which shard this GPU holds")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--parity-mode", default="auto", choices=["auto", "unsharded", "truth"],
                     help="N > 1, untimed: compare the sharded answer with an unsharded index on rank 0 (auto: when it "
@@ -263,7 +264,7 @@ def run_b200(a):
 
     # ---- build: synthetic N(0,1) rows generated on the device, trained + added by the CUDA path
     t_build = time.perf_counter()
-    shard_rank, shard_count = (0, a.emulate_shards) if a.emulate_shards > 1 and world == 1 else (rank, world)
+    shard_rank, shard_count = (a.emulate_rank, a.emulate_shards) if a.emulate_shards > 1 and world == 1 else (rank, world)
     ix = pkg.IVFFlatIndex(pkg.Config(dimension=a.dim, nlist=a.nlist, metric=pkg.Metric.L2 if a.metric == "l2" else pkg.Metric.InnerProduct, device=local,
                                      shard_rank=shard_rank, shard_count=shard_count, pipeline_depth=a.depth))
     gen = torch.Generator(device=dev).manual_seed(12345)
@@ -547,7 +548,7 @@ def run_b200(a):
         "metric": metric_name(a), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a) + (f" [shard 0 of {a.emulate_shards} only: tuning run]" if shard_count != world else ""),
+        "config": {"workload": workload_name(a) + (f" [shard {a.emulate_rank} of {a.emulate_shards} only: tuning run]" if shard_count != world else ""),
                    "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, " +
                    ("single GPU: no exchange" if world == 1 else
                     "merge kernel stores into the peers' NVLink mailboxes + collect kernel, pipelined over batches"
