@@ -47,7 +47,8 @@ class _Config(C.Structure):
     _fields_ = [("dimension", C.c_uint32), ("nlist", C.c_uint32), ("metric", C.c_int32), ("device", C.c_int32),
                 ("max_gpu_memory", C.c_uint64), ("train_mode", C.c_int32), ("coarse_mode", C.c_int32),
                 ("page_rows", C.c_uint32), ("shard_rank", C.c_uint32), ("shard_count", C.c_uint32),
-                ("pipeline_depth", C.c_uint32), ("reserve_sms", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("pipeline_depth", C.c_uint32), ("reserve_sms", C.c_uint32), ("scan_mirror", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class _Stats(C.Structure):
@@ -205,6 +206,7 @@ class Config:
     devices: tuple = ()           # more than one entry: ONE process, one list shard per device (create_sharded)
     pipeline_depth: int = 0       # searches in flight (search_submit), 0 = 4
     reserve_sms: int = 0          # SMs a pipelined scan leaves to the neighbouring batches' small kernels, 0 = 8
+    scan_mirror: int = 0          # bf16 shadow of the lists for the tensor-core screen: 0 = auto, 1 = off, 2 = on
 
 
 @dataclass
@@ -224,6 +226,7 @@ class IVFFlatIndex:
         c.max_gpu_memory, c.train_mode, c.coarse_mode = config.max_gpu_memory, int(config.train_mode), config.coarse_mode
         c.page_rows, c.shard_rank, c.shard_count = config.page_rows, config.shard_rank, config.shard_count
         c.pipeline_depth, c.reserve_sms = config.pipeline_depth, config.reserve_sms
+        c.scan_mirror = config.scan_mirror
         self.config = config
         self._tm = tm  # borrowed, like the reference's TransferManager*
         self._h = _vp()

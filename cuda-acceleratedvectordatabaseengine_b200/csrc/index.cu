@@ -109,6 +109,7 @@ ListTable list_table(vdb_index* ix) {
     lt.nlist = ix->nlist;
     lt.page_rows = ix->page_rows;
     lt.ld = ix->ld;
+    lt.mirror_off = ix->mirror_off;
     return lt;
 }
 
@@ -475,6 +476,7 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
     VDB_TRY(scan_plan(list_table(ix), q, nq, s.probes.p, np, k, ix->cfg.metric, ppi, slot_bound(ix, nq, np, ppi), true,
                       max_ctas, s.ws_scan, &plan));
     plan.has_norms = !ix->scan_exact;
+    if (ix->scan_exact) plan.mirror = false;  // VDB_SCAN_EXACT=1: the plain fp32 scan (A/B and parity checks)
     plan.lifetime_rows = ix->d_scanned;
     plan.dot_min_rows = ix->dot_min_rows;
     if (!ix->ppi_override) plan.ppi_max = std::max(ppi, 16u);  // an explicit VDB_SCAN_PPI is taken literally
@@ -712,12 +714,28 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     if (pr == 0) {
         const uint64_t target = ix->ld >= 256 ? (768ull << 10) : (256ull << 10);
         pr = (uint32_t)std::max<uint64_t>(16, target / (ix->ld * 4ull) / 16 * 16);
+        // row widths the bf16 screen supports get whole 128-row operand tiles (1024-D: 192 -> 256 rows)
+        if (screen_supported(ix->ld, MIRROR_TILE_ROWS, cfg->metric)) pr = round_up(pr, MIRROR_TILE_ROWS);
     }
     VDB_REQUIRE(pr % 16 == 0 && pr <= 65536, "page_rows must be a multiple of 16, <= 65536");
     ix->page_rows = pr;
     ix->ids_off = (uint64_t)pr * ix->ld * 4;
     // page = [pr][ld] fp32 rows | [pr] u64 ids | [pr] fp32 |row|^2 (the dot-form screen of the L2 scan)
     ix->page_bytes = (ix->ids_off + (uint64_t)pr * 12 + 255) / 256 * 256;
+    // ... | [pr] fp32 |row - bf16(row)| | the rows as bf16 tensor-core operand tiles (the scan's bf16 screen, scan.cu):
+    // +50 % HBM for a scan that streams half the bytes.  scan_mirror: 0 = auto (on where the screen kernel supports
+    // the shape), 1 = off, 2 = on (refused when unsupported); VDB_SCAN_MIRROR overrides (0 / 1).
+    {
+        uint32_t want = cfg->scan_mirror;
+        if (const char* e = std::getenv("VDB_SCAN_MIRROR")) want = std::atoi(e) ? 2u : 1u;
+        const bool can = screen_supported(ix->ld, pr, cfg->metric);
+        VDB_REQUIRE(want <= 2, "scan_mirror must be 0 (auto), 1 (off) or 2 (on)");
+        VDB_REQUIRE(want != 2 || can, "scan_mirror: the bf16 screen needs a row stride of 128 * {1,2,4,6,8} floats and page_rows % 128 == 0");
+        if (can && want != 1) {
+            ix->mirror_off = (uint32_t)((ix->ids_off + (uint64_t)pr * 16 + 1023) / 1024 * 1024);
+            ix->page_bytes = ((uint64_t)ix->mirror_off + (uint64_t)pr * ix->ld * 2 + 255) / 256 * 256;
+        }
+    }
     ix->pages_per_slab = (uint32_t)std::max<uint64_t>(1, SLAB_BYTES / ix->page_bytes);
     ix->h_rows.assign(ix->nlist, 0);
     ix->h_pages.resize(ix->nlist);
@@ -918,7 +936,7 @@ static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids
         VDB_TRY(index_upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
         VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, asg, ix->d_rows.p, ix->fill_buf.p,
                                     ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p, ix->page_rows, ix->ld,
-                                    ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->stream));
+                                    ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->mirror_off, ix->stream));
         ix->h_rows = new_rows;
         VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), ix->nlist * 4, cudaMemcpyHostToDevice,
                                      ix->stream));
@@ -1266,7 +1284,7 @@ int32_t vdb_index_append_list(vdb_index* ix, uint32_t list, const float* vectors
                                      ix->stream));
         VDB_TRY(launch_page_norms(reinterpret_cast<const float*>(page), ix->ld,
                                   reinterpret_cast<float*>(page + ix->ids_off + (size_t)ix->page_rows * 8), r,
-                                  (uint32_t)take, ix->stream));
+                                  (uint32_t)take, ix->mirror_off, ix->page_rows, ix->stream));
         done += take;
     }
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));

@@ -26,6 +26,8 @@
 //   3. merge_kernel         per query: page partials -> per-list top-k
 //      (multiset, as search_list_cpu returns it) -> sort by (dist,id), drop
 //      duplicate ids, pad: merge_results.
+#include <cuda_bf16.h>
+
 #include "scan.cuh"
 #include "exchange.cuh"
 #include "topk.cuh"
@@ -1088,6 +1090,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------- 2b. bf16 tensor-core screen
+
+#include "screen.cuh"
+
 // ------------------------------------------------------------------ 3. merge
 
 struct MergeParams {
@@ -1329,9 +1335,34 @@ int32_t launch_scan(const ScanParams& sp, uint32_t grid, uint32_t smem, cudaStre
     return VDB_OK;
 }
 
+template <int NJ>
+int32_t launch_screen(const screen::Params& sp, uint32_t grid, uint32_t smem, cudaStream_t stream) {
+    static bool configured[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !configured[dev]) {
+        VDB_CUDA_TRY(cudaFuncSetAttribute(screen::screen_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)SMEM_BUDGET));
+        configured[dev] = true;
+    }
+    screen::screen_kernel<NJ><<<grid, screen::THREADS, smem, stream>>>(sp);
+    VDB_CUDA_TRY(cudaGetLastError());
+    return VDB_OK;
+}
+
+// pool entries per query of the screen kernel: room for the global-bound merge (2k) and for a useful number of
+// pushes between compactions
+uint32_t screen_pool(uint32_t k) { return next_pow2(std::max(2 * k, 32u)); }
+
 }  // namespace
 
 int32_t scan_max_k() { return (int32_t)MAX_K; }
+
+bool screen_supported(uint32_t ld, uint32_t page_rows, int metric) {
+    const bool width = ld == 128 || ld == 256 || ld == 512 || ld == 768 || ld == 1024;  // 32 * NJ float4, NJ in {1,2,4,6,8}
+    return width && page_rows % MIRROR_TILE_ROWS == 0 && (metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP) &&
+           screen::smem_bytes(ld, 3) <= SMEM_BUDGET;
+}
 
 int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots, uint32_t k, uint32_t nq) {
     if ((uint64_t)nq * k > cap_gtop) {
@@ -1378,12 +1409,17 @@ int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots
         VDB_CUDA_TRY(cudaMalloc(&part_d, cap_part * 4));
         VDB_CUDA_TRY(cudaMalloc(&part_i, cap_part * 8));
     }
+    if (!qconst) {  // bf16 image of a batch's queries for the screen kernel: 64 slots at the widest supported row
+        VDB_CUDA_TRY(cudaMalloc(&qimg, (size_t)screen::NQ * 1024 * 2));
+        VDB_CUDA_TRY(cudaMalloc(&qconst, (size_t)screen::NQ * 16));
+    }
     if (!totals) {
         VDB_CUDA_TRY(cudaMalloc(&totals, 4 * 4));
         VDB_CUDA_TRY(cudaMalloc(&stats, 4 * 8));
         VDB_CUDA_TRY(cudaMemset(stats, 0, 4 * 8));
     }
-    bytes = (uint64_t)cap_lists * 16 + (uint64_t)cap_pairs * 8 + cap_slots * sizeof(ScanItem) + cap_part * 12 + 48;
+    bytes = (uint64_t)cap_lists * 16 + (uint64_t)cap_pairs * 8 + cap_slots * sizeof(ScanItem) + cap_part * 12 + 48 +
+            (uint64_t)screen::NQ * (1024 * 2 + 16);
     return VDB_OK;
 }
 
@@ -1392,6 +1428,7 @@ void ScanWorkspace::release() {
     cudaFree(gpairs); cudaFree(pair_slot); cudaFree(items); cudaFree(part_cnt); cudaFree(qthr);
     cudaFree(gtop_d); cudaFree(gtop_i); cudaFree(glock);
     cudaFree(part_d); cudaFree(part_i); cudaFree(totals); cudaFree(stats);
+    cudaFree(qimg); cudaFree(qconst);
     *this = ScanWorkspace();
 }
 
@@ -1444,6 +1481,9 @@ int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, co
     pl.info = ScanLaunchInfo{QT, P, S, NJ, (uint32_t)grid, scan_smem_bytes(lt.ld, S, QT, P, stage_rows),
                              std::max(1u, std::min(64u, (P - k) / STAGE_ROWS))};
     pl.stage_rows = stage_rows;
+    // pages with a bf16 shadow: the tensor-core screen streams half the bytes (one batch of <= 64 queries per launch)
+    pl.mirror = lt.mirror_off != 0 && has_ids && nq <= (uint32_t)screen::NQ && screen_pool(k) <= screen::POOL_ENTRIES &&
+                screen_supported(lt.ld, lt.page_rows, metric);
     *out = pl;
     return VDB_OK;
 }
@@ -1457,6 +1497,11 @@ int32_t scan_enqueue_groups(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t 
     VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_d, 0x7f, (size_t)pl.nq * pl.k * 4, stream));
     VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_i, 0xff, (size_t)pl.nq * pl.k * 8, stream));
     VDB_CUDA_TRY(cudaMemsetAsync(ws.glock, 0, (size_t)pl.nq * 4, stream));
+    if (pl.mirror) {
+        screen::query_image_kernel<<<screen::NQ * 32 / 256, 256, 0, stream>>>(pl.queries, pl.nq, lt.ld, ws.qimg,
+                                                                              reinterpret_cast<float4*>(ws.qconst));
+        VDB_CUDA_TRY(cudaGetLastError());
+    }
     if (lt.nlist <= 8192) {
         const uint32_t gsm = 4 * (lt.nlist + 1) * 4;
         static bool gconf[16] = {false};
@@ -1503,6 +1548,26 @@ int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t st
     sp.check_interval = pl.info.check_interval;
     sp.metric = pl.metric;
     const uint32_t grid = pl.info.grid, smem = pl.info.smem_bytes;
+    if (pl.mirror) {
+        screen::Params mp;
+        mp.sp = sp;
+        mp.sp.P = screen_pool(pl.k);
+        mp.qimg = ws.qimg;
+        mp.qconst = reinterpret_cast<const float4*>(ws.qconst);
+        mp.nkb = pl.lt.ld / 64;
+        mp.qt = std::min<uint32_t>(screen::NQ, screen::POOL_ENTRIES / mp.sp.P);
+        uint32_t S = 8;
+        while (S > 3 && screen::smem_bytes(pl.lt.ld, S) > SMEM_BUDGET) --S;
+        mp.S = S;
+        const uint32_t msmem = screen::smem_bytes(pl.lt.ld, S);
+        switch (pl.lt.ld) {
+            case 128: return launch_screen<1>(mp, grid, msmem, stream);
+            case 256: return launch_screen<2>(mp, grid, msmem, stream);
+            case 512: return launch_screen<4>(mp, grid, msmem, stream);
+            case 768: return launch_screen<6>(mp, grid, msmem, stream);
+            default: return launch_screen<8>(mp, grid, msmem, stream);
+        }
+    }
     switch (pl.info.NJ) {
         case 1: VDB_TRY(launch_scan<1>(sp, grid, smem, stream)); break;
         case 2: VDB_TRY(launch_scan<2>(sp, grid, smem, stream)); break;

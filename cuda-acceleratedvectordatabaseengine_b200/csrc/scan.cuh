@@ -38,6 +38,8 @@ struct ScanWorkspace {
     float* part_d = nullptr;
     uint64_t* part_i = nullptr;
     uint64_t cap_slots = 0, cap_part = 0;
+    uint8_t* qimg = nullptr;                // bf16 image of the batch's queries (screen kernel), 64 slots
+    void* qconst = nullptr;                 // [64] float4 {|q|^2, |q|, |q - bf16(q)|, 0}
     uint32_t* totals = nullptr;             // [0] items, [1] slots
     unsigned long long* stats = nullptr;    // [0] algorithmic rows, [1] unique rows
     uint64_t bytes = 0;
@@ -64,6 +66,7 @@ struct ScanPlan {
     unsigned long long* lifetime_rows = nullptr;  // optional device counter: += distinct probed rows of every search
     uint32_t dot_min_rows;  // dot-form screen only for launches with >= this many distinct rows per CTA (default 20000)
     bool has_norms;  // every page's id block is followed by [page_rows] f32 |v|^2 (index pages): L2 may screen by dot product
+    bool mirror = false;  // the pages carry a bf16 shadow and the shape fits: the scan runs as the tensor-core screen kernel
     ScanLaunchInfo info;
 };
 
@@ -95,5 +98,7 @@ int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts,
                     float* out_d, uint64_t* out_i, cudaStream_t stream);
 
 int32_t scan_max_k();
+// can an index of this row stride / page size / metric keep a bf16 shadow for the tensor-core screen?
+bool screen_supported(uint32_t ld, uint32_t page_rows, int metric);
 
 }  // namespace vdb

@@ -1,0 +1,518 @@
+// The bf16 tensor-core screen of the inverted-list scan (included by scan.cu, inside its unnamed namespace).
+//
+// The list scan is HBM-bound: every probed fp32 row (3 KB at 768-D) is streamed once per batch.  An index that
+// keeps a bf16 shadow of its pages (ListTable::mirror_off: the rows rounded to bf16, stored as ready-made
+// 128-byte-swizzled [128 rows][64 elements] operand tiles, plus |v - bf16(v)| per row) lets the scan stream HALF
+// the bytes: this kernel brings the shadow tiles in with 1-D bulk TMA copies, multiplies them on the tensor cores
+// (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM) against the bf16 image of the WHOLE query batch (<= 64
+// queries, resident in shared memory for the kernel's lifetime, UMMA N = 64), and turns every (row, query) dot
+// product into a LOWER BOUND of the exact distance:
+//     q.v - q~.v~ = (q - q~).v + q~.(v - v~)   =>   |q.v - q~.v~| <= e_q |v| + (|q| + e_q) e_v  (+ accumulation slack)
+// with e_q = |q - q~|, e_v = |v - v~| computed exactly (rounded up) when the shadow is written.  A pair whose lower
+// bound beats the query's running k-th distance -- after the first rows of a query almost none does -- is re-scored
+// EXACTLY from the fp32 row in the page with the arithmetic of scan_kernel (same per-lane FMA chain, same
+// 16-8-4-2-1 summation tree), so the distances that reach the pools, the partial results and the merge are bit
+// for bit those of the fp32 scan: the screen only decides which pairs are worth the exact arithmetic.
+//
+// Roles (192 threads, one CTA per SM, persistent over dynamically claimed items):
+//   warp 4, one thread   producer: claims items, announces row tiles (descriptor ring), streams the shadow tiles
+//                        of the item's pages through an S-stage ring of 16 KB (128 rows x 64 elements) stages
+//   warp 5, one thread   tcgen05.mma issuer + TMEM owner: per row tile ld/64 stages x 4 MMAs (M128 N64 K16) into
+//                        one of two 64-column accumulators; tcgen05.commit frees the stage / publishes the tile
+//   warps 0-3            thread = row of the tile = TMEM lane.  Phase A: read the dot products of the queries
+//                        that probe this list (tcgen05.ld), evaluate the lower bound, ballot the admitted pairs
+//                        into shared memory, hand the accumulator back.  Phase B: warp w owns queries w, w+4, ...:
+//                        exact re-score of their admitted rows (fp32 row from the page, query from global
+//                        memory), push into the query's pool (owned by that warp: no atomics), compact when full.
+//                        Last tile of an item: pools -> partial-result slots, global bound update (as scan_kernel).
+#pragma once
+
+namespace screen {
+
+constexpr int NQ = 64;                    // UMMA N: query slots of a batch
+constexpr int THREADS = 192;
+constexpr int CONSUMERS = 128;
+constexpr int RT_RING = 4;                // row-tile descriptors in flight
+constexpr uint32_t A_STAGE = MIRROR_TILE_BYTES;  // 16 KB
+constexpr uint32_t B_BLOCK = NQ * 128;           // 8 KB: one K block of the query image
+constexpr uint32_t POOL_ENTRIES = 2048;   // candidate-pool entries per CTA, split evenly over a pass's queries
+constexpr uint32_t F_FIRST = 1u, F_LAST = 2u, F_END = 0x80000000u;
+// tensor-core accumulation (fp32, K <= 1024 products that are exact in fp32) and the fp32 rounding of the exact
+// inner-product chain, relative to |q||v|: 2^-11 is > 4x the worst case of one truncation per addition
+constexpr float ACC_SLACK = 4.8828125e-4f;
+
+struct Params {
+    ScanParams sp;         // the scan's arguments; sp.P = pool entries per query of this kernel
+    const uint8_t* qimg;   // [ld/64][64][128 B] bf16 image of the batch's queries (zero rows beyond nq)
+    const float4* qconst;  // [64] {|q|^2, |q| rounded up, |q - bf16(q)| rounded up, 0}
+    uint32_t S;            // ring stages
+    uint32_t qt;           // queries per pass over an item = min(64, POOL_ENTRIES / P)
+    uint32_t nkb;          // K blocks = ld / 64
+};
+
+struct Smem {
+    uint8_t* sa;        // [S][16 KB]
+    uint8_t* sb;        // [nkb][8 KB]
+    uint64_t* pool_i;   // [POOL_ENTRIES]
+    float* pool_d;      // [POOL_ENTRIES]
+    uint32_t* cnt;      // [64]
+    float* thr;         // [64]
+    uint32_t* spair;    // [64]
+    uint32_t* sqidx;    // [64]
+    float* qc;          // [64] |q|^2 (1 - DOT_SLACK)
+    float* uc;          // [64] 2 e_q + 2 ACC_SLACK |q|
+    float* wc;          // [64] 2 (|q| + e_q)
+    uint32_t* adm;      // [64][4] admitted rows of the current tile, per query and consumer warp
+    uint32_t* tq;       // [2][64] query index of each slot of a pass          (producer -> consumers)
+    uint32_t* tslot;    // [2][64] partial-result slot of each (pair, range)
+    uint32_t* rt;       // [RT_RING][8] row-tile descriptors
+    uint64_t *full, *empty;        // [8] each
+    uint64_t *rtfull, *rtempty;    // [RT_RING]
+    uint64_t* pfree;               // [2]
+    uint64_t *acc_full, *acc_empty;  // [2]
+    uint64_t* bfull;               // [1]
+    uint32_t* tmem_slot;
+};
+
+__host__ __device__ inline uint32_t fixed_bytes() {
+    return POOL_ENTRIES * 12 + 7 * NQ * 4 + NQ * 4 * 4 + 2 * 2 * NQ * 4 + RT_RING * 8 * 4 + (8 + 8 + 2 * RT_RING + 2 + 2 + 2 + 1) * 8 + 16;
+}
+__host__ __device__ inline uint32_t smem_bytes(uint32_t ld, uint32_t S) {
+    return 1024 + S * A_STAGE + (ld / 64) * B_BLOCK + fixed_bytes();
+}
+
+__device__ __forceinline__ Smem carve(uint8_t* raw, const Params& p) {
+    uint8_t* q = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+    Smem s;
+    s.sa = q;                  q += p.S * A_STAGE;
+    s.sb = q;                  q += p.nkb * B_BLOCK;
+    s.pool_i = (uint64_t*)q;   q += POOL_ENTRIES * 8;
+    s.pool_d = (float*)q;      q += POOL_ENTRIES * 4;
+    s.cnt = (uint32_t*)q;      q += NQ * 4;
+    s.thr = (float*)q;         q += NQ * 4;
+    s.spair = (uint32_t*)q;    q += NQ * 4;
+    s.sqidx = (uint32_t*)q;    q += NQ * 4;
+    s.qc = (float*)q;          q += NQ * 4;
+    s.uc = (float*)q;          q += NQ * 4;
+    s.wc = (float*)q;          q += NQ * 4;
+    s.adm = (uint32_t*)q;      q += NQ * 4 * 4;
+    s.tq = (uint32_t*)q;       q += 2 * NQ * 4;
+    s.tslot = (uint32_t*)q;    q += 2 * NQ * 4;
+    s.rt = (uint32_t*)q;       q += RT_RING * 8 * 4;
+    s.full = (uint64_t*)q;     q += 8 * 8;
+    s.empty = (uint64_t*)q;    q += 8 * 8;
+    s.rtfull = (uint64_t*)q;   q += RT_RING * 8;
+    s.rtempty = (uint64_t*)q;  q += RT_RING * 8;
+    s.pfree = (uint64_t*)q;    q += 2 * 8;
+    s.acc_full = (uint64_t*)q; q += 2 * 8;
+    s.acc_empty = (uint64_t*)q; q += 2 * 8;
+    s.bfull = (uint64_t*)q;    q += 8;
+    s.tmem_slot = (uint32_t*)q;
+    return s;
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, rows 128 bytes apart, 128-byte swizzle, 8-row groups 1024 bytes apart (as tc_common.cuh)
+__device__ __forceinline__ uint64_t desc_sw128(const void* tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(tile) & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// fp32 accumulator, bf16 x bf16, both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// four accumulator columns of this thread's TMEM lane (one tcgen05.ld each), complete on return
+__device__ __forceinline__ void tmem_ld4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float (&v)[4]) {
+    uint32_t a, b, c, d;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%4];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%1}, [%5];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%2}, [%6];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%3}, [%7];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+        : "r"(t0), "r"(t1), "r"(t2), "r"(t3)
+        : "memory");
+    v[0] = __uint_as_float(a);
+    v[1] = __uint_as_float(b);
+    v[2] = __uint_as_float(c);
+    v[3] = __uint_as_float(d);
+}
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
+
+// this lane's share of the exact q.v of one page row: the arithmetic of the inner-product branch of score_batch
+template <int NJ>
+__device__ __forceinline__ float exact_ip_lane(const float4* __restrict__ g4, uint32_t ld4, uint32_t r, uint32_t lane,
+                                               const float4 (&q)[NJ]) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+        const float4 v = __ldg(&g4[r * ld4 + lane + 32 * jj]);
+        const float2 qlo = make_float2(q[jj].x, q[jj].y);
+        acc = jj == 0 ? __fmul2_rn(qlo, make_float2(v.x, v.y)) : __ffma2_rn(qlo, make_float2(v.x, v.y), acc);
+        acc = __ffma2_rn(make_float2(q[jj].z, q[jj].w), make_float2(v.z, v.w), acc);
+    }
+    return acc.x + acc.y;
+}
+
+__device__ __forceinline__ void producer(const Params& p, const Smem& s) {
+    const ScanParams& sp = p.sp;
+    const uint32_t total = *sp.totals;
+    const uint32_t page_rows = sp.lt.page_rows;
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+    // the batch's queries: the B operand of every MMA of this CTA
+    mbar_expect_tx(s.bfull, p.nkb * B_BLOCK);
+    for (uint32_t kb = 0; kb < p.nkb; ++kb)
+        tma_bulk_g2s(s.sb + kb * B_BLOCK, p.qimg + (size_t)kb * B_BLOCK, B_BLOCK, s.bfull);
+    uint32_t stage = 0, phase = 0, ri = 0, rphase = 0, pb = 0, pphase = 0;
+    uint32_t ii = atomicAdd(sp.work_counter, 1u);
+    ScanItem it = sp.items[min(ii, total ? total - 1 : 0)];
+    while (ii < total) {
+        const uint32_t ii_next = atomicAdd(sp.work_counter, 1u);
+        const ScanItem it_next = sp.items[min(ii_next, total - 1)];
+        for (uint32_t g0 = 0; g0 < it.gcount; g0 += p.qt) {
+            const uint32_t qcount = min(p.qt, it.gcount - g0);
+            const uint64_t policy = (g0 + p.qt < it.gcount) ? keep : stream;
+            mbar_wait(&s.pfree[pb], pphase ^ 1);
+#pragma unroll 4
+            for (uint32_t j = 0; j < qcount; ++j) {
+                const uint32_t pair = sp.gpairs[it.gbase + g0 + j];
+                s.tq[pb * NQ + j] = pair / sp.np;
+                s.tslot[pb * NQ + j] = sp.pair_slot[pair] + it.range;
+            }
+            bool first = true;
+            for (uint32_t pgi = 0; pgi < it.npg; ++pgi) {
+                const uint32_t pg = it.pg0 + pgi;
+                const uint32_t rows_in_page = min(page_rows, it.rows_left - pgi * page_rows);
+                const uint8_t* mirror = reinterpret_cast<const uint8_t*>(sp.lt.page_vec[pg]) + sp.lt.mirror_off;
+                for (uint32_t r0 = 0; r0 < rows_in_page; r0 += MIRROR_TILE_ROWS) {
+                    const bool last = pgi + 1 == it.npg && r0 + MIRROR_TILE_ROWS >= rows_in_page;
+                    mbar_wait(&s.rtempty[ri], rphase ^ 1);
+                    uint32_t* d = s.rt + ri * 8;
+                    d[0] = (first ? F_FIRST : 0u) | (last ? F_LAST : 0u);
+                    d[1] = qcount;
+                    d[2] = pb;
+                    d[3] = pg;
+                    d[4] = r0;
+                    d[5] = min((uint32_t)MIRROR_TILE_ROWS, rows_in_page - r0);
+                    mbar_arrive(&s.rtfull[ri]);  // release: publishes the descriptor (and, on a first tile, the pass arrays)
+                    if (++ri == RT_RING) {
+                        ri = 0;
+                        rphase ^= 1;
+                    }
+                    first = false;
+                    const uint8_t* src = mirror + (size_t)(r0 / MIRROR_TILE_ROWS) * p.nkb * A_STAGE;
+                    for (uint32_t kb = 0; kb < p.nkb; ++kb) {
+                        mbar_wait(&s.empty[stage], phase ^ 1);
+                        mbar_expect_tx(&s.full[stage], A_STAGE);
+                        tma_bulk_g2s_hint(s.sa + stage * A_STAGE, src + (size_t)kb * A_STAGE, A_STAGE, &s.full[stage],
+                                          policy);
+                        if (++stage == p.S) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+            if (++pb == 2) {
+                pb = 0;
+                pphase ^= 1;
+            }
+        }
+        ii = ii_next;
+        it = it_next;
+    }
+    mbar_wait(&s.rtempty[ri], rphase ^ 1);
+    s.rt[ri * 8] = F_END;
+    mbar_arrive(&s.rtfull[ri]);
+}
+
+__device__ __forceinline__ void mma_issuer(const Params& p, const Smem& s, uint32_t tmem_base) {
+    constexpr uint32_t idesc = idesc_bf16(MIRROR_TILE_ROWS, NQ);
+    mbar_wait(s.bfull, 0);
+    tc_fence_after();
+    uint32_t stage = 0, phase = 0, ri = 0, rphase = 0, buf = 0, bph = 0;
+    for (;;) {
+        mbar_wait(&s.rtfull[ri], rphase);
+        const uint32_t flags = s.rt[ri * 8];
+        mbar_arrive(&s.rtempty[ri]);
+        if (++ri == RT_RING) {
+            ri = 0;
+            rphase ^= 1;
+        }
+        if (flags & F_END) break;
+        mbar_wait(&s.acc_empty[buf], bph ^ 1);  // the consumers have read this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * NQ;
+        for (uint32_t kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(&s.full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = desc_sw128(s.sa + stage * A_STAGE), db = desc_sw128(s.sb + kb * B_BLOCK);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)  // 16 bf16 = 32 bytes per MMA inside the swizzle atom
+                umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit(&s.empty[stage]);
+            if (++stage == p.S) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        umma_commit(&s.acc_full[buf]);
+        if (++buf == 2) {
+            buf = 0;
+            bph ^= 1;
+        }
+    }
+}
+
+template <int NJ>
+__device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32_t tmem_base) {
+    const ScanParams& sp = p.sp;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ld4 = sp.lt.ld >> 2, page_rows = sp.lt.page_rows, P = sp.P;
+    const bool l2 = sp.metric == VDB_METRIC_L2;
+    // the helpers of scan_kernel (compact_pool, contribute_global) work on this view of the pools
+    ScanSmem ss{};
+    ss.pool_i = s.pool_i;
+    ss.pool_d = s.pool_d;
+    ss.cnt = s.cnt;
+    ss.thr = s.thr;
+    ss.spair = s.spair;
+    ss.sqidx = s.sqidx;
+    uint32_t ri = 0, rphase = 0, buf = 0, bph = 0, qcount = 0;
+    for (;;) {
+        mbar_wait(&s.rtfull[ri], rphase);
+        const uint32_t* d = s.rt + ri * 8;
+        const uint32_t flags = d[0], qc_new = d[1], pbi = d[2], pg = d[3], r0 = d[4], nrows = d[5];
+        if (flags & F_END) break;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.rtempty[ri]);
+        if (++ri == RT_RING) {
+            ri = 0;
+            rphase ^= 1;
+        }
+        if (flags & F_FIRST) {  // a new pass over an item: per-query state of its queries
+            qcount = qc_new;
+            if (tid < qcount) {
+                const uint32_t q = s.tq[pbi * NQ + tid];
+                s.cnt[tid] = 0;
+                s.sqidx[tid] = q;
+                s.spair[tid] = s.tslot[pbi * NQ + tid];
+                s.thr[tid] = key2f(__ldcg(&sp.qthr[q]));  // what earlier items already proved
+                const float4 c = __ldg(&p.qconst[q]);
+                s.qc[tid] = c.x * (1.f - DOT_SLACK);
+                s.uc[tid] = 2.f * c.z + 2.f * ACC_SLACK * c.y;
+                s.wc[tid] = 2.f * (c.y + c.z);
+            }
+            bar_consumers();
+            if (lane == 0) mbar_arrive(&s.pfree[pbi]);
+        } else if (tid < qcount) {
+            // bounds other CTAs published meanwhile; a racing update by the query's owner warp is another valid bound
+            s.thr[tid] = fminf(s.thr[tid], key2f(__ldcg(&sp.qthr[s.sqidx[tid]])));
+        }
+        // this thread's row of the tile
+        const uint8_t* page = reinterpret_cast<const uint8_t*>(__ldg(&sp.lt.page_vec[pg]));
+        const uint64_t* ids = reinterpret_cast<const uint64_t*>(__ldg(&sp.lt.page_ids[pg]));
+        const float* norms = reinterpret_cast<const float*>(ids + page_rows);
+        const bool valid = tid < nrows;
+        float vn = 0.f, ev = 0.f;
+        if (valid) {
+            vn = __ldg(&norms[r0 + tid]);
+            ev = __ldg(&norms[page_rows + r0 + tid]);
+        }
+        const float nv = __fmul_ru(__fsqrt_ru(vn), 1.00001f);
+        const float sr = l2 ? vn * (1.f - DOT_SLACK) : 0.f;
+
+        // ---- phase A: lower bounds from the tensor-core dot products
+        mbar_wait(&s.acc_full[buf], bph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((warp * 32u) << 16) + buf * NQ;
+        for (uint32_t j0 = 0; j0 < qcount; j0 += 4) {
+            uint32_t col[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) col[u] = j0 + u < qcount ? s.sqidx[j0 + u] : 0u;
+            float dot[4];
+            tmem_ld4(taddr + col[0], taddr + col[1], taddr + col[2], taddr + col[3], dot);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u;
+                if (j < qcount) {  // warp-uniform
+                    const float slack = fmaf(nv, s.uc[j], ev * s.wc[j]);
+                    // L2: (|q|^2 + |v|^2)(1 - DOT_SLACK) - 2 q~.v~ - 2 E;  inner product: -q~.v~ - E
+                    const float lb = l2 ? fmaf(-2.f, dot[u], sr + s.qc[j]) - slack : fmaf(-0.5f, slack, -dot[u]);
+                    const uint32_t m = __ballot_sync(0xffffffffu, valid && lb <= s.thr[j]);
+                    if (lane == 0) s.adm[j * 4 + warp] = m;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.acc_empty[buf]);
+        if (++buf == 2) {
+            buf = 0;
+            bph ^= 1;
+        }
+        bar_consumers();
+
+        // ---- phase B: exact distances of the admitted pairs, by the warp that owns the query's pool
+        const float4* g4 = reinterpret_cast<const float4*>(page);
+        for (uint32_t j = warp; j < qcount; j += 4) {
+            const uint4 am = *reinterpret_cast<const uint4*>(&s.adm[j * 4]);
+            if ((am.x | am.y | am.z | am.w) == 0u) continue;
+            float4 q[NJ];
+            {
+                const float4* q4 = reinterpret_cast<const float4*>(sp.queries) + (size_t)s.sqidx[j] * ld4;
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) q[jj] = __ldg(&q4[lane + 32 * jj]);
+            }
+            float* pd = s.pool_d + (size_t)j * P;
+            uint64_t* pi = s.pool_i + (size_t)j * P;
+#pragma unroll 1
+            for (uint32_t w = 0; w < 4; ++w) {
+                uint32_t m = w == 0 ? am.x : w == 1 ? am.y : w == 2 ? am.z : am.w;
+                while (m) {
+                    const uint32_t L = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+                    const uint32_t r = r0 + w * 32u + L;  // page row
+                    float e = l2 ? exact_l2_lane<NJ, true>(g4, ld4, r, page_rows, lane, q)
+                                 : exact_ip_lane<NJ>(g4, ld4, r, lane, q);
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) e += __shfl_xor_sync(0xffffffffu, e, step);
+                    if (!l2) e = -e;  // IP distance = -dot, kernels.cuh:59
+                    if (e <= s.thr[j]) {  // identical in every lane
+                        const uint32_t c = s.cnt[j];
+                        __syncwarp();
+                        if (lane == 0) {
+                            pd[c] = e;
+                            pi[c] = __ldg(&ids[r]);
+                            s.cnt[j] = c + 1;
+                        }
+                        __syncwarp();
+                        if (c + 1 == P) compact_pool(ss, sp, j, lane);  // keeps the best k, tightens thr[j]
+                    }
+                }
+            }
+        }
+
+        if (flags & F_LAST) {  // item done: best k of every query of the pass -> its partial-result slot
+            for (uint32_t j = warp; j < qcount; j += 4) {
+                compact_pool(ss, sp, j, lane);
+                const float bound = s.thr[j];
+                const uint32_t kept = s.cnt[j];
+                uint32_t nc = 0;
+                for (uint32_t i0 = 0; i0 < kept; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const bool ok = i < kept && s.pool_d[(size_t)j * P + i] <= bound;
+                    nc += __popc(__ballot_sync(0xffffffffu, ok));  // sorted ascending: survivors are a prefix
+                }
+                const size_t slot = s.spair[j];
+                for (uint32_t i = lane; i < nc; i += 32) {
+                    sp.part_d[slot * sp.k + i] = s.pool_d[(size_t)j * P + i];
+                    sp.part_i[slot * sp.k + i] = s.pool_i[(size_t)j * P + i];
+                }
+                if (lane == 0) sp.part_cnt[slot] = nc;
+                if (nc > 0) contribute_global(ss, sp, j, nc, lane);
+            }
+        }
+        bar_consumers();  // adm and the per-query state are rewritten by the next tile
+    }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(THREADS, 1) screen_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t screen_smem[];
+    const Smem s = carve(screen_smem, p);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < 8; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        for (uint32_t i = 0; i < RT_RING; ++i) {
+            mbar_init(&s.rtfull[i], 1);
+            mbar_init(&s.rtempty[i], 5);  // four consumer warps + the MMA issuer
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(&s.pfree[i], 4);
+            mbar_init(&s.acc_full[i], 1);
+            mbar_init(&s.acc_empty[i], 4);
+        }
+        mbar_init(s.bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 5) {  // two accumulators of 64 fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_slot)),
+                     "n"(2 * NQ)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s.tmem_slot;
+    if (warp < 4) {
+        consumers<NJ>(p, s, tmem_base);
+    } else if (warp == 4) {
+        if (lane == 0) producer(p, s);
+    } else if (lane == 0) {
+        mma_issuer(p, s, tmem_base);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * NQ) : "memory");
+    }
+}
+
+// bf16 image + constants of the batch's queries: one warp per query slot (64 slots, zero rows beyond nq)
+__global__ void __launch_bounds__(256) query_image_kernel(const float* __restrict__ queries, uint32_t nq, uint32_t ld,
+                                                          uint8_t* __restrict__ qimg, float4* __restrict__ qconst) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= (uint32_t)NQ) return;
+    float nrm = 0.f, err = 0.f;
+    for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+        const float4 t = slot < nq ? reinterpret_cast<const float4*>(queries + (size_t)slot * ld)[c]
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+        uint2 bits;
+        bits.x = *reinterpret_cast<const uint32_t*>(&lo);
+        bits.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(qimg + mirror_elem_off(slot, c * 4u, ld, NQ)) = bits;
+        nrm = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, nrm))));
+        const float dx = t.x - __low2float(lo), dy = t.y - __high2float(lo);
+        const float dz = t.z - __low2float(hi), dw = t.w - __high2float(hi);
+        err = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, err))));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        err += __shfl_xor_sync(0xffffffffu, err, o);
+    }
+    if (lane == 0)
+        qconst[slot] = make_float4(nrm, __fmul_ru(__fsqrt_ru(nrm), 1.0002f), __fmul_ru(__fsqrt_ru(err), 1.0002f), 0.f);
+}
+
+}  // namespace screen

@@ -75,7 +75,10 @@ typedef struct {
     uint32_t pipeline_depth; /* searches in flight (vdb_index_search_submit), 0 = 4, at most 8 */
     uint32_t reserve_sms;    /* SMs a pipelined list scan leaves to the coarse / merge kernels of the neighbouring
                                 batches, 0 = 8, 0xffffffff = none */
-    uint32_t reserved[3];
+    uint32_t scan_mirror;    /* bf16 shadow of the inverted lists for the tensor-core screen of the list scan (+50 % HBM,
+                                half the bytes streamed per search; results unchanged): 0 = auto (on where supported:
+                                row stride 128 * {1,2,4,6,8} floats), 1 = off, 2 = on (refused where unsupported) */
+    uint32_t reserved[2];
 } vdb_config;
 
 typedef struct {
