@@ -128,11 +128,12 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
-def profiled_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one scan_kernel launch from the committed ncu --set full
-    capture of this same workload (profiles/scan_traffic.json, written from the .ncu-rep by tools/ncu_summary.py)."""
+def profiled_traffic(mirror=False):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed ncu --set full capture of
+    this same workload (profiles/scan_traffic.json: the fp32 scan_kernel; profiles/screen_traffic.json: the bf16
+    screen_kernel; written from the .ncu-rep by tools/ncu_summary.py)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "screen_traffic.json" if mirror else "scan_traffic.json")) as f:
             return float(json.load(f)["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -516,8 +517,11 @@ def run_b200(a):
         items += ss.scan_items
     t = ix.search_submit(q_all[0], a.nprobe, a.k, Dd[0], Id[0])
     ix.search_wait(t)
-    scan_ctas = int(ix.last_search_stats().scan_ctas)
+    ss = ix.last_search_stats()
+    scan_ctas = int(ss.scan_ctas)
     bpr = 4 * a.dim + 8
+    bpr_streamed = int(ss.streamed_bytes_per_row) or bpr  # 2*ld + 8 when the bf16 tensor-core screen ran
+    mirror = bpr_streamed != bpr
     peak, peak_src = measured_peak()
     nsearch = max(prof["searches"], 1)
     # kernel time: the scan streams' busy time per launch (first scan start .. last scan end over the timed
@@ -526,11 +530,12 @@ def run_b200(a):
     scan_ms = (prof["scan_span_ms"] / nsearch) if (pipelined and prof["scan_span_ms"] > 0) else prof["scan_ms"] / nsearch
     alg_bytes = alg_rows * bpr / a.steps
     uniq_bytes = uniq_rows * bpr / a.steps
-    achieved = uniq_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    streamed_bytes = uniq_rows * bpr_streamed / a.steps
+    achieved = streamed_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
 
     rank_scan_ms = None
     if world > 1:  # per-rank scan time and distinct bytes: shows how well the list ownership balances
-        mine = torch.tensor([scan_ms, uniq_bytes / 1e9], device=dev, dtype=torch.float64)
+        mine = torch.tensor([scan_ms, streamed_bytes / 1e9], device=dev, dtype=torch.float64)
         allr = torch.empty((world, 2), device=dev, dtype=torch.float64)
         dist.all_gather_into_tensor(allr, mine)
         rank_scan_ms = [[round(float(a), 3), round(float(b_), 2)] for a, b_ in allr.cpu().tolist()]
@@ -555,18 +560,26 @@ def run_b200(a):
                     if exch is not None else "NCCL all-gather + merge kernel per batch"),
                    "pipeline": (f"{depth} batches in flight: coarse/grouping of batch i+1 and merge/exchange of batch i-1 "
                                 f"overlap the scan of batch i ({scan_ctas} scan CTAs of 148 SMs)") if pipelined else "none",
-                   "cache": f"inputs larger than L2: each batch streams {uniq_bytes / 1e9:.2f} GB of distinct list data",
+                   "cache": f"inputs larger than L2: each batch streams {streamed_bytes / 1e9:.2f} GB of distinct list data" +
+                            (f" (bf16 shadow of {uniq_bytes / 1e9:.2f} GB of fp32 rows)" if mirror else ""),
+                   "scan": ("bf16 tensor-core screen over the lists' bf16 shadow (tcgen05), exact fp32 re-score of the "
+                            "admitted pairs: results bit-identical to the fp32 scan") if mirror else "fp32 list scan",
                    "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
                    "index_gb": round(st.gpu_memory_bytes / 1e9, 2),
                    **({"rank_scan_ms_and_unique_gb": rank_scan_ms} if rank_scan_ms else {}),
                    **({"parity": parity} if parity else {})},
-        # frac = distinct probed bytes / scan time / peak: a list probed by several queries of the batch streams from
-        # HBM once.  `reuse` = algorithmic bytes (every query's probed rows) / distinct bytes.
-        "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     "traffic": profiled_traffic() if (headline and world == 1 and shard_count == 1) else None,
+        # frac = bytes the scan streams (distinct probed rows x bytes per row as stored for the scan) / scan time / peak:
+        # a list probed by several queries of the batch streams from HBM once, and the bf16 screen streams the rows'
+        # bf16 shadow (2*ld + 8 bytes per row) instead of the fp32 rows.  `unique_bytes_per_launch` is the fp32 size of
+        # the same rows (4*dim + 8 each: what SURVEY 8d counts), `fp32_equivalent_gbs` that size over the scan time;
+        # `reuse` = algorithmic bytes (every query's probed rows) / distinct bytes.
+        "roofline": {"bound": "hbm", "kernel": "screen_kernel" if mirror else "scan_kernel", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": profiled_traffic(mirror) if (headline and world == 1 and shard_count == 1) else None,
                      "peak_source": peak_src,
+                     "streamed_bytes_per_launch": streamed_bytes,
+                     "fp32_equivalent_gbs": uniq_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0,
                      "algorithmic_bytes_per_launch": alg_bytes, "unique_bytes_per_launch": uniq_bytes,
                      "reuse": alg_bytes / uniq_bytes if uniq_bytes else None,
                      "algorithmic_gbs": alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0,

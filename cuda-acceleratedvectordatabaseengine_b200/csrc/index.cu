@@ -476,7 +476,10 @@ int32_t vdb::index_enqueue_search(vdb_index* ix, SearchSlot& s, const float* que
     VDB_TRY(scan_plan(list_table(ix), q, nq, s.probes.p, np, k, ix->cfg.metric, ppi, slot_bound(ix, nq, np, ppi), true,
                       max_ctas, s.ws_scan, &plan));
     plan.has_norms = !ix->scan_exact;
-    if (ix->scan_exact) plan.mirror = false;  // VDB_SCAN_EXACT=1: the plain fp32 scan (A/B and parity checks)
+    if (ix->scan_exact) {  // VDB_SCAN_EXACT=1: the plain fp32 scan (A/B and parity checks)
+        plan.mirror = false;
+        plan.info.mirror = 0;
+    }
     plan.lifetime_rows = ix->d_scanned;
     plan.dot_min_rows = ix->dot_min_rows;
     if (!ix->ppi_override) plan.ppi_max = std::max(ppi, 16u);  // an explicit VDB_SCAN_PPI is taken literally
@@ -1362,6 +1365,7 @@ int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
     DeviceGuard g(ix->device);
     std::memset(out, 0, sizeof(*out));
     out->bytes_per_row = 4ull * ix->dim + 8;
+    out->streamed_bytes_per_row = out->bytes_per_row;
     if (ix->last_slot < 0) return VDB_OK;
     SearchSlot& s = ix->slots[ix->last_slot];
     VDB_TRY(index_finish_slot(ix, s));
@@ -1373,6 +1377,8 @@ int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
     out->unique_rows = st[1];
     out->scan_items = tot[0];
     out->scan_ctas = s.info.grid;
+    // the bf16 screen streams the shadow row, |v|^2 and |v - bf16(v)|; ids and fp32 rows only for admitted pairs
+    if (s.info.mirror) out->streamed_bytes_per_row = 2ull * ix->ld + 8;
     return VDB_OK;
 }
 

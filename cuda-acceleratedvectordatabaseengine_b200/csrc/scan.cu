@@ -1484,6 +1484,7 @@ int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, co
     // pages with a bf16 shadow: the tensor-core screen streams half the bytes (one batch of <= 64 queries per launch)
     pl.mirror = lt.mirror_off != 0 && has_ids && nq <= (uint32_t)screen::NQ && screen_pool(k) <= screen::POOL_ENTRIES &&
                 screen_supported(lt.ld, lt.page_rows, metric);
+    pl.info.mirror = pl.mirror ? 1u : 0u;
     *out = pl;
     return VDB_OK;
 }

@@ -50,6 +50,7 @@ struct ScanWorkspace {
 
 struct ScanLaunchInfo {
     uint32_t QT, P, S, NJ, grid, smem_bytes, check_interval;
+    uint32_t mirror;  // 1: this launch runs the bf16 tensor-core screen over the pages' shadow
 };
 
 struct PublishTarget;  // exchange.cuh

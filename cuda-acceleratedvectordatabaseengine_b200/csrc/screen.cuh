@@ -38,8 +38,9 @@ constexpr uint32_t B_BLOCK = NQ * 128;           // 8 KB: one K block of the que
 constexpr uint32_t POOL_ENTRIES = 2048;   // candidate-pool entries per CTA, split evenly over a pass's queries
 constexpr uint32_t F_FIRST = 1u, F_LAST = 2u, F_END = 0x80000000u;
 // tensor-core accumulation (fp32, K <= 1024 products that are exact in fp32) and the fp32 rounding of the exact
-// inner-product chain, relative to |q||v|: 2^-11 is > 4x the worst case of one truncation per addition
-constexpr float ACC_SLACK = 4.8828125e-4f;
+// inner-product chain, relative to |q||v|.  Measured through cuBLAS on this part (tools/tc_accumulate_check.py, K = 768
+// and 1024, Gaussian / 16-binade / all-positive values): at most 1.3e-6; 2^-14 = 6.1e-5 leaves a factor of ~50.
+constexpr float ACC_SLACK = 6.103515625e-5f;
 
 struct Params {
     ScanParams sp;         // the scan's arguments; sp.P = pool entries per query of this kernel
@@ -72,6 +73,7 @@ struct Smem {
     uint64_t *acc_full, *acc_empty;  // [2]
     uint64_t* bfull;               // [1]
     uint32_t* tmem_slot;
+    uint32_t* redo;     // a warp left rows of a cold query out of round 0 of the current tile
 };
 
 __host__ __device__ inline uint32_t fixed_bytes() {
@@ -108,6 +110,7 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, const Params& p) {
     s.acc_empty = (uint64_t*)q; q += 2 * 8;
     s.bfull = (uint64_t*)q;    q += 8;
     s.tmem_slot = (uint32_t*)q;
+    s.redo = s.tmem_slot + 1;
     return s;
 }
 
@@ -349,6 +352,13 @@ __device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32
         mbar_wait(&s.acc_full[buf], bph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((warp * 32u) << 16) + buf * NQ;
+        // A query that has no bound yet (a "cold" query: the first rows of its first items) would admit every row of
+        // the tile, and every admitted pair costs an exact re-score.  Round 0 therefore admits, per warp, only the
+        // rows with the smallest lower bounds for it; phase B turns those into a real bound; round 1 re-reads the
+        // same accumulator and admits what still passes among the rows left out.  Any choice of the round-0 subset
+        // is sound -- every row is tested against a bound that holds before it is dropped.
+        const uint32_t cold_rows = sp.k <= 16 ? (sp.k + 1) / 2 + 1 : 32u;  // per warp: ~2k per tile
+        uint64_t coldq = 0, coldtaken = 0;  // queries this warp treated as cold / rows (this thread's) taken for them
         for (uint32_t j0 = 0; j0 < qcount; j0 += 4) {
             uint32_t col[4];
 #pragma unroll
@@ -362,45 +372,49 @@ __device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32
                     const float slack = fmaf(nv, s.uc[j], ev * s.wc[j]);
                     // L2: (|q|^2 + |v|^2)(1 - DOT_SLACK) - 2 q~.v~ - 2 E;  inner product: -q~.v~ - E
                     const float lb = l2 ? fmaf(-2.f, dot[u], sr + s.qc[j]) - slack : fmaf(-0.5f, slack, -dot[u]);
-                    const uint32_t m = __ballot_sync(0xffffffffu, valid && lb <= s.thr[j]);
+                    const float thr = s.thr[j];
+                    bool pass = valid && lb <= thr;
+                    if (thr == INFINITY && cold_rows < 32u) {  // warp-uniform: thr comes from shared memory
+                        const uint32_t key = valid && !(lb != lb) ? f2key(lb) : 0xffffffffu;
+                        bool taken = false;
+                        for (uint32_t t = 0; t < cold_rows; ++t) {
+                            const uint32_t mn = __reduce_min_sync(0xffffffffu, taken ? 0xffffffffu : key);
+                            if (mn == 0xffffffffu) break;
+                            taken |= key == mn;
+                        }
+                        pass = valid && taken;
+                        coldq |= 1ull << j;
+                        if (taken) coldtaken |= 1ull << j;
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, pass);
                     if (lane == 0) s.adm[j * 4 + warp] = m;
                 }
             }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.acc_empty[buf]);
-        if (++buf == 2) {
-            buf = 0;
-            bph ^= 1;
-        }
+        if (coldq != 0 && lane == 0) *s.redo = 1u;
         bar_consumers();
+        const bool redo = *s.redo != 0u;  // some warp left rows out: the accumulator is needed again
+        if (!redo) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_empty[buf]);
+        }
 
-        // ---- phase B: exact distances of the admitted pairs, by the warp that owns the query's pool
         const float4* g4 = reinterpret_cast<const float4*>(page);
-        for (uint32_t j = warp; j < qcount; j += 4) {
-            const uint4 am = *reinterpret_cast<const uint4*>(&s.adm[j * 4]);
-            if ((am.x | am.y | am.z | am.w) == 0u) continue;
-            float4 q[NJ];
-            {
-                const float4* q4 = reinterpret_cast<const float4*>(sp.queries) + (size_t)s.sqidx[j] * ld4;
+        // ---- phase B: exact distances of the admitted pairs, by the warp that owns the query's pool
+        auto phase_b = [&]() {
+            for (uint32_t j = warp; j < qcount; j += 4) {
+                const uint4 am = *reinterpret_cast<const uint4*>(&s.adm[j * 4]);
+                if ((am.x | am.y | am.z | am.w) == 0u) continue;
+                float4 q[NJ];
+                {
+                    const float4* q4 = reinterpret_cast<const float4*>(sp.queries) + (size_t)s.sqidx[j] * ld4;
 #pragma unroll
-                for (int jj = 0; jj < NJ; ++jj) q[jj] = __ldg(&q4[lane + 32 * jj]);
-            }
-            float* pd = s.pool_d + (size_t)j * P;
-            uint64_t* pi = s.pool_i + (size_t)j * P;
-#pragma unroll 1
-            for (uint32_t w = 0; w < 4; ++w) {
-                uint32_t m = w == 0 ? am.x : w == 1 ? am.y : w == 2 ? am.z : am.w;
-                while (m) {
-                    const uint32_t L = (uint32_t)__ffs((int)m) - 1u;
-                    m &= m - 1u;
-                    const uint32_t r = r0 + w * 32u + L;  // page row
-                    float e = l2 ? exact_l2_lane<NJ, true>(g4, ld4, r, page_rows, lane, q)
-                                 : exact_ip_lane<NJ>(g4, ld4, r, lane, q);
-#pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) e += __shfl_xor_sync(0xffffffffu, e, step);
-                    if (!l2) e = -e;  // IP distance = -dot, kernels.cuh:59
+                    for (int jj = 0; jj < NJ; ++jj) q[jj] = __ldg(&q4[lane + 32 * jj]);
+                }
+                float* pd = s.pool_d + (size_t)j * P;
+                uint64_t* pi = s.pool_i + (size_t)j * P;
+                auto push = [&](float e, uint32_t r) {
                     if (e <= s.thr[j]) {  // identical in every lane
                         const uint32_t c = s.cnt[j];
                         __syncwarp();
@@ -412,8 +426,77 @@ __device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32
                         __syncwarp();
                         if (c + 1 == P) compact_pool(ss, sp, j, lane);  // keeps the best k, tightens thr[j]
                     }
+                };
+#pragma unroll 1
+                for (uint32_t w = 0; w < 4; ++w) {
+                    uint32_t m = w == 0 ? am.x : w == 1 ? am.y : w == 2 ? am.z : am.w;
+                    while (m) {  // two admitted rows at a time: their (HBM) row loads overlap
+                        const uint32_t La = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        const bool two = m != 0u;
+                        const uint32_t Lb = two ? (uint32_t)__ffs((int)m) - 1u : La;
+                        m &= m - 1u;  // (0 & anything = 0)
+                        const uint32_t ra = r0 + w * 32u + La, rb = r0 + w * 32u + Lb;  // page rows
+                        float ea, eb;
+                        if (l2) {
+                            ea = exact_l2_lane<NJ, true>(g4, ld4, ra, page_rows, lane, q);
+                            eb = exact_l2_lane<NJ, true>(g4, ld4, rb, page_rows, lane, q);
+                        } else {
+                            ea = exact_ip_lane<NJ>(g4, ld4, ra, lane, q);
+                            eb = exact_ip_lane<NJ>(g4, ld4, rb, lane, q);
+                        }
+#pragma unroll
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            ea += __shfl_xor_sync(0xffffffffu, ea, step);
+                            eb += __shfl_xor_sync(0xffffffffu, eb, step);
+                        }
+                        if (!l2) {  // IP distance = -dot, kernels.cuh:59
+                            ea = -ea;
+                            eb = -eb;
+                        }
+                        push(ea, ra);
+                        if (two) push(eb, rb);
+                    }
                 }
             }
+        };
+        phase_b();
+        if (redo) {
+            // a bound for the cold queries from what round 0 found (a pool compacts by itself only when it is full)
+            for (uint32_t j = warp; j < qcount; j += 4)
+                if (s.thr[j] == INFINITY && s.cnt[j] >= sp.k) compact_pool(ss, sp, j, lane);
+            bar_consumers();  // every pool has taken its round-0 rows: thr is what round 1 tests against
+            if (tid == 0) *s.redo = 0u;
+            for (uint32_t j0 = 0; j0 < qcount; j0 += 4) {
+                uint32_t col[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) col[u] = j0 + u < qcount ? s.sqidx[j0 + u] : 0u;
+                float dot[4] = {0.f, 0.f, 0.f, 0.f};
+                if ((coldq >> j0) & 0xfull)  // warp-uniform
+                    tmem_ld4(taddr + col[0], taddr + col[1], taddr + col[2], taddr + col[3], dot);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + u;
+                    if (j < qcount) {
+                        uint32_t m = 0;
+                        if ((coldq >> j) & 1ull) {
+                            const float slack = fmaf(nv, s.uc[j], ev * s.wc[j]);
+                            const float lb = l2 ? fmaf(-2.f, dot[u], sr + s.qc[j]) - slack : fmaf(-0.5f, slack, -dot[u]);
+                            m = __ballot_sync(0xffffffffu, valid && !((coldtaken >> j) & 1ull) && lb <= s.thr[j]);
+                        }
+                        if (lane == 0) s.adm[j * 4 + warp] = m;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_empty[buf]);
+            bar_consumers();
+            phase_b();
+        }
+        if (++buf == 2) {
+            buf = 0;
+            bph ^= 1;
         }
 
         if (flags & F_LAST) {  // item done: best k of every query of the pass -> its partial-result slot
@@ -460,6 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) screen_kernel(const __grid_constan
             mbar_init(&s.acc_empty[i], 4);
         }
         mbar_init(s.bfull, 1);
+        *s.redo = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }

@@ -621,6 +621,7 @@ int32_t composite_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
         out->unique_rows += st.unique_rows;
         out->scan_items += st.scan_items;
         out->bytes_per_row = st.bytes_per_row;
+        out->streamed_bytes_per_row = st.streamed_bytes_per_row;
         out->scan_ctas = st.scan_ctas;
     }
     return VDB_OK;

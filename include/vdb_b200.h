@@ -100,6 +100,8 @@ typedef struct {
     uint64_t scan_items;
     uint64_t bytes_per_row; /* 4*dim + 8 */
     uint64_t scan_ctas;     /* persistent CTAs of the list-scan launch */
+    uint64_t streamed_bytes_per_row; /* what the scan kernel streams per distinct row: bytes_per_row for the fp32
+                                        scan; 2*row_stride + 8 when the bf16 screen ran (vdb_config.scan_mirror) */
 } vdb_search_stats;
 
 typedef struct vdb_index vdb_index;

@@ -3,7 +3,8 @@
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_scan_final [scan_kernel]
 
 writes <out>_summary.csv (selected raw metrics, one column per captured launch), <out>_stalls.txt (top
-instructions by warp-stall samples) and, for the scan kernel, profiles/scan_traffic.json."""
+instructions by warp-stall samples) and, for the scan kernels, profiles/scan_traffic.json (scan_kernel) or
+profiles/screen_traffic.json (screen_kernel)."""
 import csv
 import json
 import subprocess
@@ -65,7 +66,7 @@ def main():
                 f.write("top instructions by samples:\n")
                 for r in sorted(body2, key=lambda r: -int(r[si] or 0))[:30]:
                     f.write(f"  {r[si]:>7s}  {r[so][:110]}\n")
-        if kname == "scan_kernel":
+        if kname in ("scan_kernel", "screen_kernel"):
             # the longest captured launch is the list scan (the coarse step no longer uses this kernel)
             ti, ri, wi = hdr.index("gpu__time_duration.sum"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             ui, uw = units[ri], units[wi]
@@ -74,7 +75,9 @@ def main():
             tr = float(best[ri]) * scale[ui] + float(best[wi]) * scale[uw]
             json.dump({"dram_bytes_per_launch": tr, "dram_read": float(best[ri]) * scale[ui],
                        "dram_write": float(best[wi]) * scale[uw], "kernel_time": best[ti] + " " + units[ti],
-                       "source": rep.split("/")[-1]}, open("profiles/scan_traffic.json", "w"), indent=1)
+                       "source": rep.split("/")[-1]},
+                      open("profiles/screen_traffic.json" if kname == "screen_kernel" else "profiles/scan_traffic.json", "w"),
+                      indent=1)
 
 
 if __name__ == "__main__":
