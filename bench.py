@@ -507,7 +507,7 @@ def run_b200(a):
     # ---- byte accounting of the timed batches (untimed replay; stats come from the grouping kernel)
     if exch is not None:
         ix.attach_exchange(None)  # the replay is local: no collective needed for the byte counts
-    alg_rows = uniq_rows = items = 0
+    alg_rows = uniq_rows = items = rescored = 0
     scan_ctas = 0
     for s in range(a.steps):
         ix.search_async(q_all[a.warmup + s], a.nprobe, a.k, Dd[0], Id[0], stream)
@@ -515,6 +515,7 @@ def run_b200(a):
         alg_rows += ss.algorithmic_rows
         uniq_rows += ss.unique_rows
         items += ss.scan_items
+        rescored += ss.rescored_pairs
     t = ix.search_submit(q_all[0], a.nprobe, a.k, Dd[0], Id[0])
     ix.search_wait(t)
     ss = ix.last_search_stats()
@@ -579,6 +580,9 @@ def run_b200(a):
                      "traffic": profiled_traffic(mirror) if (headline and world == 1 and shard_count == 1) else None,
                      "peak_source": peak_src,
                      "streamed_bytes_per_launch": streamed_bytes,
+                     # pairs the screen admitted: each re-reads one fp32 row (4*ld bytes) for the exact distance
+                     "rescored_pairs_per_launch": rescored / a.steps,
+                     "rescore_bytes_per_launch": rescored / a.steps * 4 * a.dim,
                      "fp32_equivalent_gbs": uniq_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0,
                      "algorithmic_bytes_per_launch": alg_bytes, "unique_bytes_per_launch": uniq_bytes,
                      "reuse": alg_bytes / uniq_bytes if uniq_bytes else None,

@@ -61,7 +61,7 @@ class _Stats(C.Structure):
 class _SearchStats(C.Structure):
     _fields_ = [("algorithmic_rows", C.c_uint64), ("unique_rows", C.c_uint64), ("scan_items", C.c_uint64),
                 ("bytes_per_row", C.c_uint64), ("scan_ctas", C.c_uint64),
-                ("streamed_bytes_per_row", C.c_uint64)]
+                ("streamed_bytes_per_row", C.c_uint64), ("rescored_pairs", C.c_uint64)]
 
 
 # every symbol include/vdb_b200.h declares: name -> (restype, argtypes)

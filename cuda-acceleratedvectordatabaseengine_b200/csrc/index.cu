@@ -1369,16 +1369,19 @@ int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
     if (ix->last_slot < 0) return VDB_OK;
     SearchSlot& s = ix->slots[ix->last_slot];
     VDB_TRY(index_finish_slot(ix, s));
-    unsigned long long st[2] = {0, 0};
+    unsigned long long st[3] = {0, 0, 0};
     uint32_t tot[2] = {0, 0};
-    VDB_CUDA_TRY(cudaMemcpy(st, s.ws_scan.stats, 16, cudaMemcpyDeviceToHost));
+    VDB_CUDA_TRY(cudaMemcpy(st, s.ws_scan.stats, 24, cudaMemcpyDeviceToHost));
     VDB_CUDA_TRY(cudaMemcpy(tot, s.ws_scan.totals, 8, cudaMemcpyDeviceToHost));
     out->algorithmic_rows = st[0];
     out->unique_rows = st[1];
     out->scan_items = tot[0];
     out->scan_ctas = s.info.grid;
     // the bf16 screen streams the shadow row, |v|^2 and |v - bf16(v)|; ids and fp32 rows only for admitted pairs
-    if (s.info.mirror) out->streamed_bytes_per_row = 2ull * ix->ld + 8;
+    if (s.info.mirror) {
+        out->streamed_bytes_per_row = 2ull * ix->ld + 8;
+        out->rescored_pairs = st[2];
+    }
     return VDB_OK;
 }
 

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(1024) build_groups_kernel(ListTable lt, const 
     if (tid == 0) {
         wl.stats[0] = 0;
         wl.stats[1] = 0;
+        wl.stats[2] = 0;  // (row, query) pairs the screen kernel re-scored exactly
     }
     for (uint32_t q = tid; q < wl.nq; q += NT) wl.qthr[q] = KEY_INF;
     __syncthreads();
@@ -548,11 +549,10 @@ __device__ __forceinline__ void compact_pool(const ScanSmem& s, const ScanParams
 // over every row scanned so far by any CTA tightens it to what the final answer will be, so that later items
 // admit, keep and hand to the merge almost nothing.  (The partial results stay the source of truth for the
 // merge -- this list only feeds the bound, which is published only while its k ids are distinct.)
-__device__ __forceinline__ void contribute_global(const ScanSmem& s, const ScanParams& p, uint32_t j, uint32_t nc,
-                                                  uint32_t lane) {
-    float* d = s.pool_d + (size_t)j * p.P;
-    uint64_t* id = s.pool_i + (size_t)j * p.P;
-    const uint32_t q = s.sqidx[j], k = p.k;
+// d / id: P entries of shared memory whose first nc (<= k, sorted) are the contribution; the rest is scratch.
+__device__ __forceinline__ void contribute_global_at(float* d, uint64_t* id, uint32_t q, const ScanParams& p,
+                                                     uint32_t nc, uint32_t lane) {
+    const uint32_t k = p.k;
     if (!(d[0] <= key2f(__ldcg(&p.qthr[q])))) return;  // cannot improve the running top-k (warp-uniform)
     // try-lock: when another CTA is updating this query's list right now, skip -- the bound merely tightens a
     // little later, and no warp ever waits on another CTA
@@ -610,6 +610,10 @@ __device__ __forceinline__ void contribute_global(const ScanSmem& s, const ScanP
     __threadfence();
     __syncwarp();
     if (lane == 0) atomicExch(&p.glock[q], 0u);
+}
+__device__ __forceinline__ void contribute_global(const ScanSmem& s, const ScanParams& p, uint32_t j, uint32_t nc,
+                                                  uint32_t lane) {
+    contribute_global_at(s.pool_d + (size_t)j * p.P, s.pool_i + (size_t)j * p.P, s.sqidx[j], p, nc, lane);
 }
 
 // Sum V per-lane partials across the warp: log2(V) "halving" exchanges leave
@@ -1556,6 +1560,7 @@ int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t st
         mp.qimg = ws.qimg;
         mp.qconst = reinterpret_cast<const float4*>(ws.qconst);
         mp.nkb = pl.lt.ld / 64;
+        mp.rescored = ws.stats + 2;
         mp.qt = std::min<uint32_t>(screen::NQ, screen::POOL_ENTRIES / mp.sp.P);
         uint32_t S = 8;
         while (S > 3 && screen::smem_bytes(pl.lt.ld, S) > SMEM_BUDGET) --S;

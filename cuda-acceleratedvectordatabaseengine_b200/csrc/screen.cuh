@@ -49,6 +49,7 @@ struct Params {
     uint32_t S;            // ring stages
     uint32_t qt;           // queries per pass over an item = min(64, POOL_ENTRIES / P)
     uint32_t nkb;          // K blocks = ld / 64
+    unsigned long long* rescored;  // += (row, query) pairs re-scored exactly (statistics)
 };
 
 struct Smem {
@@ -359,6 +360,7 @@ __device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32
         // is sound -- every row is tested against a bound that holds before it is dropped.
         const uint32_t cold_rows = sp.k <= 16 ? (sp.k + 1) / 2 + 1 : 32u;  // per warp: ~2k per tile
         uint64_t coldq = 0, coldtaken = 0;  // queries this warp treated as cold / rows (this thread's) taken for them
+        bool want = false;                  // this thread's row was admitted for some query
         for (uint32_t j0 = 0; j0 < qcount; j0 += 4) {
             uint32_t col[4];
 #pragma unroll
@@ -388,9 +390,15 @@ __device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32
                     }
                     const uint32_t m = __ballot_sync(0xffffffffu, pass);
                     if (lane == 0) s.adm[j * 4 + warp] = m;
+                    want |= pass;
                 }
             }
         }
+        // the fp32 copy of an admitted row is on its way to L2 while the other queries are still being tested
+        if (want)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(page + (size_t)(r0 + tid) * sp.lt.ld * 4),
+                         "r"(sp.lt.ld * 4)
+                         : "memory");
         if (coldq != 0 && lane == 0) *s.redo = 1u;
         bar_consumers();
         const bool redo = *s.redo != 0u;  // some warp left rows out: the accumulator is needed again
@@ -427,37 +435,43 @@ __device__ __forceinline__ void consumers(const Params& p, const Smem& s, uint32
                         if (c + 1 == P) compact_pool(ss, sp, j, lane);  // keeps the best k, tightens thr[j]
                     }
                 };
-#pragma unroll 1
-                for (uint32_t w = 0; w < 4; ++w) {
-                    uint32_t m = w == 0 ? am.x : w == 1 ? am.y : w == 2 ? am.z : am.w;
-                    while (m) {  // two admitted rows at a time: their (HBM) row loads overlap
-                        const uint32_t La = (uint32_t)__ffs((int)m) - 1u;
-                        m &= m - 1u;
-                        const bool two = m != 0u;
-                        const uint32_t Lb = two ? (uint32_t)__ffs((int)m) - 1u : La;
-                        m &= m - 1u;  // (0 & anything = 0)
-                        const uint32_t ra = r0 + w * 32u + La, rb = r0 + w * 32u + Lb;  // page rows
-                        float ea, eb;
-                        if (l2) {
-                            ea = exact_l2_lane<NJ, true>(g4, ld4, ra, page_rows, lane, q);
-                            eb = exact_l2_lane<NJ, true>(g4, ld4, rb, page_rows, lane, q);
-                        } else {
-                            ea = exact_ip_lane<NJ>(g4, ld4, ra, lane, q);
-                            eb = exact_ip_lane<NJ>(g4, ld4, rb, lane, q);
-                        }
+                constexpr int RB = 2;  // admitted rows re-scored at a time: their row loads overlap (4 measured slower)
+                unsigned long long mlo = (unsigned long long)am.x | ((unsigned long long)am.y << 32);
+                unsigned long long mhi = (unsigned long long)am.z | ((unsigned long long)am.w << 32);
+                uint32_t nres = 0;
+                for (;;) {
+                    uint32_t rows[RB];
+                    int n = 0;
 #pragma unroll
-                        for (int step = 16; step >= 1; step >>= 1) {
-                            ea += __shfl_xor_sync(0xffffffffu, ea, step);
-                            eb += __shfl_xor_sync(0xffffffffu, eb, step);
+                    for (int t = 0; t < RB; ++t) {
+                        if (mlo) {
+                            rows[t] = r0 + (uint32_t)__ffsll((long long)mlo) - 1u;  // page row
+                            mlo &= mlo - 1ull;
+                            ++n;
+                        } else if (mhi) {
+                            rows[t] = r0 + 64u + (uint32_t)__ffsll((long long)mhi) - 1u;
+                            mhi &= mhi - 1ull;
+                            ++n;
+                        } else {
+                            rows[t] = t ? rows[0] : r0;
                         }
-                        if (!l2) {  // IP distance = -dot, kernels.cuh:59
-                            ea = -ea;
-                            eb = -eb;
-                        }
-                        push(ea, ra);
-                        if (two) push(eb, rb);
                     }
+                    if (n == 0) break;
+                    nres += (uint32_t)n;
+                    float e[RB];
+#pragma unroll
+                    for (int t = 0; t < RB; ++t)
+                        e[t] = l2 ? exact_l2_lane<NJ, true>(g4, ld4, rows[t], page_rows, lane, q)
+                                  : exact_ip_lane<NJ>(g4, ld4, rows[t], lane, q);
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1)
+#pragma unroll
+                        for (int t = 0; t < RB; ++t) e[t] += __shfl_xor_sync(0xffffffffu, e[t], step);
+#pragma unroll
+                    for (int t = 0; t < RB; ++t)
+                        if (t < n) push(l2 ? e[t] : -e[t], rows[t]);  // IP distance = -dot, kernels.cuh:59
                 }
+                if (lane == 0 && nres) atomicAdd(p.rescored, (unsigned long long)nres);
             }
         };
         phase_b();

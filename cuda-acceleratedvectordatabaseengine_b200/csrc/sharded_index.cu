@@ -622,6 +622,7 @@ int32_t composite_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
         out->scan_items += st.scan_items;
         out->bytes_per_row = st.bytes_per_row;
         out->streamed_bytes_per_row = st.streamed_bytes_per_row;
+        out->rescored_pairs += st.rescored_pairs;
         out->scan_ctas = st.scan_ctas;
     }
     return VDB_OK;

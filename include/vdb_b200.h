@@ -102,6 +102,8 @@ typedef struct {
     uint64_t scan_ctas;     /* persistent CTAs of the list-scan launch */
     uint64_t streamed_bytes_per_row; /* what the scan kernel streams per distinct row: bytes_per_row for the fp32
                                         scan; 2*row_stride + 8 when the bf16 screen ran (vdb_config.scan_mirror) */
+    uint64_t rescored_pairs; /* (row, query) pairs the bf16 screen admitted and re-scored exactly in fp32 (each one
+                                reads the row's fp32 copy: 4*row_stride more bytes); 0 for the fp32 scan */
 } vdb_search_stats;
 
 typedef struct vdb_index vdb_index;
