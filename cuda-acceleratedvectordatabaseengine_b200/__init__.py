@@ -207,7 +207,7 @@ class Config:
     devices: tuple = ()           # more than one entry: ONE process, one list shard per device (create_sharded)
     pipeline_depth: int = 0       # searches in flight (search_submit), 0 = 4
     reserve_sms: int = 0          # SMs a pipelined scan leaves to the neighbouring batches' small kernels, 0 = 8
-    scan_mirror: int = 0          # bf16 shadow of the lists for the tensor-core screen: 0 = auto, 1 = off, 2 = on
+    scan_mirror: int = 0          # shadow of the lists for the tensor-core screen: 0 = auto, 1 = off, 2 = bf16, 3 = int8
 
 
 @dataclass

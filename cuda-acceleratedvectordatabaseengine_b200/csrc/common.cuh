@@ -57,22 +57,29 @@ struct ListTable {
     uint32_t nlist;
     uint32_t page_rows;
     uint32_t ld;  // floats per row, multiple of 4
-    // bf16 shadow of every page (0 = none): byte offset, from the page's row block, of the page's rows rounded to
-    // bf16 and stored as the shared-memory image of [128 rows][64 elements] tensor-core operand tiles (128-byte
-    // swizzle), row tile major, then K block; [page_rows] fp32 |v - bf16(v)| sit behind the page's norms
+    // Low-precision shadow of every page for the tensor-core screen of the list scan (0 = none): byte offset, from
+    // the page's row block, of the page's rows rounded to bf16 (mirror_kind 1) or quantised to int8 with one scale
+    // per row (mirror_kind 2), stored as the shared-memory image of [128 rows][128 bytes] tensor-core operand tiles
+    // (128-byte swizzle), row tile major, then K block.  Behind the page's norms sit [page_rows] fp32
+    // |v - shadow(v)| and (int8) [page_rows] fp32 row scales.
     uint32_t mirror_off = 0;
+    uint32_t mirror_kind = 0;
 };
 
-constexpr uint32_t MIRROR_TILE_ROWS = 128;   // rows per operand tile of the bf16 shadow (UMMA M)
-constexpr uint32_t MIRROR_TILE_K = 64;       // bf16 elements per tile row = 128 bytes = one swizzle atom
-constexpr uint32_t MIRROR_TILE_BYTES = MIRROR_TILE_ROWS * MIRROR_TILE_K * 2;
+constexpr uint32_t MIRROR_NONE = 0, MIRROR_BF16 = 1, MIRROR_I8 = 2;
+constexpr uint32_t MIRROR_TILE_ROWS = 128;   // rows per operand tile of the shadow (UMMA M)
+constexpr uint32_t MIRROR_TILE_BYTES = MIRROR_TILE_ROWS * 128;  // a tile row is 128 bytes = one swizzle atom
+__host__ __device__ inline uint32_t mirror_elem_bytes(uint32_t kind) { return kind == MIRROR_I8 ? 1u : 2u; }
 
-// byte offset, inside a page's (or a query block's) bf16 shadow, of element e of row r: tile (r / 128, e / 64),
-// row r % 128 at 128 bytes per row, 16-byte chunks XOR-swizzled by the row's low three bits -- exactly what a
-// SWIZZLE_128B tensor map would leave in shared memory, so a plain bulk copy of a tile yields a UMMA operand
-__host__ __device__ inline uint32_t mirror_elem_off(uint32_t r, uint32_t e, uint32_t ld, uint32_t tile_rows = MIRROR_TILE_ROWS) {
-    const uint32_t rt = r / tile_rows, rr = r % tile_rows, kb = e >> 6, c = (e >> 3) & 7u, w = e & 7u;
-    return (rt * (ld >> 6) + kb) * (tile_rows * 128u) + rr * 128u + ((c ^ (rr & 7u)) << 4) + (w << 1);
+// byte offset, inside a page's (or a query block's) shadow, of element e of row r (elements of eb = 1 or 2 bytes):
+// tile (r / tile_rows, e / (128 / eb)), row r % tile_rows at 128 bytes per row, 16-byte chunks XOR-swizzled by the
+// row's low three bits -- exactly what a SWIZZLE_128B tensor map would leave in shared memory, so a plain bulk copy
+// of a tile yields a UMMA operand
+__host__ __device__ inline uint32_t mirror_elem_off(uint32_t r, uint32_t e, uint32_t ld, uint32_t eb,
+                                                    uint32_t tile_rows = MIRROR_TILE_ROWS) {
+    const uint32_t b = e * eb;  // byte position inside the row
+    const uint32_t rt = r / tile_rows, rr = r % tile_rows, kb = b >> 7, c = (b >> 4) & 7u, w = b & 15u;
+    return (rt * ((ld * eb) >> 7) + kb) * (tile_rows * 128u) + rr * 128u + ((c ^ (rr & 7u)) << 4) + w;
 }
 
 inline uint32_t next_pow2(uint32_t v) {

@@ -110,6 +110,7 @@ ListTable list_table(vdb_index* ix) {
     lt.page_rows = ix->page_rows;
     lt.ld = ix->ld;
     lt.mirror_off = ix->mirror_off;
+    lt.mirror_kind = ix->mirror_kind;
     return lt;
 }
 
@@ -725,18 +726,24 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     ix->ids_off = (uint64_t)pr * ix->ld * 4;
     // page = [pr][ld] fp32 rows | [pr] u64 ids | [pr] fp32 |row|^2 (the dot-form screen of the L2 scan)
     ix->page_bytes = (ix->ids_off + (uint64_t)pr * 12 + 255) / 256 * 256;
-    // ... | [pr] fp32 |row - bf16(row)| | the rows as bf16 tensor-core operand tiles (the scan's bf16 screen, scan.cu):
-    // +50 % HBM for a scan that streams half the bytes.  scan_mirror: 0 = auto (on where the screen kernel supports
-    // the shape), 1 = off, 2 = on (refused when unsupported); VDB_SCAN_MIRROR overrides (0 / 1).
+    // ... | [pr] fp32 |row - shadow(row)| | [pr] fp32 row scales | the rows once more in low precision, as tensor-core
+    // operand tiles: the scan's screen (screen.cuh) streams the shadow instead of the fp32 rows.  scan_mirror: 0 = auto
+    // (bf16 where the screen kernel supports the shape), 1 = off, 2 = bf16 (+50 % HBM, half the bytes per search),
+    // 3 = int8 with one scale per row (+25 % HBM, a quarter of the bytes); 2 / 3 are refused where unsupported.
+    // VDB_SCAN_MIRROR overrides: 0 = off, 1 = bf16, 2 = int8.
     {
         uint32_t want = cfg->scan_mirror;
-        if (const char* e = std::getenv("VDB_SCAN_MIRROR")) want = std::atoi(e) ? 2u : 1u;
+        if (const char* e = std::getenv("VDB_SCAN_MIRROR")) {
+            const int v = std::atoi(e);
+            want = v == 0 ? 1u : v == 2 ? 3u : 2u;
+        }
         const bool can = screen_supported(ix->ld, pr, cfg->metric);
-        VDB_REQUIRE(want <= 2, "scan_mirror must be 0 (auto), 1 (off) or 2 (on)");
-        VDB_REQUIRE(want != 2 || can, "scan_mirror: the bf16 screen needs a row stride of 128 * {1,2,4,6,8} floats and page_rows % 128 == 0");
+        VDB_REQUIRE(want <= 3, "scan_mirror must be 0 (auto), 1 (off), 2 (bf16) or 3 (int8)");
+        VDB_REQUIRE(want < 2 || can, "scan_mirror: the screen needs a row stride of 128 * {1,2,4,6,8} floats and page_rows % 128 == 0");
         if (can && want != 1) {
-            ix->mirror_off = (uint32_t)((ix->ids_off + (uint64_t)pr * 16 + 1023) / 1024 * 1024);
-            ix->page_bytes = ((uint64_t)ix->mirror_off + (uint64_t)pr * ix->ld * 2 + 255) / 256 * 256;
+            ix->mirror_kind = want == 3 ? MIRROR_I8 : MIRROR_BF16;
+            ix->mirror_off = (uint32_t)((ix->ids_off + (uint64_t)pr * 20 + 1023) / 1024 * 1024);
+            ix->page_bytes = ((uint64_t)ix->mirror_off + (uint64_t)pr * ix->ld * mirror_elem_bytes(ix->mirror_kind) + 255) / 256 * 256;
         }
     }
     ix->pages_per_slab = (uint32_t)std::max<uint64_t>(1, SLAB_BYTES / ix->page_bytes);
@@ -939,7 +946,7 @@ static int32_t add_impl(vdb_index* ix, const float* vectors, const uint64_t* ids
         VDB_TRY(index_upload_list_tables(ix));  // uploads h_rows (= old counts) and the grown chains
         VDB_TRY(launch_scatter_rows(x, ix->ld, dids, ix->total_vectors + lo, m, asg, ix->d_rows.p, ix->fill_buf.p,
                                     ix->d_page_off.p, ix->d_page_vec.p, ix->d_page_ids.p, ix->page_rows, ix->ld,
-                                    ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->mirror_off, ix->stream));
+                                    ix->nlist, ix->cfg.shard_rank, ix->d_owner.p, ix->mirror_off, ix->mirror_kind, ix->stream));
         ix->h_rows = new_rows;
         VDB_CUDA_TRY(cudaMemcpyAsync(ix->d_rows.p, ix->h_rows.data(), ix->nlist * 4, cudaMemcpyHostToDevice,
                                      ix->stream));
@@ -1287,7 +1294,7 @@ int32_t vdb_index_append_list(vdb_index* ix, uint32_t list, const float* vectors
                                      ix->stream));
         VDB_TRY(launch_page_norms(reinterpret_cast<const float*>(page), ix->ld,
                                   reinterpret_cast<float*>(page + ix->ids_off + (size_t)ix->page_rows * 8), r,
-                                  (uint32_t)take, ix->mirror_off, ix->page_rows, ix->stream));
+                                  (uint32_t)take, ix->mirror_off, ix->mirror_kind, ix->page_rows, ix->stream));
         done += take;
     }
     VDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
@@ -1379,7 +1386,7 @@ int32_t vdb_index_last_search_stats(vdb_index* ix, vdb_search_stats* out) {
     out->scan_ctas = s.info.grid;
     // the bf16 screen streams the shadow row, |v|^2 and |v - bf16(v)|; ids and fp32 rows only for admitted pairs
     if (s.info.mirror) {
-        out->streamed_bytes_per_row = 2ull * ix->ld + 8;
+        out->streamed_bytes_per_row = ix->mirror_kind == MIRROR_I8 ? 1ull * ix->ld + 12 : 2ull * ix->ld + 8;
         out->rescored_pairs = st[2];
     }
     return VDB_OK;

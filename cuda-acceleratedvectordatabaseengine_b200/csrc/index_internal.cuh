@@ -125,7 +125,7 @@ struct vdb_index {
     vdb_config cfg{};
     uint32_t dim = 0, ld = 0, nlist = 0, page_rows = 0;
     uint64_t page_bytes = 0, ids_off = 0;
-    uint32_t mirror_off = 0;  // bf16 shadow of every page (ListTable::mirror_off), 0 = none
+    uint32_t mirror_off = 0, mirror_kind = 0;  // low-precision shadow of every page (ListTable::mirror_off), 0 = none
     int device = 0;
     cudaStream_t stream = nullptr;  // train / add / bookkeeping
     bool trained = false;

@@ -924,23 +924,54 @@ __global__ void hist_kernel(const uint32_t* __restrict__ assign, uint64_t n, uin
     if (!owner || owner[l] == shard_rank) atomicAdd(&hist[l], 1u);
 }
 
-// bf16 shadow of one float4 of a page row (ListTable::mirror_off): store the four rounded values at their place in
-// the operand-tile image and return this lane's share of |v - bf16(v)|^2 (the differences are exact in fp32)
-__device__ __forceinline__ float mirror_store4(uint8_t* mirror, uint32_t r, uint32_t c4, uint32_t ld, const float4 t) {
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
-    uint2 bits;
-    bits.x = *reinterpret_cast<const uint32_t*>(&lo);
-    bits.y = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(mirror + mirror_elem_off(r, c4 * 4u, ld)) = bits;
-    const float dx = t.x - __low2float(lo), dy = t.y - __high2float(lo);
-    const float dz = t.z - __low2float(hi), dw = t.w - __high2float(hi);
-    return fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
-}
-// |v - bf16(v)| from the lanes' partial sums, rounded up (the sum's own rounding, < 2^-14 relative, included)
-__device__ __forceinline__ float mirror_err_norm(float part) {
+// Shadow of one page row for the tensor-core screen of the list scan (ListTable::mirror_off / mirror_kind), written
+// by the warp that just stored the fp32 row (src = that row, 16-byte aligned, ld floats): the values rounded to bf16,
+// or quantised to int8 with the row's own scale (max |v_i| / 127), go to their place in the operand-tile image;
+// err_out[0] = |v - shadow(v)| rounded up, err_out[page_rows] = the row scale (int8).  The differences are exact in
+// fp32 (bf16) or one fused rounding each (int8: v_i - scale * n_i), the sum's own rounding (< 2^-14 relative) is
+// inside the factor 1.0002.
+__device__ __forceinline__ void mirror_write_row(uint8_t* mirror, uint32_t kind, uint32_t r, uint32_t ld,
+                                                 const float4* __restrict__ src, float* err_out, uint32_t page_rows,
+                                                 uint32_t lane) {
+    float err = 0.f;
+    if (kind == MIRROR_BF16) {
+        for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+            const float4 t = src[c];
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+            uint2 bits;
+            bits.x = *reinterpret_cast<const uint32_t*>(&lo);
+            bits.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(mirror + mirror_elem_off(r, c * 4u, ld, 2)) = bits;
+            const float dx = t.x - __low2float(lo), dy = t.y - __high2float(lo);
+            const float dz = t.z - __low2float(hi), dw = t.w - __high2float(hi);
+            err += fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+        }
+    } else {
+        float mx = 0.f;
+        for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+            const float4 t = src[c];
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+        }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    return __fmul_ru(__fsqrt_ru(part), 1.0002f);
+        for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float scale = mx * (1.f / 127.f);
+        const float inv = scale > 0.f ? 1.f / scale : 0.f;
+        for (uint32_t c = lane; c < (ld >> 2); c += 32) {
+            const float4 t = src[c];
+            const float nx = fminf(fmaxf(rintf(t.x * inv), -127.f), 127.f), ny = fminf(fmaxf(rintf(t.y * inv), -127.f), 127.f);
+            const float nz = fminf(fmaxf(rintf(t.z * inv), -127.f), 127.f), nw = fminf(fmaxf(rintf(t.w * inv), -127.f), 127.f);
+            const uint32_t bits = ((uint32_t)(int)nx & 0xffu) | (((uint32_t)(int)ny & 0xffu) << 8) |
+                                  (((uint32_t)(int)nz & 0xffu) << 16) | (((uint32_t)(int)nw & 0xffu) << 24);
+            *reinterpret_cast<uint32_t*>(mirror + mirror_elem_off(r, c * 4u, ld, 1)) = bits;
+            const float dx = fmaf(-scale, nx, t.x), dy = fmaf(-scale, ny, t.y);
+            const float dz = fmaf(-scale, nz, t.z), dw = fmaf(-scale, nw, t.w);
+            err += fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+        }
+        if (lane == 0) err_out[page_rows] = scale;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+    if (lane == 0) err_out[0] = __fmul_ru(__fsqrt_ru(err), 1.0002f);
 }
 
 // one warp per new row: claim the next slot of its list, copy row + id into the page
@@ -953,7 +984,8 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
                                                            const uint64_t* __restrict__ page_vec,
                                                            const uint64_t* __restrict__ page_ids, uint32_t page_rows,
                                                            uint32_t ld, uint32_t nlist, uint32_t shard_rank,
-                                                           const uint8_t* __restrict__ owner, uint32_t mirror_off) {
+                                                           const uint8_t* __restrict__ owner, uint32_t mirror_off,
+                                                           uint32_t mirror_kind) {
     const uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (v >= n) return;
@@ -967,8 +999,6 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
     float4* dst = reinterpret_cast<float4*>(page_vec[pg]) + (size_t)r * (ld >> 2);
     const float4* src = reinterpret_cast<const float4*>(x + v * ldx);
     float nrm = 0.f;  // |row|^2 for the scan's dot-form screen (any fixed order: its rounding is inside the slack)
-    float err = 0.f;
-    uint8_t* mirror = reinterpret_cast<uint8_t*>(page_vec[pg]) + mirror_off;
     for (uint32_t c = lane; c < (ld >> 2); c += 32) {
         const float4 t = src[c];
         dst[c] = t;
@@ -976,45 +1006,43 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
         nrm = fmaf(t.y, t.y, nrm);
         nrm = fmaf(t.z, t.z, nrm);
         nrm = fmaf(t.w, t.w, nrm);
-        if (mirror_off) err += mirror_store4(mirror, r, c, ld, t);
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-    if (mirror_off) err = mirror_err_norm(err);
+    uint64_t* idp = reinterpret_cast<uint64_t*>(page_ids[pg]);
+    float* nb = reinterpret_cast<float*>(idp + page_rows);  // the norms follow the page's id block
     if (lane == 0) {
-        uint64_t* idp = reinterpret_cast<uint64_t*>(page_ids[pg]);
         idp[r] = ids ? ids[v] : id_base + v;
-        float* nb = reinterpret_cast<float*>(idp + page_rows);
-        nb[r] = nrm;  // the norms follow the page's id block
-        if (mirror_off) nb[page_rows + r] = err;  // then |v - bf16(v)|
+        nb[r] = nrm;
     }
+    if (mirror_off)  // then |v - shadow(v)| and the row scales
+        mirror_write_row(reinterpret_cast<uint8_t*>(page_vec[pg]) + mirror_off, mirror_kind, r, ld, src,
+                         nb + page_rows + r, page_rows, lane);
 }
 
 // |row|^2 of rows [r0, r0 + count) of one page (rows copied in without the scatter kernel: vdb_index_append_list)
-// (+ the bf16 shadow and its error norms when the index keeps one: mirror_off != 0, page_rows = rows per page)
+// (+ the low-precision shadow, its error norms and row scales when the index keeps one: mirror_off != 0)
 __global__ void __launch_bounds__(256) page_norms_kernel(const float* __restrict__ rows, uint32_t ld,
                                                          float* __restrict__ norms, uint32_t r0, uint32_t count,
-                                                         uint32_t mirror_off, uint32_t page_rows) {
+                                                         uint32_t mirror_off, uint32_t mirror_kind,
+                                                         uint32_t page_rows) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= count) return;
     const float4* src = reinterpret_cast<const float4*>(rows + (size_t)(r0 + w) * ld);
-    uint8_t* mirror = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(rows)) + mirror_off;
-    float nrm = 0.f, err = 0.f;
+    float nrm = 0.f;
     for (uint32_t c = lane; c < (ld >> 2); c += 32) {
         const float4 t = src[c];
         nrm = fmaf(t.x, t.x, nrm);
         nrm = fmaf(t.y, t.y, nrm);
         nrm = fmaf(t.z, t.z, nrm);
         nrm = fmaf(t.w, t.w, nrm);
-        if (mirror_off) err += mirror_store4(mirror, r0 + w, c, ld, t);
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-    if (mirror_off) err = mirror_err_norm(err);
-    if (lane == 0) {
-        norms[r0 + w] = nrm;
-        if (mirror_off) norms[page_rows + r0 + w] = err;
-    }
+    if (lane == 0) norms[r0 + w] = nrm;
+    if (mirror_off)
+        mirror_write_row(const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(rows)) + mirror_off, mirror_kind, r0 + w,
+                         ld, src, norms + page_rows + r0 + w, page_rows, lane);
 }
 
 // [n][dim] (any stride) -> [n][ld] zero-padded
@@ -1283,20 +1311,21 @@ int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, u
                             const uint32_t* assign, const uint32_t* old_rows, uint32_t* fill,
                             const uint32_t* page_off, const uint64_t* page_vec, const uint64_t* page_ids,
                             uint32_t page_rows, uint32_t ld, uint32_t nlist, uint32_t shard_rank,
-                            const uint8_t* owner, uint32_t mirror_off, cudaStream_t stream) {
+                            const uint8_t* owner, uint32_t mirror_off, uint32_t mirror_kind, cudaStream_t stream) {
     if (n == 0) return VDB_OK;
     const uint64_t blocks = (n * 32 + 255) / 256;
     scatter_rows_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(x, ldx, ids, id_base, n, assign, old_rows, fill,
                                                               page_off, page_vec, page_ids, page_rows, ld, nlist,
-                                                              shard_rank, owner, mirror_off);
+                                                              shard_rank, owner, mirror_off, mirror_kind);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
 }
 
 int32_t launch_page_norms(const float* rows, uint32_t ld, float* norms, uint32_t r0, uint32_t count,
-                          uint32_t mirror_off, uint32_t page_rows, cudaStream_t stream) {
+                          uint32_t mirror_off, uint32_t mirror_kind, uint32_t page_rows, cudaStream_t stream) {
     if (count == 0) return VDB_OK;
-    page_norms_kernel<<<(count * 32 + 255) / 256, 256, 0, stream>>>(rows, ld, norms, r0, count, mirror_off, page_rows);
+    page_norms_kernel<<<(count * 32 + 255) / 256, 256, 0, stream>>>(rows, ld, norms, r0, count, mirror_off, mirror_kind,
+                                                                    page_rows);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
 }

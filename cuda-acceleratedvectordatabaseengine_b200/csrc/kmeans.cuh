@@ -93,9 +93,9 @@ int32_t launch_scatter_rows(const float* x, uint32_t ldx, const uint64_t* ids, u
                             const uint32_t* assign, const uint32_t* old_rows, uint32_t* fill,
                             const uint32_t* page_off, const uint64_t* page_vec, const uint64_t* page_ids,
                             uint32_t page_rows, uint32_t ld, uint32_t nlist, uint32_t shard_rank,
-                            const uint8_t* owner, uint32_t mirror_off, cudaStream_t stream);
+                            const uint8_t* owner, uint32_t mirror_off, uint32_t mirror_kind, cudaStream_t stream);
 int32_t launch_page_norms(const float* rows, uint32_t ld, float* norms, uint32_t r0, uint32_t count,
-                          uint32_t mirror_off, uint32_t page_rows, cudaStream_t stream);
+                          uint32_t mirror_off, uint32_t mirror_kind, uint32_t page_rows, cudaStream_t stream);
 int32_t launch_pad_rows(const float* src, uint32_t lds, uint32_t dim, float* dst, uint32_t ld, uint64_t n,
                         cudaStream_t stream);
 

@@ -1339,19 +1339,29 @@ int32_t launch_scan(const ScanParams& sp, uint32_t grid, uint32_t smem, cudaStre
     return VDB_OK;
 }
 
-template <int NJ>
+template <int NJ, bool I8>
 int32_t launch_screen(const screen::Params& sp, uint32_t grid, uint32_t smem, cudaStream_t stream) {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        VDB_CUDA_TRY(cudaFuncSetAttribute(screen::screen_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VDB_CUDA_TRY(cudaFuncSetAttribute(screen::screen_kernel<NJ, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)SMEM_BUDGET));
         configured[dev] = true;
     }
-    screen::screen_kernel<NJ><<<grid, screen::THREADS, smem, stream>>>(sp);
+    screen::screen_kernel<NJ, I8><<<grid, screen::THREADS, smem, stream>>>(sp);
     VDB_CUDA_TRY(cudaGetLastError());
     return VDB_OK;
+}
+template <bool I8>
+int32_t launch_screen_width(const screen::Params& mp, uint32_t ld, uint32_t grid, uint32_t smem, cudaStream_t stream) {
+    switch (ld) {
+        case 128: return launch_screen<1, I8>(mp, grid, smem, stream);
+        case 256: return launch_screen<2, I8>(mp, grid, smem, stream);
+        case 512: return launch_screen<4, I8>(mp, grid, smem, stream);
+        case 768: return launch_screen<6, I8>(mp, grid, smem, stream);
+        default: return launch_screen<8, I8>(mp, grid, smem, stream);
+    }
 }
 
 // pool entries per query of the screen kernel: room for the global-bound merge (2k) and for a useful number of
@@ -1415,7 +1425,7 @@ int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots
     }
     if (!qconst) {  // bf16 image of a batch's queries for the screen kernel: 64 slots at the widest supported row
         VDB_CUDA_TRY(cudaMalloc(&qimg, (size_t)screen::NQ * 1024 * 2));
-        VDB_CUDA_TRY(cudaMalloc(&qconst, (size_t)screen::NQ * 16));
+        VDB_CUDA_TRY(cudaMalloc(&qconst, (size_t)screen::NQ * 32));
     }
     if (!totals) {
         VDB_CUDA_TRY(cudaMalloc(&totals, 4 * 4));
@@ -1423,7 +1433,7 @@ int32_t ScanWorkspace::reserve(uint32_t nlists, uint32_t npairs, uint64_t nslots
         VDB_CUDA_TRY(cudaMemset(stats, 0, 4 * 8));
     }
     bytes = (uint64_t)cap_lists * 16 + (uint64_t)cap_pairs * 8 + cap_slots * sizeof(ScanItem) + cap_part * 12 + 48 +
-            (uint64_t)screen::NQ * (1024 * 2 + 16);
+            (uint64_t)screen::NQ * (1024 * 2 + 32);
     return VDB_OK;
 }
 
@@ -1503,8 +1513,8 @@ int32_t scan_enqueue_groups(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t 
     VDB_CUDA_TRY(cudaMemsetAsync(ws.gtop_i, 0xff, (size_t)pl.nq * pl.k * 8, stream));
     VDB_CUDA_TRY(cudaMemsetAsync(ws.glock, 0, (size_t)pl.nq * 4, stream));
     if (pl.mirror) {
-        screen::query_image_kernel<<<screen::NQ * 32 / 256, 256, 0, stream>>>(pl.queries, pl.nq, lt.ld, ws.qimg,
-                                                                              reinterpret_cast<float4*>(ws.qconst));
+        screen::query_image_kernel<<<screen::NQ * 32 / 256, 256, 0, stream>>>(pl.queries, pl.nq, lt.ld, lt.mirror_kind,
+                                                                              ws.qimg, reinterpret_cast<float4*>(ws.qconst));
         VDB_CUDA_TRY(cudaGetLastError());
     }
     if (lt.nlist <= 8192) {
@@ -1559,20 +1569,16 @@ int32_t scan_enqueue_scan(const ScanPlan& pl, ScanWorkspace& ws, cudaStream_t st
         mp.sp.P = screen_pool(pl.k);
         mp.qimg = ws.qimg;
         mp.qconst = reinterpret_cast<const float4*>(ws.qconst);
-        mp.nkb = pl.lt.ld / 64;
+        const bool i8 = pl.lt.mirror_kind == MIRROR_I8;
+        mp.nkb = pl.lt.ld * mirror_elem_bytes(pl.lt.mirror_kind) / 128;
         mp.rescored = ws.stats + 2;
         mp.qt = std::min<uint32_t>(screen::NQ, screen::POOL_ENTRIES / mp.sp.P);
         uint32_t S = 8;
         while (S > 3 && screen::smem_bytes(pl.lt.ld, S) > SMEM_BUDGET) --S;
         mp.S = S;
         const uint32_t msmem = screen::smem_bytes(pl.lt.ld, S);
-        switch (pl.lt.ld) {
-            case 128: return launch_screen<1>(mp, grid, msmem, stream);
-            case 256: return launch_screen<2>(mp, grid, msmem, stream);
-            case 512: return launch_screen<4>(mp, grid, msmem, stream);
-            case 768: return launch_screen<6>(mp, grid, msmem, stream);
-            default: return launch_screen<8>(mp, grid, msmem, stream);
-        }
+        return i8 ? launch_screen_width<true>(mp, pl.lt.ld, grid, msmem, stream)
+                  : launch_screen_width<false>(mp, pl.lt.ld, grid, msmem, stream);
     }
     switch (pl.info.NJ) {
         case 1: VDB_TRY(launch_scan<1>(sp, grid, smem, stream)); break;

@@ -75,9 +75,11 @@ typedef struct {
     uint32_t pipeline_depth; /* searches in flight (vdb_index_search_submit), 0 = 4, at most 8 */
     uint32_t reserve_sms;    /* SMs a pipelined list scan leaves to the coarse / merge kernels of the neighbouring
                                 batches, 0 = 8, 0xffffffff = none */
-    uint32_t scan_mirror;    /* bf16 shadow of the inverted lists for the tensor-core screen of the list scan (+50 % HBM,
-                                half the bytes streamed per search; results unchanged): 0 = auto (on where supported:
-                                row stride 128 * {1,2,4,6,8} floats), 1 = off, 2 = on (refused where unsupported) */
+    uint32_t scan_mirror;    /* low-precision shadow of the inverted lists for the tensor-core screen of the list scan
+                                (results unchanged: admitted pairs are re-scored in fp32): 0 = auto (bf16 where
+                                supported: row stride 128 * {1,2,4,6,8} floats), 1 = off, 2 = bf16 (+50 % HBM, half the
+                                bytes streamed per search), 3 = int8 with a scale per row (+25 % HBM, a quarter of the
+                                bytes); 2 and 3 are refused where unsupported */
     uint32_t reserved[2];
 } vdb_config;
 
@@ -101,8 +103,9 @@ typedef struct {
     uint64_t bytes_per_row; /* 4*dim + 8 */
     uint64_t scan_ctas;     /* persistent CTAs of the list-scan launch */
     uint64_t streamed_bytes_per_row; /* what the scan kernel streams per distinct row: bytes_per_row for the fp32
-                                        scan; 2*row_stride + 8 when the bf16 screen ran (vdb_config.scan_mirror) */
-    uint64_t rescored_pairs; /* (row, query) pairs the bf16 screen admitted and re-scored exactly in fp32 (each one
+                                        scan; 2*row_stride + 8 (bf16) or row_stride + 12 (int8) when the screen
+                                        ran (vdb_config.scan_mirror) */
+    uint64_t rescored_pairs; /* (row, query) pairs the screen admitted and re-scored exactly in fp32 (each one
                                 reads the row's fp32 copy: 4*row_stride more bytes); 0 for the fp32 scan */
 } vdb_search_stats;
 

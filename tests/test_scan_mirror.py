@@ -1,6 +1,7 @@
-"""The bf16 tensor-core screen of the list scan (csrc/screen.cuh): an index that keeps a bf16 shadow of its pages
-streams half the bytes, bounds every (row, query) distance from below with the tensor-core dot product of the rounded
-operands and re-scores only the admitted pairs -- with the fp32 scan's own arithmetic.  The screen may only ever admit
+"""The tensor-core screen of the list scan (csrc/screen.cuh): an index that keeps a low-precision shadow of its pages
+(bf16, or int8 with a scale per row) streams a half / a quarter of the bytes, bounds every (row, query) distance from
+below with the tensor-core dot product of the shadow operands and re-scores only the admitted pairs -- with the fp32
+scan's own arithmetic.  The screen may only ever admit
 MORE than the exact test would, so results must be BIT-IDENTICAL to the plain fp32 scan (VDB_SCAN_EXACT=1) and agree
 with the oracle, for both metrics, every supported row width, ragged pages, tiny and huge k, and where the bound is
 tight (large norms, tiny distances) or useless (huge offsets: everything is re-scored)."""
@@ -20,7 +21,7 @@ pytestmark = pytest.mark.gpu
 def build(dim, nlist, metric, cent, db, mirror, chunks=2):
     old = {k_: os.environ.get(k_) for k_ in ("VDB_SCAN_EXACT", "VDB_SCAN_MIRROR")}
     os.environ["VDB_SCAN_EXACT"] = "0" if mirror else "1"
-    os.environ["VDB_SCAN_MIRROR"] = "1" if mirror else "0"
+    os.environ["VDB_SCAN_MIRROR"] = str(int(mirror))  # 0 = none (and the fp32 scan), 1 = bf16, 2 = int8
     try:
         ix = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist, metric=metric))
     finally:
@@ -58,18 +59,23 @@ CASES = {
 }
 
 
+BF16, I8 = 1, 2
+
+
+@pytest.mark.parametrize("kind", [BF16, I8])
 @pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_mirror_scan_is_bit_identical_to_the_fp32_scan_and_matches_the_oracle(name, metric):
+def test_mirror_scan_is_bit_identical_to_the_fp32_scan_and_matches_the_oracle(name, metric, kind):
     dim, nlist, n, nq, nprobe, k, gen = CASES[name]
     x = np.ascontiguousarray(gen(n + nq, dim), np.float32)
     db, q = x[:n], x[n:]
     cent = db[:: n // nlist][:nlist].copy()
-    a = build(dim, nlist, metric, cent, db, mirror=True, chunks=3)
-    b = build(dim, nlist, metric, cent, db, mirror=False)
+    a = build(dim, nlist, metric, cent, db, mirror=kind, chunks=3)
+    b = build(dim, nlist, metric, cent, db, mirror=0)
     for np_, k_ in ((nprobe, k), (nlist, k), (1, 3)):
         Da, Ia = a.search(q, np_, k_)
-        assert a.last_search_stats().streamed_bytes_per_row == 2 * dim + 8  # the screen kernel really ran
+        # the screen kernel really ran
+        assert a.last_search_stats().streamed_bytes_per_row == (2 * dim + 8 if kind == BF16 else dim + 12)
         Db, Ib = b.search(q, np_, k_)
         assert b.last_search_stats().streamed_bytes_per_row == 4 * dim + 8
         assert np.array_equal(Da, Db) and np.array_equal(Ia, Ib), f"{name}: the screen changed the result (nprobe {np_})"
@@ -87,13 +93,14 @@ def test_mirror_scan_is_bit_identical_to_the_fp32_scan_and_matches_the_oracle(na
         check_search(Da, Ia, Dr, Ir)
 
 
-def test_batches_wider_than_the_screen_fall_back_and_chunked_batches_agree():
+@pytest.mark.parametrize("kind", [BF16, I8])
+def test_batches_wider_than_the_screen_fall_back_and_chunked_batches_agree(kind):
     dim, nlist, n = 128, 32, 30000
     x = O.gaussian(21, n + 200, dim)
     db, q = x[:n], x[n:]
     cent = db[:nlist].copy()
-    a = build(dim, nlist, O.METRIC_L2, cent, db, mirror=True)
-    b = build(dim, nlist, O.METRIC_L2, cent, db, mirror=False)
+    a = build(dim, nlist, O.METRIC_L2, cent, db, mirror=kind)
+    b = build(dim, nlist, O.METRIC_L2, cent, db, mirror=0)
     Da, Ia = a.search(q, 8, 10)          # 200 queries: the fp32 scan kernel
     Db, Ib = b.search(q, 8, 10)
     assert np.array_equal(Da, Db) and np.array_equal(Ia, Ib)
@@ -102,7 +109,8 @@ def test_batches_wider_than_the_screen_fall_back_and_chunked_batches_agree():
         assert np.array_equal(D, Db[lo:lo + 64]) and np.array_equal(I, Ib[lo:lo + 64])
 
 
-def test_loaded_epoch_gets_its_shadow(tmp_path):
+@pytest.mark.parametrize("kind", [BF16, I8])
+def test_loaded_epoch_gets_its_shadow(tmp_path, kind):
     """rows that arrive through vdb_index_append_list (epoch load) get norms, error norms and the bf16 shadow from
     page_norms_kernel, not the scatter kernel"""
     storage = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200.storage")
@@ -110,10 +118,10 @@ def test_loaded_epoch_gets_its_shadow(tmp_path):
     x = O.gaussian(31, n + 12, dim)
     db, q = x[:n], x[n:]
     cent = db[:nlist].copy()
-    src = build(dim, nlist, O.METRIC_L2, cent, db, mirror=False)
+    src = build(dim, nlist, O.METRIC_L2, cent, db, mirror=0)
     d = os.path.join(tmp_path, "ep")
     storage.save_epoch(src, d)
-    os.environ["VDB_SCAN_MIRROR"] = "1"
+    os.environ["VDB_SCAN_MIRROR"] = str(kind)
     try:
         scr = pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist))
     finally:
@@ -130,8 +138,9 @@ def test_loaded_epoch_gets_its_shadow(tmp_path):
 
 
 def test_unsupported_shapes_refuse_an_explicit_shadow_and_auto_skips_it():
-    with pytest.raises(Exception):
-        pkg.IVFFlatIndex(pkg.Config(dimension=100, nlist=4, scan_mirror=2))
+    for want in (2, 3):
+        with pytest.raises(Exception):
+            pkg.IVFFlatIndex(pkg.Config(dimension=100, nlist=4, scan_mirror=want))
     ix = pkg.IVFFlatIndex(pkg.Config(dimension=100, nlist=4))  # auto: no shadow, fp32 scan
     x = O.gaussian(41, 3000, 100)
     ix.centroids = x[:4].copy()

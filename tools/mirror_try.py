@@ -13,9 +13,12 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 pkg = importlib.import_module("cuda-acceleratedvectordatabaseengine_b200")
 
 
+KIND = int(os.environ.get("MIRROR_KIND", "1"))  # 1 = bf16, 2 = int8
+
+
 def make(dim, nlist, metric, mirror):
     os.environ["VDB_SCAN_EXACT"] = "0" if mirror else "1"
-    os.environ["VDB_SCAN_MIRROR"] = "1" if mirror else "0"
+    os.environ["VDB_SCAN_MIRROR"] = str(KIND) if mirror else "0"
     return pkg.IVFFlatIndex(pkg.Config(dimension=dim, nlist=nlist, metric=metric))
 
 
