@@ -728,7 +728,7 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
     ix->page_bytes = (ix->ids_off + (uint64_t)pr * 12 + 255) / 256 * 256;
     // ... | [pr] fp32 |row - shadow(row)| | [pr] fp32 row scales | the rows once more in low precision, as tensor-core
     // operand tiles: the scan's screen (screen.cuh) streams the shadow instead of the fp32 rows.  scan_mirror: 0 = auto
-    // (bf16 where the screen kernel supports the shape), 1 = off, 2 = bf16 (+50 % HBM, half the bytes per search),
+    // (int8 where the screen kernel supports the shape), 1 = off, 2 = bf16 (+50 % HBM, half the bytes per search),
     // 3 = int8 with one scale per row (+25 % HBM, a quarter of the bytes); 2 / 3 are refused where unsupported.
     // VDB_SCAN_MIRROR overrides: 0 = off, 1 = bf16, 2 = int8.
     {
@@ -741,7 +741,7 @@ int32_t vdb_index_create(const vdb_config* cfg, vdb_index** out) {
         VDB_REQUIRE(want <= 3, "scan_mirror must be 0 (auto), 1 (off), 2 (bf16) or 3 (int8)");
         VDB_REQUIRE(want < 2 || can, "scan_mirror: the screen needs a row stride of 128 * {1,2,4,6,8} floats and page_rows % 128 == 0");
         if (can && want != 1) {
-            ix->mirror_kind = want == 3 ? MIRROR_I8 : MIRROR_BF16;
+            ix->mirror_kind = want == 2 ? MIRROR_BF16 : MIRROR_I8;  // auto: int8 (less memory, fewer bytes per search)
             ix->mirror_off = (uint32_t)((ix->ids_off + (uint64_t)pr * 20 + 1023) / 1024 * 1024);
             ix->page_bytes = ((uint64_t)ix->mirror_off + (uint64_t)pr * ix->ld * mirror_elem_bytes(ix->mirror_kind) + 255) / 256 * 256;
         }

@@ -76,7 +76,7 @@ typedef struct {
     uint32_t reserve_sms;    /* SMs a pipelined list scan leaves to the coarse / merge kernels of the neighbouring
                                 batches, 0 = 8, 0xffffffff = none */
     uint32_t scan_mirror;    /* low-precision shadow of the inverted lists for the tensor-core screen of the list scan
-                                (results unchanged: admitted pairs are re-scored in fp32): 0 = auto (bf16 where
+                                (results unchanged: admitted pairs are re-scored in fp32): 0 = auto (int8 where
                                 supported: row stride 128 * {1,2,4,6,8} floats), 1 = off, 2 = bf16 (+50 % HBM, half the
                                 bytes streamed per search), 3 = int8 with a scale per row (+25 % HBM, a quarter of the
                                 bytes); 2 and 3 are refused where unsupported */
