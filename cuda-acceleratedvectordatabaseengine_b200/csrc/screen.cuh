@@ -1,24 +1,29 @@
-// The bf16 tensor-core screen of the inverted-list scan (included by scan.cu, inside its unnamed namespace).
+// The tensor-core screen of the inverted-list scan (included by scan.cu, inside its unnamed namespace).
 //
 // The list scan is HBM-bound: every probed fp32 row (3 KB at 768-D) is streamed once per batch.  An index that
-// keeps a bf16 shadow of its pages (ListTable::mirror_off: the rows rounded to bf16, stored as ready-made
-// 128-byte-swizzled [128 rows][64 elements] operand tiles, plus |v - bf16(v)| per row) lets the scan stream HALF
-// the bytes: this kernel brings the shadow tiles in with 1-D bulk TMA copies, multiplies them on the tensor cores
-// (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM) against the bf16 image of the WHOLE query batch (<= 64
-// queries, resident in shared memory for the kernel's lifetime, UMMA N = 64), and turns every (row, query) dot
-// product into a LOWER BOUND of the exact distance:
+// keeps a low-precision shadow of its pages (ListTable::mirror_off / mirror_kind: the rows rounded to bf16, or
+// quantised to int8 with one scale per row, stored as ready-made 128-byte-swizzled [128 rows][128 bytes] operand
+// tiles, plus |v - shadow(v)| and the scale per row) lets the scan stream a HALF / a QUARTER of the bytes: this kernel
+// brings the shadow tiles in with 1-D bulk TMA copies, multiplies them on the tensor cores (tcgen05.mma kind::f16,
+// bf16 x bf16 -> fp32, or kind::i8, int8 x int8 -> int32, accumulators in TMEM) against the image of the WHOLE query
+// batch (<= 64 queries, resident in shared memory for the kernel's lifetime; int8 queries as two terms, the second
+// the quantised residual of the first), and turns every (row, query) dot product into a LOWER BOUND of the exact
+// distance.  With q~, v~ the shadows, e_q = |q - q~|, e_v = |v - v~| (exact differences, norms rounded up):
 //     q.v - q~.v~ = (q - q~).v + q~.(v - v~)   =>   |q.v - q~.v~| <= e_q |v| + (|q| + e_q) e_v  (+ accumulation slack)
-// with e_q = |q - q~|, e_v = |v - v~| computed exactly (rounded up) when the shadow is written.  A pair whose lower
-// bound beats the query's running k-th distance -- after the first rows of a query almost none does -- is re-scored
-// EXACTLY from the fp32 row in the page with the arithmetic of scan_kernel (same per-lane FMA chain, same
-// 16-8-4-2-1 summation tree), so the distances that reach the pools, the partial results and the merge are bit
-// for bit those of the fp32 scan: the screen only decides which pairs are worth the exact arithmetic.
+// (Cauchy-Schwarz twice, |q~| <= |q| + e_q).  A pair whose lower bound beats the query's running k-th distance --
+// after the first rows of a query almost none does -- is re-scored EXACTLY from the fp32 row in the page with the
+// arithmetic of scan_kernel (same per-lane FMA chain, same 16-8-4-2-1 summation tree), so the distances that reach
+// the pools, the partial results and the merge are bit for bit those of the fp32 scan: the screen only decides
+// which pairs are worth the exact arithmetic.  tests/test_screen_bound.py checks the inequality on the CPU,
+// tests/test_scan_mirror.py the bit-identity on the GPU.
 //
 // Roles (192 threads, one CTA per SM, persistent over dynamically claimed items):
-//   warp 4, one thread   producer: claims items, announces row tiles (descriptor ring), streams the shadow tiles
-//                        of the item's pages through an S-stage ring of 16 KB (128 rows x 64 elements) stages
-//   warp 5, one thread   tcgen05.mma issuer + TMEM owner: per row tile ld/64 stages x 4 MMAs (M128 N64 K16) into
-//                        one of two 64-column accumulators; tcgen05.commit frees the stage / publishes the tile
+//   warp 4, one thread   producer: claims items, announces row tiles (descriptor ring; the tile's row constants are
+//                        bulk-copied into the descriptor's slot), streams the shadow tiles of the item's pages
+//                        through an S-stage ring of 16 KB (128 rows x 128 bytes) stages
+//   warp 5, one thread   tcgen05.mma issuer + TMEM owner: per row tile (row bytes / 128) stages x 4 MMAs (M128, N64
+//                        K16 bf16 / N128 K32 int8) into one of two accumulators; tcgen05.commit frees the stage /
+//                        publishes the tile
 //   warps 0-3            thread = row of the tile = TMEM lane.  Phase A: read the dot products of the queries
 //                        that probe this list (tcgen05.ld), evaluate the lower bound, ballot the admitted pairs
 //                        into shared memory, hand the accumulator back.  Phase B: warp w owns queries w, w+4, ...:

@@ -187,6 +187,7 @@ public:
         uint32_t shard_rank = 0, shard_count = 1;  // one process per GPU (this process holds shard_rank's lists)
         std::vector<int> devices;   // more than one entry: ONE process, one list shard per device
         uint32_t pipeline_depth = 0;  // searches in flight, 0 = 4
+        uint32_t scan_mirror = 0;     // low-precision shadow for the tensor-core screen: 0 auto, 1 off, 2 bf16, 3 int8
     };
     struct SearchParams {
         uint32_t nprobe = 10;
@@ -207,6 +208,7 @@ public:
         c.shard_rank = config.shard_rank;
         c.shard_count = config.shard_count;
         c.pipeline_depth = config.pipeline_depth;
+        c.scan_mirror = config.scan_mirror;
         if (config.devices.size() > 1) {
             std::vector<int32_t> devs(config.devices.begin(), config.devices.end());
             detail::check(vdb_index_create_sharded(&c, devs.data(), static_cast<int32_t>(devs.size()), &ix_),
