@@ -1522,7 +1522,10 @@ int32_t vdb_bruteforce_search(const float* database, const float* queries, const
         // concurrently running items within L2 (148 x 768 KB) while the tiles re-read them; widen only when the
         // partial-result buffer (nq x ranges x k entries) would get out of hand
         uint32_t ppi = 1;
-        while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (8ull << 30)) ppi *= 2;
+        while ((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 > (8ull << 30) && ppi < npages) ppi *= 2;
+        // (one range per query is the floor: beyond it widening no longer helps -- the round-1 loop never ended)
+        VDB_REQUIRE((uint64_t)nq * ((npages + ppi - 1) / ppi) * k * 12 <= (8ull << 30),
+                    "bruteforce: nq * k partial results exceed 8 GiB: split the query batch");
         const uint64_t slots = (uint64_t)nq * ((npages + ppi - 1) / ppi);
         VDB_TRY(scan_search(lt, q, nq, zero.p, 1, k, metric, ppi, slots, ws, false, dd, di, nullptr, s));
         return deliver();

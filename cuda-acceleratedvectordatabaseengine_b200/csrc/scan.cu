@@ -1495,7 +1495,8 @@ int32_t scan_plan(const ListTable& lt, const float* queries_dev, uint32_t nq, co
     pl.info = ScanLaunchInfo{QT, P, S, NJ, (uint32_t)grid, scan_smem_bytes(lt.ld, S, QT, P, stage_rows),
                              std::max(1u, std::min(64u, (P - k) / STAGE_ROWS))};
     pl.stage_rows = stage_rows;
-    // pages with a bf16 shadow: the tensor-core screen streams half the bytes (one batch of <= 64 queries per launch)
+    // pages with a low-precision shadow: the tensor-core screen streams a half / a quarter of the bytes (one batch of
+    // <= 64 queries per launch; wider batches and unsupported shapes keep the fp32 kernel)
     pl.mirror = lt.mirror_off != 0 && has_ids && nq <= (uint32_t)screen::NQ && screen_pool(k) <= screen::POOL_ENTRIES &&
                 screen_supported(lt.ld, lt.page_rows, metric);
     pl.info.mirror = pl.mirror ? 1u : 0u;
