@@ -549,11 +549,13 @@ def run_b200(a):
         r = reference_sample(a, steps=3, warmup=1, max_seconds=20.0)
         cpu = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     headline = (a.n, a.dim, a.metric, a.nlist, a.nprobe, a.k, a.batch) == (10_000_000, 768, "l2", 4096, 32, 10, 64)
-    launches_per_step = 5 + (1 if world > 1 else 0)
+    launches_per_step = 5 + (1 if mirror else 0) + (1 if world > 1 else 0)  # + query_image_kernel with a shadow
     line = {
         "metric": metric_name(a), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": ("f32" if not mirror else
+                  f"f32 ({'int8' if bpr_streamed == a.dim + 12 else 'bf16'} tensor-core screen, fp32 exact re-score of the admitted pairs)"),
+        "data": "synthetic",
         "config": {"workload": workload_name(a) + (f" [shard {a.emulate_rank} of {a.emulate_shards} only: tuning run]" if shard_count != world else ""),
                    "parallelism": f"lists sharded over {world} GPU(s), byte-balanced ownership, " +
                    ("single GPU: no exchange" if world == 1 else
@@ -563,8 +565,9 @@ def run_b200(a):
                                 f"overlap the scan of batch i ({scan_ctas} scan CTAs of 148 SMs)") if pipelined else "none",
                    "cache": f"inputs larger than L2: each batch streams {streamed_bytes / 1e9:.2f} GB of distinct list data" +
                             (f" (bf16 shadow of {uniq_bytes / 1e9:.2f} GB of fp32 rows)" if mirror else ""),
-                   "scan": ("bf16 tensor-core screen over the lists' bf16 shadow (tcgen05), exact fp32 re-score of the "
-                            "admitted pairs: results bit-identical to the fp32 scan") if mirror else "fp32 list scan",
+                   "scan": (f"tensor-core screen over the lists' {'int8' if bpr_streamed == a.dim + 12 else 'bf16'} shadow "
+                            "(tcgen05), exact fp32 re-score of the admitted pairs: results bit-identical to the fp32 scan")
+                           if mirror else "fp32 list scan",
                    "ntrain": min(a.ntrain, a.n), "page_rows": st.page_rows,
                    "build_s": round(t_build, 1), "train_s": round(t_train, 1), "add_s": round(t_add, 1),
                    "index_gb": round(st.gpu_memory_bytes / 1e9, 2),
@@ -594,8 +597,8 @@ def run_b200(a):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
                 "d2h_bytes_per_step": a.batch * a.k * 12},
-        # per step: score_gemm (tcgen05) + coarse_select + build_groups + scan + merge (+ collect, or merge of the
-        # all-gathered parts)
+        # per step: score_gemm (tcgen05) + coarse_select + (query_image) + build_groups + scan / screen + merge (+ collect,
+        # or merge of the all-gathered parts)
         "gpu_launches": a.steps * launches_per_step,
         "clocks": clocks,
     }
