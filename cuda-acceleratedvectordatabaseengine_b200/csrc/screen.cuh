@@ -225,20 +225,6 @@ __device__ __forceinline__ void tmem_ld8(const uint32_t (&t)[8], int (&v)[8]) {
         : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7])
         : "memory");
 }
-// non-blocking: has this phase of the barrier completed?
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
 
 // this lane's share of the exact q.v of one page row: the arithmetic of the inner-product branch of score_batch
