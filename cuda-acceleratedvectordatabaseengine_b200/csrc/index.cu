@@ -630,19 +630,35 @@ int32_t reserve_slots(vdb_index* ix) {
     return VDB_OK;
 }
 
-// the shapes one pass cannot take (partial-result buffer) are split over query chunks, each a pass of its own
+// the shapes one pass cannot (partial-result buffer) or should not (below) take are split over query chunks, each a
+// pass of its own; the chunks ride the search pipeline like separately submitted batches (`depth` in flight)
 int32_t search_chunked(vdb_index* ix, const float* queries, uint32_t nq, uint32_t nprobe, uint32_t k, float* distances,
                        uint64_t* indices, uint32_t nq_chunk) {
-    for (uint32_t lo = 0; lo < nq; lo += nq_chunk) {
+    int32_t st = VDB_OK;
+    for (uint32_t lo = 0; lo < nq && st == VDB_OK; lo += nq_chunk) {
         const uint32_t m = std::min(nq_chunk, nq - lo);
         SearchSlot* s = nullptr;
         uint64_t t = 0;
-        VDB_TRY(index_acquire_slot(ix, &s, &t));
-        VDB_TRY(index_enqueue_search(ix, *s, queries + (size_t)lo * ix->dim, m, nprobe, k, distances + (size_t)lo * k,
-                                     indices + (size_t)lo * k, index_pipeline_streams(ix, t), true));
-        VDB_TRY(index_finish_slot(ix, *s));
+        st = index_acquire_slot(ix, &s, &t);  // waits for (and delivers) the chunk that used this slot `depth` ago
+        if (st == VDB_OK)
+            st = index_enqueue_search(ix, *s, queries + (size_t)lo * ix->dim, m, nprobe, k, distances + (size_t)lo * k,
+                                      indices + (size_t)lo * k, index_pipeline_streams(ix, t), true);
     }
-    return VDB_OK;
+    for (uint32_t i = 0; i < ix->depth; ++i) {  // the chunks still in flight (also after an error: nothing may stay busy)
+        const int32_t fs = index_finish_slot(ix, ix->slots[i]);
+        if (st == VDB_OK) st = fs;
+    }
+    return st;
+}
+
+// An index with a shadow answers a batch wider than the screen kernel's 64 queries chunk by chunk: the
+// chunks stream the int8 / bf16 shadow and do their dot products on the tensor cores, where one wide pass would take
+// the fp32 kernel and be compute-bound (10 000 queries -- the reference's bench/benchmark.cpp -- are 157 chunks of
+// ~1.1 ms against tens of seconds of fp32 FMAs).  Same results either way.
+uint32_t screen_chunk(const vdb_index* ix, uint32_t nq, uint32_t k, uint32_t nq_chunk) {
+    if (ix->mirror_off && !ix->scan_exact && nq > screen_max_batch() && k <= screen_max_k())
+        return std::min(nq_chunk, screen_max_batch());
+    return nq_chunk;
 }
 
 int32_t check_search_args(vdb_index* ix, const void* q, const void* d, const void* i, uint32_t nq, uint32_t nprobe,
@@ -1016,6 +1032,7 @@ int32_t vdb_index_search_submit(vdb_index* ix, const float* queries, uint32_t nq
     DeviceGuard g(ix->device);
     uint32_t ppi = 1, nq_chunk = nq;
     choose_ppi(ix, nq, std::min(nprobe, ix->nlist), k, &ppi, &nq_chunk);
+    nq_chunk = screen_chunk(ix, nq, k, nq_chunk);
     if (nq_chunk < nq) {  // too large for one pass: done chunk by chunk right here, the ticket is already complete
         VDB_TRY(search_chunked(ix, queries, nq, nprobe, k, distances, indices, nq_chunk));
         *ticket = ix->next_ticket;

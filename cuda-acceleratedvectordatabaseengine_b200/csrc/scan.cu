@@ -1372,6 +1372,9 @@ uint32_t screen_pool(uint32_t k) { return next_pow2(std::max(2 * k, 32u)); }
 
 int32_t scan_max_k() { return (int32_t)MAX_K; }
 
+uint32_t screen_max_batch() { return (uint32_t)screen::NQ; }
+uint32_t screen_max_k() { return screen::POOL_ENTRIES / 2; }  // screen_pool(k) = pow2 >= 2k must fit the pool region
+
 bool screen_supported(uint32_t ld, uint32_t page_rows, int metric) {
     const bool width = ld == 128 || ld == 256 || ld == 512 || ld == 768 || ld == 1024;  // 32 * NJ float4, NJ in {1,2,4,6,8}
     return width && page_rows % MIRROR_TILE_ROWS == 0 && (metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP) &&

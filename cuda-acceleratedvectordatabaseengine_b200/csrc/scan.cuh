@@ -99,7 +99,10 @@ int32_t merge_parts(const float* dparts, const uint64_t* iparts, uint32_t parts,
                     float* out_d, uint64_t* out_i, cudaStream_t stream);
 
 int32_t scan_max_k();
-// can an index of this row stride / page size / metric keep a bf16 shadow for the tensor-core screen?
+// can an index of this row stride / page size / metric keep a low-precision shadow for the tensor-core screen?
 bool screen_supported(uint32_t ld, uint32_t page_rows, int metric);
+// the screen kernel takes batches of at most screen_max_batch() queries with k <= screen_max_k()
+uint32_t screen_max_batch();
+uint32_t screen_max_k();
 
 }  // namespace vdb

@@ -94,14 +94,14 @@ def test_mirror_scan_is_bit_identical_to_the_fp32_scan_and_matches_the_oracle(na
 
 
 @pytest.mark.parametrize("kind", [BF16, I8])
-def test_batches_wider_than_the_screen_fall_back_and_chunked_batches_agree(kind):
+def test_batches_wider_than_the_screen_are_chunked_and_agree(kind):
     dim, nlist, n = 128, 32, 30000
     x = O.gaussian(21, n + 200, dim)
     db, q = x[:n], x[n:]
     cent = db[:nlist].copy()
     a = build(dim, nlist, O.METRIC_L2, cent, db, mirror=kind)
     b = build(dim, nlist, O.METRIC_L2, cent, db, mirror=0)
-    Da, Ia = a.search(q, 8, 10)          # 200 queries: the fp32 scan kernel
+    Da, Ia = a.search(q, 8, 10)          # 200 queries: four pipelined chunks of <= 64 through the screen kernel
     Db, Ib = b.search(q, 8, 10)
     assert np.array_equal(Da, Db) and np.array_equal(Ia, Ib)
     for lo in range(0, 200, 64):         # 64 at a time: the screen kernel
